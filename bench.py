@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — chunks/s of the B200-native BirdNET v2.4 hot path (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one pass of the hot path over one batch of 3 s chunks:
+  N = 1 : BASELINE config[1] — soundscape.wav, 3 s window / 1.5 s overlap (79 chunks) tiled to batch = 256.
+  N > 1 : the same batch per GPU (weak scaling, independent chunks, no data-path collective); the only
+          collective is the NCCL all-gather of the per-chunk top-10 (80 B/chunk), inside the timed region.
+`value`  : chunks/s with the PCM already resident in HBM (device pointers through the C ABI).
+`e2e`    : chunks/s through the host-buffer C-ABI call (bnb_analyze_batch): pinned host float32 PCM -> H2D ->
+           kernels -> sigmoid/top-10 -> D2H, every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "birdnet-go_b200"))
+
+METRIC = "3s-chunks/sec"
+UNIT = "chunks/s"
+BATCH = 256
+N_SAMPLES = 144000
+N_SPECIES = 6522
+TOP_K = 10
+# SURVEY.md §8(d) / BASELINE.md §4: algorithmic work per chunk
+FLOP_PER_CHUNK = 2 * 328305984
+FLOP_PW_PER_CHUNK = 2 * 279244800            # the dense 1x1 ("pointwise") layers: expand + project (+ pool-mix 1x1 in stem)
+MIN_HBM_BYTES_PER_CHUNK = 576000 + 26088
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ workloads
+def read_wav_int16(path):
+    import struct
+    b = open(path, "rb").read()
+    p, fmt, data = 12, None, None
+    while p + 8 <= len(b):
+        cid, sz = b[p:p + 4], struct.unpack_from("<I", b, p + 4)[0]
+        if cid == b"fmt ":
+            fmt = struct.unpack_from("<HHIIHH", b, p + 8)
+        elif cid == b"data":
+            data = b[p + 8:p + 8 + sz]
+        p += 8 + sz + (sz & 1)
+    assert fmt[5] == 16 and fmt[1] == 1 and fmt[2] == 48000
+    return np.frombuffer(data, "<i2")
+
+
+def soundscape_batch(batch=BATCH):
+    """config[1]: window 144000 / step 72000 over soundscape.wav (79 chunks), tiled to `batch`; float32 = int16/32768
+    (internal/analysis/process.go:491-494)."""
+    pcm = read_wav_int16(os.path.join(REPO, "assets", "soundscape.wav"))
+    n = (len(pcm) - N_SAMPLES) // 72000 + 1
+    idx = np.arange(batch) % n
+    out = np.empty((batch, N_SAMPLES), np.float32)
+    for i, j in enumerate(idx):
+        out[i] = pcm[j * 72000:j * 72000 + N_SAMPLES].astype(np.float32) / np.float32(32768.0)
+    return out
+
+
+def synth_chunks(n, seed0=1234, fs=48000):
+    """config[2] generator: per chunk seed = seed0 + id; pink noise (RMS 0.05) + linear chirp
+    1->10 kHz at amplitude 0.2*U(0.1,1), clipped, quantised to int16, / 32768."""
+    out = np.empty((n, N_SAMPLES), np.float32)
+    t = np.arange(N_SAMPLES) / fs
+    f = np.fft.rfftfreq(N_SAMPLES, 1.0 / fs)
+    shape = np.zeros_like(f)
+    shape[1:] = 1.0 / np.sqrt(f[1:])
+    for i in range(n):
+        rng = np.random.default_rng(seed0 + i)
+        spec = (rng.standard_normal(len(f)) + 1j * rng.standard_normal(len(f))) * shape
+        pink = np.fft.irfft(spec, N_SAMPLES)
+        pink *= 0.05 / np.sqrt(np.mean(pink ** 2))
+        amp = 0.2 * rng.uniform(0.1, 1.0)
+        chirp = amp * np.sin(2 * np.pi * (1000.0 * t + 0.5 * (9000.0 / 3.0) * t * t))
+        x = np.clip(pink + chirp, -1.0, 1.0)
+        out[i] = np.round(x * 32767.0).astype(np.int16).astype(np.float32) / np.float32(32768.0)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(steps, warmup, sample_chunks=16):
+    """The reference's CPU implementation of the path, as restated by oracle/ (kind = "port": no Go toolchain,
+    no libtensorflowlite_c in this image — DESIGN.md).  float32 torch-CPU on all host threads; each step = a bounded
+    sample of `sample_chunks` chunks of the same soundscape workload."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import torch
+    import birdnet_oracle as bo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    o = bo.Oracle(dtype=torch.float32)
+    x = soundscape_batch(sample_chunks)
+    for _ in range(max(1, warmup)):
+        o.predict_batch(x[:4], batch=4)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.predict_batch(x, batch=sample_chunks)
+    dt = time.perf_counter() - t0
+    cps = steps * sample_chunks / dt
+    model = ""
+    try:
+        model = [ln.split(":", 1)[1].strip() for ln in open("/proc/cpuinfo") if ln.startswith("model name")][0]
+    except Exception:
+        pass
+    return cps, dt, {"value": cps, "unit": UNIT, "cores": cores, "kind": "port",
+                     "sample": "%d steps x %d soundscape chunks, torch-CPU fp32 restatement of the .tflite graph (oracle/), %s" % (steps, sample_chunks, model)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--precision", default="default", choices=["default", "f32", "f16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "soundscape.wav 3s window / 1.5s overlap (79 chunks) tiled to batch=%d per GPU, BirdNET v2.4 fp32 weights" % a.batch,
+              "batch_per_gpu": a.batch, "global_batch": a.batch * world, "l2": "device inputs rotate over 2 distinct 147 MB buffers (> 126 MB L2)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(a.steps, 8))
+        cps, dt, cb = cpu_reference_run(steps, min(a.warmup, 1))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 1),
+                          "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "soundscape.wav (reference repo) tiled", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": cps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import birdnet_b200 as bb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    prec = {"default": bb.PRECISION_DEFAULT, "f32": bb.PRECISION_F32, "f16x3": bb.PRECISION_F16X3}[a.precision]
+    clf = bb.B200Classifier(device=local, max_batch=a.batch, micro_batch=a.micro_batch, precision=prec)
+    B = a.batch
+    host = soundscape_batch(B)
+    if world > 1:
+        host = np.roll(host, rank * 7, axis=0)     # each rank analyses its own shard of the stream
+    # device-resident inputs: two distinct copies so consecutive steps never find their input in L2
+    d_in = [torch.from_numpy(host).cuda(), torch.from_numpy(host[::-1].copy()).cuda()]
+    d_logits = torch.empty((B, N_SPECIES), dtype=torch.float32, device="cuda")
+    d_idx = torch.empty((B, TOP_K), dtype=torch.int32, device="cuda")
+    d_conf = torch.empty((B, TOP_K), dtype=torch.float32, device="cuda")
+    g_idx = torch.empty((world * B, TOP_K), dtype=torch.int32, device="cuda") if world > 1 else None
+    g_conf = torch.empty((world * B, TOP_K), dtype=torch.float32, device="cuda") if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        clf.analyze_batch_device(d_in[i & 1].data_ptr(), bb.PCM_F32, B, 1.0, TOP_K, d_idx.data_ptr(), d_conf.data_ptr(), d_logits.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(g_idx, d_idx)
+            dist.all_gather_into_tensor(g_conf, d_conf)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, a.warmup)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = clf.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(a.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = clf.kernel_launches() - l0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    value = world * B * a.steps / (ms * 1e-3)
+
+    # per-kernel-category split inside the same kind of region (events around every launch)
+    clf.profile_begin()
+    for i in range(a.steps):
+        step(i)
+    prof = clf.profile_end()
+
+    # end-to-end through the host-buffer C-ABI call, pinned host memory, H2D + D2H inside the timed region
+    pin = [torch.from_numpy(host).pin_memory(), torch.from_numpy(host[::-1].copy()).pin_memory()]
+    idx_h = np.empty((B, TOP_K), np.int32); conf_h = np.empty((B, TOP_K), np.float32)
+    import ctypes as C
+
+    def e2e_step(i):
+        rc = clf._lib.bnb_analyze_batch(clf._h, C.c_void_p(pin[i & 1].data_ptr()), bb.PCM_F32, B, C.c_float(1.0), TOP_K,
+                                        idx_h.ctypes.data_as(C.c_void_p), conf_h.ctypes.data_as(C.c_void_p), None)
+        if rc != 0:
+            raise RuntimeError(bb.last_error())
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e_value = world * B * a.steps / e2e_s
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks, which = _peaks()
+        pw_ms = prof["pw_expand"][0] + prof["pw_project"][0]
+        pw_launches = prof["pw_expand"][1] + prof["pw_project"][1]
+        pw_flops = FLOP_PW_PER_CHUNK * B * a.steps - 2 * 7077888 * B * a.steps      # minus the pool-mix 1x1 (fused in the stem kernel)
+        tf = pw_flops / (pw_ms * 1e-3) / 1e12 if pw_ms > 0 else 0.0
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1373.2)))
+        total_ms = sum(v[0] for v in prof.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if clf.runtime_info()[2] == "FP32" else "f16x3(tcgen05 3-term split, f32 accumulate)+f32",
+            "data": "soundscape.wav (reference repo fixture) tiled; weights = reference BirdNET_GLOBAL_6K_V2.4_Model_FP32.tflite",
+            "config": config, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * N_SAMPLES * 4), "d2h_bytes_per_step": int(B * TOP_K * 8),
+                    "api": "bnb_analyze_batch(float32 PCM in pinned host memory) -> top-10 (idx, conf)"},
+            "roofline": {"bound": "tensor", "kernel": "pointwise 1x1 conv GEMMs (expand + project, %d launches/step)" % (pw_launches // max(1, a.steps)),
+                         "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+                         "peak_source": which + " bf16 dense (sustained)", "share_of_step": pw_ms / total_ms if total_ms else None},
+            "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items()},
+            "flop_roofline_frac": (value / world) * FLOP_PER_CHUNK / (peak_tf * 1e12),
+            "hbm_floor_frac": (value / world) * MIN_HBM_BYTES_PER_CHUNK / (float(peaks["hbm_gbs"]) * 1e9),
+            "precision": clf.runtime_info()[2],
+        }
+        if not a.no_cpu_baseline and world == 1:
+            _, _, cb = cpu_reference_run(3, 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,279 @@
+"""ctypes binding of libbirdnet_b200.so + the host-side mirror of the reference's classifier surface.
+
+`B200Classifier` mirrors `inference.Classifier` / `EmbeddingExtractor`
+(/root/reference/internal/inference/backend.go:8-29): `predict(samples) -> raw logits`,
+`num_species()`, `close()`.  `BirdNET` mirrors `BirdNET.Predict`
+(/root/reference/internal/classifier/analyze.go:25-110): sensitivity-sigmoid, label pairing,
+top-10.  Everything numeric happens in the CUDA library; this module never computes the model
+on the CPU and raises if the library cannot be loaded (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libbirdnet_b200.so")
+REPO = os.path.dirname(os.path.dirname(_HERE))
+DEFAULT_MODEL = os.path.join(REPO, "assets", "BirdNET_GLOBAL_6K_V2.4_Model_FP32.tflite")
+DEFAULT_LABELS = os.path.join(REPO, "assets", "BirdNET_GLOBAL_6K_V2.4_Labels_en_us.txt")
+
+PCM_F32, PCM_S16 = 0, 1
+PRECISION_DEFAULT, PRECISION_F32, PRECISION_F16X3 = 0, 1, 2
+OK = 0
+ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_UNSUPPORTED_MODEL, ERR_CUDA, ERR_CLOSED, ERR_OOM, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
+DEFAULT_TOP_K = 10   # internal/classifier/tracing.go:59
+
+
+class Options(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("max_batch", C.c_int32), ("micro_batch", C.c_int32),
+                ("precision", C.c_int32), ("use_graphs", C.c_int32), ("reserved", C.c_int32 * 9)]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("b200: status=%d: %s" % (status, msg))
+        self.status = status
+
+
+class B200Unavailable(B200Error):
+    """Mirror of ErrOpenVINOUnavailable (openvino/openvino.go:31): caller should fall back."""
+
+
+_lib = None
+
+# name -> (restype, argtypes): every symbol include/birdnet_b200.h declares
+SYMBOLS = {
+    "bnb_init": (C.c_int, []),
+    "bnb_device_count": (C.c_int, []),
+    "bnb_abi_version": (C.c_int, []),
+    "bnb_last_error": (C.c_char_p, []),
+    "bnb_classifier_create": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(Options), C.POINTER(C.c_void_p)]),
+    "bnb_classifier_destroy": (None, [C.c_void_p]),
+    "bnb_num_species": (C.c_int, [C.c_void_p]),
+    "bnb_num_samples": (C.c_int, [C.c_void_p]),
+    "bnb_embedding_dim": (C.c_int, [C.c_void_p]),
+    "bnb_max_batch": (C.c_int, [C.c_void_p]),
+    "bnb_runtime_device": (C.c_char_p, [C.c_void_p]),
+    "bnb_runtime_precision": (C.c_char_p, [C.c_void_p]),
+    "bnb_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bnb_predict_with_embeddings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "bnb_predict_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bnb_analyze_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnb_predict_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnb_analyze_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnb_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "bnb_last_device_ms": (C.c_float, [C.c_void_p]),
+    "bnb_profile_begin": (C.c_int, [C.c_void_p]),
+    "bnb_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "bnb_describe_model": (C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+    "bnb_debug_read_tensor": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "bnb_debug_keep_intermediates": (C.c_int, [C.c_void_p, C.c_int]),
+}
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the in-tree library (built by birdnet_b200.build).  Fails loudly if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise B200Unavailable(ERR_NO_DEVICE, "libbirdnet_b200.so not built (%s); run `python -m birdnet_b200.build`" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)           # AttributeError if the .so does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load_library().bnb_last_error().decode("utf-8", "replace")
+
+
+def _check(rc):
+    if rc < 0:
+        msg = last_error()
+        raise (B200Unavailable if rc == ERR_NO_DEVICE else B200Error)(rc, msg)
+    return rc
+
+
+def describe_model(model_bytes: bytes) -> str:
+    lib = load_library()
+    buf = C.create_string_buffer(1 << 16)
+    n = _check(lib.bnb_describe_model(model_bytes, len(model_bytes), buf, len(buf)))
+    return buf.raw[:n].decode()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class B200Classifier:
+    """inference.Classifier + EmbeddingExtractor backed by libbirdnet_b200 (NOT thread-safe: backend.go:7)."""
+
+    def __init__(self, model_data: bytes | None = None, device=-1, max_batch=256, micro_batch=0,
+                 precision=PRECISION_DEFAULT, use_graphs=0):
+        lib = load_library()
+        if model_data is None:
+            with open(DEFAULT_MODEL, "rb") as f:
+                model_data = f.read()
+        o = Options()
+        o.struct_size = C.sizeof(Options)
+        o.device, o.max_batch, o.micro_batch, o.precision, o.use_graphs = device, max_batch, micro_batch, precision, use_graphs
+        h = C.c_void_p()
+        _check(lib.bnb_classifier_create(model_data, len(model_data), C.byref(o), C.byref(h)))
+        self._lib, self._h = lib, h
+        self.n_species = lib.bnb_num_species(h)
+        self.n_samples = lib.bnb_num_samples(h)
+        self.emb_dim = lib.bnb_embedding_dim(h)
+        self.max_batch = lib.bnb_max_batch(h)
+
+    # --- inference.Classifier ---------------------------------------------------------------------
+    def predict(self, samples):
+        """Raw logits (pre-activation) for exactly `n_samples` float32 samples."""
+        if self._h is None:
+            raise B200Error(ERR_CLOSED, "classifier is closed")
+        x = np.ascontiguousarray(samples, np.float32).reshape(-1)
+        out = np.empty(self.n_species, np.float32)
+        _check(self._lib.bnb_predict(self._h, _ptr(x), x.size, _ptr(out)))
+        return out
+
+    def predict_with_embeddings(self, samples):
+        if self._h is None:
+            raise B200Error(ERR_CLOSED, "classifier is closed")
+        x = np.ascontiguousarray(samples, np.float32).reshape(-1)
+        out = np.empty(self.n_species, np.float32)
+        emb = np.empty(self.emb_dim, np.float32)
+        _check(self._lib.bnb_predict_with_embeddings(self._h, _ptr(x), x.size, _ptr(out), _ptr(emb)))
+        return out, emb
+
+    def num_species(self):
+        return self.n_species
+
+    def close(self):
+        if self._h is not None:
+            self._lib.bnb_classifier_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- batched surface ---------------------------------------------------------------------------
+    def _fmt(self, pcm):
+        if pcm.dtype == np.int16:
+            return PCM_S16
+        if pcm.dtype == np.float32:
+            return PCM_F32
+        raise TypeError("pcm must be float32 or int16")
+
+    def predict_batch(self, pcm, with_embeddings=False, out=None):
+        """pcm [B,144000] float32|int16 (host) -> logits [B,6522] (and embeddings [B,1024])."""
+        pcm = np.ascontiguousarray(pcm)
+        if pcm.ndim != 2 or pcm.shape[1] != self.n_samples:
+            raise B200Error(ERR_INVALID_ARGUMENT, "input size mismatch: expected [B,%d], got %s" % (self.n_samples, pcm.shape))
+        B = pcm.shape[0]
+        logits = out if out is not None else np.empty((B, self.n_species), np.float32)
+        emb = np.empty((B, self.emb_dim), np.float32) if with_embeddings else None
+        _check(self._lib.bnb_predict_batch(self._h, _ptr(pcm), self._fmt(pcm), B, _ptr(logits), _ptr(emb) if emb is not None else None))
+        return (logits, emb) if with_embeddings else logits
+
+    def analyze_batch(self, pcm, sensitivity=1.0, k=DEFAULT_TOP_K, want_logits=False):
+        pcm = np.ascontiguousarray(pcm)
+        B = pcm.shape[0]
+        idx = np.empty((B, k), np.int32)
+        conf = np.empty((B, k), np.float32)
+        logits = np.empty((B, self.n_species), np.float32) if want_logits else None
+        _check(self._lib.bnb_analyze_batch(self._h, _ptr(pcm), self._fmt(pcm), B, float(sensitivity), k, _ptr(idx), _ptr(conf),
+                                           _ptr(logits) if logits is not None else None))
+        return (idx, conf, logits) if want_logits else (idx, conf)
+
+    # raw-pointer variants (device memory owned by the caller, e.g. torch tensors' data_ptr())
+    def predict_batch_device(self, d_pcm, fmt, B, d_logits, d_emb=0, stream=0):
+        _check(self._lib.bnb_predict_batch_device(self._h, d_pcm, fmt, B, d_logits, d_emb or None, stream or None))
+
+    def analyze_batch_device(self, d_pcm, fmt, B, sensitivity, k, d_idx, d_conf, d_logits=0, stream=0):
+        _check(self._lib.bnb_analyze_batch_device(self._h, d_pcm, fmt, B, float(sensitivity), k, d_idx, d_conf, d_logits or None, stream or None))
+
+    # --- introspection -------------------------------------------------------------------------------
+    def kernel_launches(self):
+        return int(self._lib.bnb_kernel_launches(self._h))
+
+    def last_device_ms(self):
+        return float(self._lib.bnb_last_device_ms(self._h))
+
+    def runtime_info(self):
+        return (self._lib.bnb_runtime_device(self._h).decode(), "B200-native", self._lib.bnb_runtime_precision(self._h).decode())
+
+    PROFILE_CATEGORIES = ("minmax", "frontend", "stem_mix", "pw_expand", "depthwise", "se_gate", "pw_project", "post_conv",
+                          "row_mean", "fc_head", "topk")
+
+    def profile_begin(self):
+        _check(self._lib.bnb_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> {category: (ms, launches)} accumulated since profile_begin()."""
+        n = len(self.PROFILE_CATEGORIES)
+        ms = np.zeros(n, np.float32)
+        cnt = np.zeros(n, np.int64)
+        _check(self._lib.bnb_profile_end(self._h, _ptr(ms), _ptr(cnt), n))
+        return {c: (float(ms[i]), int(cnt[i])) for i, c in enumerate(self.PROFILE_CATEGORIES)}
+
+    def keep_intermediates(self, on=True):
+        _check(self._lib.bnb_debug_keep_intermediates(self._h, int(on)))
+
+    def read_tensor(self, tensor, max_elems=1 << 26):
+        buf = np.empty(max_elems, np.float32)
+        n = _check(self._lib.bnb_debug_read_tensor(self._h, tensor, _ptr(buf), buf.size))
+        return buf[:n].copy()
+
+
+class Result:
+    __slots__ = ("species", "confidence")
+
+    def __init__(self, species, confidence):
+        self.species, self.confidence = species, confidence
+
+    def __repr__(self):
+        return "Result(%r, %.4f)" % (self.species, self.confidence)
+
+
+class BirdNET:
+    """Mirror of classifier.BirdNET's Predict surface (analyze.go:25-110) on the B200 backend."""
+
+    def __init__(self, labels=None, sensitivity=1.0, **kw):
+        if labels is None:
+            with open(DEFAULT_LABELS, encoding="utf-8") as f:
+                labels = [ln.rstrip("\n") for ln in f if ln.strip()]
+        self.classifier = B200Classifier(**kw)
+        if len(labels) != self.classifier.num_species():     # validateModelAndLabels, birdnet.go:1248-1282
+            n = self.classifier.num_species()
+            self.classifier.close()
+            raise ValueError("mismatched labels and predictions lengths: %d vs %d" % (len(labels), n))
+        self.labels, self.sensitivity = labels, sensitivity
+
+    def predict(self, sample):
+        """sample: [[float32 x 144000]] like Predict(ctx, [][]float32); uses sample[0] (analyze.go:60)."""
+        if self.classifier is None:
+            raise RuntimeError("classifier backend is not initialized")
+        if len(sample) == 0 or len(sample[0]) == 0:
+            raise ValueError("empty audio sample")
+        x = np.ascontiguousarray(sample[0], np.float32)[None]
+        if x.shape[1] != self.classifier.n_samples:
+            raise B200Error(ERR_INVALID_ARGUMENT, "input size mismatch: expected %d samples, got %d" % (self.classifier.n_samples, x.shape[1]))
+        idx, conf = self.classifier.analyze_batch(x, self.sensitivity, DEFAULT_TOP_K)
+        return [Result(self.labels[i], float(c)) for i, c in zip(idx[0], conf[0])]
+
+    def predict_batch(self, chunks, k=DEFAULT_TOP_K):
+        idx, conf = self.classifier.analyze_batch(chunks, self.sensitivity, k)
+        return [[Result(self.labels[i], float(c)) for i, c in zip(ri, rc)] for ri, rc in zip(idx, conf)]
+
+    def close(self):
+        if self.classifier is not None:
+            self.classifier.close()
+            self.classifier = None

@@ -1,0 +1,83 @@
+"""Build libbirdnet_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m birdnet_b200.build [--force] [--verbose]
+
+The shared library links the static CUDA runtime only; it does not depend on torch.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)                       # birdnet-go_b200/
+CSRC = os.path.join(ROOT, "csrc")
+LIB = os.path.join(ROOT, "lib", "libbirdnet_b200.so")
+SOURCES = ["capi.cu", "engine.cu", "frontend.cu", "conv_f32.cu", "post.cu", "pw_tc.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _digest():
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(os.path.dirname(ROOT), "include")):
+        for fn in sorted(os.listdir(root)):
+            if fn.endswith((".cu", ".cuh", ".h")):
+                with open(os.path.join(root, fn), "rb") as f:
+                    h.update(fn.encode())
+                    h.update(f.read())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu (one object each, in parallel) and link the .so.  Returns its path."""
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    stamp = LIB + ".sha256"
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return LIB
+    nvcc = _nvcc()
+    objdir = os.path.join(ROOT, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+             "-DBNB_BUILDING"] + ARCH
+    if verbose:
+        flags += ["-Xptxas", "-v"]
+    procs = []
+    objs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        if not os.path.exists(src):
+            continue
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, "-c", src, "-o", obj] + flags
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    ok = True
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write("---- %s ----\n%s\n" % (s, out))
+        ok = ok and p.returncode == 0
+    if not ok:
+        raise RuntimeError("nvcc failed")
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ARCH + ["-Xcompiler", "-fPIC", "-cudart", "static"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,211 @@
+// capi.cu — the extern "C" surface declared in include/birdnet_b200.h.
+//
+// Error convention follows the reference's native backends: status int + thread-local message
+// (/root/reference/internal/inference/openvino/backend_openvino.go:462-470), never abort.
+#include <mutex>
+#include <new>
+
+#include "engine.h"
+
+using namespace bnb;
+
+struct bnb_classifier {
+  Engine* eng = nullptr;
+  bool closed = false;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+std::mutex g_init_mu;
+bool g_inited = false;
+int g_devices = 0;
+
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return BNB_OK;
+  } catch (const unsupported_model& e) { return fail(BNB_ERR_UNSUPPORTED_MODEL, e.what());
+  } catch (const cuda_error& e) {
+    cudaGetLastError();
+    return fail(e.code == cudaErrorMemoryAllocation ? BNB_ERR_OUT_OF_MEMORY : BNB_ERR_CUDA, e.what());
+  } catch (const std::invalid_argument& e) { return fail(BNB_ERR_INVALID_ARGUMENT, e.what());
+  } catch (const std::bad_alloc&) { return fail(BNB_ERR_OUT_OF_MEMORY, "host allocation failed");
+  } catch (const std::exception& e) { return fail(BNB_ERR_INTERNAL, e.what());
+  } catch (...) { return fail(BNB_ERR_INTERNAL, "unknown exception"); }
+}
+
+int check_handle(const bnb_classifier* h) {
+  if (!h) return fail(BNB_ERR_INVALID_ARGUMENT, "classifier handle is NULL");
+  if (h->closed || !h->eng) return fail(BNB_ERR_CLOSED, "classifier is closed");
+  return BNB_OK;
+}
+
+int check_batch(const bnb_classifier* h, const void* pcm, int format, int B) {
+  if (int rc = check_handle(h)) return rc;
+  if (!pcm) return fail(BNB_ERR_INVALID_ARGUMENT, "pcm pointer is NULL");
+  if (format != BNB_PCM_F32 && format != BNB_PCM_S16) return fail(BNB_ERR_INVALID_ARGUMENT, "unknown pcm format");
+  if (B < 0) return fail(BNB_ERR_INVALID_ARGUMENT, "negative batch size");
+  return BNB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bnb_abi_version(void) { return BNB_ABI_VERSION; }
+
+const char* bnb_last_error(void) { return g_last_error.c_str(); }
+
+int bnb_init(void) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (g_inited) return BNB_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(BNB_ERR_NO_DEVICE, std::string("b200: no CUDA device: ") + cudaGetErrorString(e)); }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p{};
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  if (ok == 0) return fail(BNB_ERR_NO_DEVICE, "b200: no compute-capability 10.x (Blackwell) device present");
+  g_devices = ok; g_inited = true;
+  return BNB_OK;
+}
+
+int bnb_device_count(void) {
+  int rc = bnb_init();
+  return rc == BNB_OK ? g_devices : rc;
+}
+
+int bnb_classifier_create(const void* tflite, size_t tflite_len, const bnb_options* opts, bnb_classifier** out) {
+  if (!out) return fail(BNB_ERR_INVALID_ARGUMENT, "out pointer is NULL");
+  *out = nullptr;
+  if (!tflite || tflite_len == 0) return fail(BNB_ERR_INVALID_ARGUMENT, "cannot create model from data (0 bytes)");
+  bnb_options o{};
+  o.device = -1;
+  if (opts) {
+    if (opts->struct_size != 0 && opts->struct_size > sizeof(bnb_options)) return fail(BNB_ERR_INVALID_ARGUMENT, "bnb_options.struct_size is larger than this library knows");
+    memcpy(&o, opts, opts->struct_size ? opts->struct_size : sizeof(bnb_options));
+  }
+  // model structure problems are reported before any device is touched
+  int rc = guarded([&] { TfModel m = parse_tflite(tflite, tflite_len); (void)build_plan(m); });
+  if (rc == BNB_ERR_INTERNAL) return fail(BNB_ERR_UNSUPPORTED_MODEL, g_last_error);
+  if (rc != BNB_OK) return rc;
+  if ((rc = bnb_init()) != BNB_OK) return rc;
+  bnb_classifier* h = new (std::nothrow) bnb_classifier();
+  if (!h) return fail(BNB_ERR_OUT_OF_MEMORY, "host allocation failed");
+  rc = guarded([&] { h->eng = new Engine(tflite, tflite_len, o); });
+  if (rc != BNB_OK) { delete h; return rc; }
+  *out = h;
+  return BNB_OK;
+}
+
+void bnb_classifier_destroy(bnb_classifier* h) {
+  if (!h) return;
+  try { delete h->eng; } catch (...) {}
+  h->eng = nullptr; h->closed = true;
+  delete h;
+}
+
+int bnb_num_species(const bnb_classifier* h) { if (int rc = check_handle(h)) return rc; return h->eng->n_species(); }
+int bnb_num_samples(const bnb_classifier* h) { if (int rc = check_handle(h)) return rc; return h->eng->n_samples(); }
+int bnb_embedding_dim(const bnb_classifier* h) { if (int rc = check_handle(h)) return rc; return h->eng->emb_dim(); }
+int bnb_max_batch(const bnb_classifier* h) { if (int rc = check_handle(h)) return rc; return h->eng->max_batch(); }
+const char* bnb_runtime_device(const bnb_classifier* h) { return check_handle(h) ? "" : h->eng->device_name(); }
+const char* bnb_runtime_precision(const bnb_classifier* h) { return check_handle(h) ? "" : h->eng->precision_name(); }
+
+int bnb_predict(bnb_classifier* h, const float* samples, size_t n_samples, float* logits) {
+  return bnb_predict_with_embeddings(h, samples, n_samples, logits, nullptr);
+}
+
+int bnb_predict_with_embeddings(bnb_classifier* h, const float* samples, size_t n_samples, float* logits, float* embeddings) {
+  if (int rc = check_handle(h)) return rc;
+  if (!samples || !logits) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL samples/logits pointer");
+  if (n_samples != (size_t)h->eng->n_samples())
+    return fail(BNB_ERR_INVALID_ARGUMENT, "input size mismatch: expected " + std::to_string(h->eng->n_samples()) + " samples, got " + std::to_string(n_samples));
+  return guarded([&] { h->eng->predict_host(samples, BNB_PCM_F32, 1, logits, embeddings); });
+}
+
+int bnb_predict_batch(bnb_classifier* h, const void* pcm, int format, int B, float* logits, float* embeddings) {
+  if (int rc = check_batch(h, pcm, format, B)) return rc;
+  if (!logits) return fail(BNB_ERR_INVALID_ARGUMENT, "logits pointer is NULL");
+  if (B > h->eng->max_batch()) return fail(BNB_ERR_INVALID_ARGUMENT, "batch exceeds max_batch");
+  if (B == 0) return BNB_OK;
+  return guarded([&] { h->eng->predict_host(pcm, format, B, logits, embeddings); });
+}
+
+int bnb_analyze_batch(bnb_classifier* h, const void* pcm, int format, int B, float sensitivity, int k, int32_t* idx, float* conf,
+                      float* logits_or_null) {
+  if (int rc = check_batch(h, pcm, format, B)) return rc;
+  if (!idx || !conf || k <= 0) return fail(BNB_ERR_INVALID_ARGUMENT, "idx/conf NULL or k <= 0");
+  if (B > h->eng->max_batch()) return fail(BNB_ERR_INVALID_ARGUMENT, "batch exceeds max_batch");
+  if (B == 0) return BNB_OK;
+  return guarded([&] { h->eng->analyze_host(pcm, format, B, sensitivity, k, idx, conf, logits_or_null); });
+}
+
+int bnb_predict_batch_device(bnb_classifier* h, const void* d_pcm, int format, int B, float* d_logits, float* d_embeddings, void* stream) {
+  if (int rc = check_batch(h, d_pcm, format, B)) return rc;
+  if (!d_logits) return fail(BNB_ERR_INVALID_ARGUMENT, "logits pointer is NULL");
+  if (B == 0) return BNB_OK;
+  return guarded([&] { h->eng->predict_device(d_pcm, format, B, d_logits, d_embeddings, static_cast<cudaStream_t>(stream)); });
+}
+
+int bnb_analyze_batch_device(bnb_classifier* h, const void* d_pcm, int format, int B, float sensitivity, int k, int32_t* d_idx,
+                             float* d_conf, float* d_logits_or_null, void* stream) {
+  if (int rc = check_batch(h, d_pcm, format, B)) return rc;
+  if (!d_idx || !d_conf || k <= 0) return fail(BNB_ERR_INVALID_ARGUMENT, "idx/conf NULL or k <= 0");
+  if (!d_logits_or_null && B > h->eng->max_batch()) return fail(BNB_ERR_INVALID_ARGUMENT, "batch exceeds max_batch (pass a logits buffer for larger batches)");
+  if (B == 0) return BNB_OK;
+  return guarded([&] { h->eng->analyze_device(d_pcm, format, B, sensitivity, k, d_idx, d_conf, d_logits_or_null, static_cast<cudaStream_t>(stream)); });
+}
+
+int64_t bnb_kernel_launches(const bnb_classifier* h) { if (int rc = check_handle(h)) return rc; return h->eng->launches(); }
+float bnb_last_device_ms(const bnb_classifier* h) { return check_handle(h) ? -1.f : h->eng->last_device_ms(); }
+
+int bnb_profile_begin(bnb_classifier* h) {
+  if (int rc = check_handle(h)) return rc;
+  h->eng->profile_begin();
+  return BNB_OK;
+}
+
+int bnb_profile_end(bnb_classifier* h, float* ms, int64_t* launches, int cap) {
+  if (int rc = check_handle(h)) return rc;
+  if (!ms || !launches || cap <= 0) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL ms/launches or cap <= 0");
+  int n = 0;
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  int rc = guarded([&] { n = h->eng->profile_end(ms, reinterpret_cast<long long*>(launches), cap); });
+  return rc != BNB_OK ? rc : n;
+}
+
+int bnb_describe_model(const void* tflite, size_t tflite_len, char* json, size_t cap) {
+  if (!tflite || !json) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL pointer");
+  std::string s;
+  int rc = guarded([&] { TfModel m = parse_tflite(tflite, tflite_len); s = describe_plan(build_plan(m)); });
+  if (rc == BNB_ERR_INTERNAL) return fail(BNB_ERR_UNSUPPORTED_MODEL, g_last_error);
+  if (rc != BNB_OK) return rc;
+  if (s.size() + 1 > cap) return fail(BNB_ERR_INVALID_ARGUMENT, "json buffer too small");
+  memcpy(json, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
+int64_t bnb_debug_read_tensor(bnb_classifier* h, int tensor, float* out, size_t cap) {
+  if (int rc = check_handle(h)) return rc;
+  if (!out) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL out pointer");
+  long long n = 0;
+  int rc = guarded([&] { n = h->eng->read_tensor(tensor, out, cap); });
+  if (rc != BNB_OK) return rc;
+  if (n < 0) return fail((int)n, "tensor not materialised by the last call (or buffer too small)");
+  return n;
+}
+
+int bnb_debug_keep_intermediates(bnb_classifier* h, int on) {
+  if (int rc = check_handle(h)) return rc;
+  h->eng->keep_intermediates(on != 0);
+  return BNB_OK;
+}
+
+}  // extern "C"

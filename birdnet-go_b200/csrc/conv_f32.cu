@@ -1,0 +1,334 @@
+// conv_f32.cu — fp32 CUDA-core kernels of the BirdNET v2.4 conv stack (ops 95-375 of the .tflite
+// the reference executes through /root/reference/internal/inference/tflite/classifier.go:107).
+//
+// These are (a) the truth path (BNB_PRECISION_F32) and (b) the kernels for every layer that is
+// not a dense pointwise GEMM: stem 4x8/s2 conv fused with the avg/max pool + concat + 1x1 mix,
+// 3x3 depthwise (+SiLU), squeeze-excite gate, global mean.  The dense 1x1 layers have a tcgen05
+// implementation in pw_tc.cu; launch_pw_conv here is their fp32 reference and the fallback for
+// shapes the tensor-core kernel does not take.
+#include "kernels.h"
+
+namespace bnb {
+
+namespace {
+
+// =================================================================================================
+// stem conv 4x8 stride 2 (SAME: pad top 1 / left 3) + ReLU  ->  {max,avg} pool 1x2 -> concat -> 1x1
+// One CTA = one stem output row (256 positions = 128 pooled positions); one thread = one pooled
+// position = two adjacent stem positions x 24 channels.
+// Input rows 2h-1 .. 2h+2 are staged in smem de-interleaved by (column mod 4) so that the
+// stride-4-column accesses of adjacent threads hit consecutive float2 words (no bank conflicts).
+// =================================================================================================
+constexpr int kStemCo = 24, kStemKh = 4, kStemKw = 8;
+constexpr int kStemThreads = 128;
+constexpr int kStemCols = 4 * kStemThreads + 8;       // padded input columns covered: [-3, 4*128+4]
+constexpr int kStemQ = kStemCols / 4;                 // 130 column quads
+
+__global__ void __launch_bounds__(kStemThreads)
+stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restrict__ stem_out, float* __restrict__ out) {
+  __shared__ __align__(16) float s_in[kStemKh][4][kStemQ][2];          // [row][col%4][col/4][ci]
+  __shared__ __align__(16) float s_w[kStemKh * kStemKw * 2 * kStemCo];  // [kh][kw][ci][co]
+  __shared__ __align__(16) float s_wm[kStemCo * 2 * kStemCo];           // [co][48]
+  __shared__ float s_b[kStemCo], s_bm[kStemCo];
+  const int tid = threadIdx.x, h = blockIdx.x, b = blockIdx.y;
+  for (int i = tid; i < kStemKh * kStemKw * 2 * kStemCo; i += kStemThreads) s_w[i] = __ldg(p.w_stem + i);
+  for (int i = tid; i < kStemCo * 2 * kStemCo; i += kStemThreads) s_wm[i] = __ldg(p.w_mix + i);
+  if (tid < kStemCo) { s_b[tid] = __ldg(p.b_stem + tid); s_bm[tid] = __ldg(p.b_mix + tid); }
+  // stage input rows; padded column index pc = col + pad_l  (pc in [0, kStemCols))
+  const float* inb = in + (size_t)b * p.in_h * p.in_w * 2;
+  for (int i = tid; i < kStemKh * kStemCols; i += kStemThreads) {
+    const int r = i / kStemCols, pc = i - r * kStemCols;
+    const int row = 2 * h - p.pad_t + r, col = pc - p.pad_l;
+    float2 v = make_float2(0.f, 0.f);
+    if (row >= 0 && row < p.in_h && col >= 0 && col < p.in_w) v = __ldg(reinterpret_cast<const float2*>(inb + ((size_t)row * p.in_w + col) * 2));
+    *reinterpret_cast<float2*>(&s_in[r][pc & 3][pc >> 2][0]) = v;
+  }
+  __syncthreads();
+
+  float acc0[kStemCo], acc1[kStemCo];
+#pragma unroll
+  for (int c = 0; c < kStemCo; ++c) { acc0[c] = s_b[c]; acc1[c] = s_b[c]; }
+  // stem position w0 = 2*tid reads padded cols 4*tid + kw ; w1 = 2*tid+1 reads 4*tid + 2 + kw
+#pragma unroll
+  for (int kh = 0; kh < kStemKh; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < kStemKw; ++kw) {
+      const int pc0 = kw, pc1 = kw + 2;   // + 4*tid
+      const float2 x0 = *reinterpret_cast<const float2*>(&s_in[kh][pc0 & 3][tid + (pc0 >> 2)][0]);
+      const float2 x1 = *reinterpret_cast<const float2*>(&s_in[kh][pc1 & 3][tid + (pc1 >> 2)][0]);
+      const float* w = s_w + ((kh * kStemKw + kw) * 2) * kStemCo;
+#pragma unroll
+      for (int c4 = 0; c4 < kStemCo / 4; ++c4) {
+        const float4 wa = *reinterpret_cast<const float4*>(w + 4 * c4);
+        const float4 wb = *reinterpret_cast<const float4*>(w + kStemCo + 4 * c4);
+        acc0[4 * c4 + 0] = fmaf(x0.x, wa.x, acc0[4 * c4 + 0]); acc0[4 * c4 + 1] = fmaf(x0.x, wa.y, acc0[4 * c4 + 1]);
+        acc0[4 * c4 + 2] = fmaf(x0.x, wa.z, acc0[4 * c4 + 2]); acc0[4 * c4 + 3] = fmaf(x0.x, wa.w, acc0[4 * c4 + 3]);
+        acc1[4 * c4 + 0] = fmaf(x1.x, wa.x, acc1[4 * c4 + 0]); acc1[4 * c4 + 1] = fmaf(x1.x, wa.y, acc1[4 * c4 + 1]);
+        acc1[4 * c4 + 2] = fmaf(x1.x, wa.z, acc1[4 * c4 + 2]); acc1[4 * c4 + 3] = fmaf(x1.x, wa.w, acc1[4 * c4 + 3]);
+        acc0[4 * c4 + 0] = fmaf(x0.y, wb.x, acc0[4 * c4 + 0]); acc0[4 * c4 + 1] = fmaf(x0.y, wb.y, acc0[4 * c4 + 1]);
+        acc0[4 * c4 + 2] = fmaf(x0.y, wb.z, acc0[4 * c4 + 2]); acc0[4 * c4 + 3] = fmaf(x0.y, wb.w, acc0[4 * c4 + 3]);
+        acc1[4 * c4 + 0] = fmaf(x1.y, wb.x, acc1[4 * c4 + 0]); acc1[4 * c4 + 1] = fmaf(x1.y, wb.y, acc1[4 * c4 + 1]);
+        acc1[4 * c4 + 2] = fmaf(x1.y, wb.z, acc1[4 * c4 + 2]); acc1[4 * c4 + 3] = fmaf(x1.y, wb.w, acc1[4 * c4 + 3]);
+      }
+    }
+  }
+  // ReLU, optional dump of the stem tensor, then pool
+  float pool[2 * kStemCo];   // [max(24) | avg(24)]
+#pragma unroll
+  for (int c = 0; c < kStemCo; ++c) {
+    const float a = fmaxf(acc0[c], 0.f), d = fmaxf(acc1[c], 0.f);
+    acc0[c] = a; acc1[c] = d;
+    pool[c] = fmaxf(a, d);
+    pool[kStemCo + c] = (a + d) * 0.5f;
+  }
+  if (stem_out != nullptr) {
+    float* so = stem_out + (((size_t)b * p.out_h + h) * p.out_w + 2 * tid) * kStemCo;
+#pragma unroll
+    for (int c = 0; c < kStemCo; ++c) { so[c] = acc0[c]; so[kStemCo + c] = acc1[c]; }
+  }
+  // 1x1 mix 48 -> 24
+  float* o = out + (((size_t)b * p.out_h + h) * (p.out_w / 2) + tid) * kStemCo;
+#pragma unroll
+  for (int co4 = 0; co4 < kStemCo / 4; ++co4) {
+    float r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int co = 4 * co4 + q;
+      float a = s_bm[co];
+      const float* w = s_wm + co * 2 * kStemCo;
+#pragma unroll
+      for (int c4 = 0; c4 < 2 * kStemCo / 4; ++c4) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + 4 * c4);
+        a = fmaf(pool[4 * c4 + 0], wv.x, a); a = fmaf(pool[4 * c4 + 1], wv.y, a);
+        a = fmaf(pool[4 * c4 + 2], wv.z, a); a = fmaf(pool[4 * c4 + 3], wv.w, a);
+      }
+      r[q] = a;
+    }
+    *reinterpret_cast<float4*>(o + 4 * co4) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// =================================================================================================
+// Generic pointwise GEMM  C[M,N] = act( f(A)[M,K] * W[N,K]^T + bias ) (+ residual)
+//   f = optional per-chunk SE gate on k, or per-channel affine+ReLU (post block), and an implicit
+//   im2col row addressing for the final KxK VALID conv.
+// 64x64 tile, BK = 16, 256 threads, 4x4 outputs per thread, operands staged k-major in smem.
+// =================================================================================================
+constexpr int kBM = 64, kBN = 64, kBK = 16;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_SILU: return silu_f(v);
+    case ACT_SIGMOID: return sigmoid_f(v);
+    default: return v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pw_conv_kernel(const PwArgs a) {
+  __shared__ __align__(16) float As[kBK][kBM + 4];
+  __shared__ __align__(16) float Ws[kBK][kBN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+  const int tx = tid & 15, ty = tid >> 4;     // thread computes rows ty*4..+3, cols tx*4..+3
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // loader mapping: each thread loads one float4 (4 consecutive k) of one row of A and of W per k-tile
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int am = m0 + lr, wn = n0 + lr;
+  const float* arow = nullptr;
+  const float* grow = nullptr;
+  int a_seg = 0, a_seg_stride = 0;     // im2col: k = seg*a_seg + j  ->  base + seg*a_seg_stride + j
+  if (am < a.M) {
+    if (a.a_mode == A_PLAIN) arow = a.A + (size_t)am * a.K;
+    else {
+      const int bidx = am / a.out_w, wo = am - bidx * a.out_w;
+      // input map [kh rows][in_w][cin]; output (0, wo): k = (kh, kw, ci) ; row kh contributes kw*cin contiguous floats
+      a_seg = a.kw * a.cin; a_seg_stride = a.in_w * a.cin;
+      arow = a.A + ((size_t)bidx * (a.K / a_seg) * a.in_w + wo) * a.cin;
+    }
+    if (a.gate) grow = a.gate + (size_t)(am / a.rows_per_chunk) * a.K;
+  }
+  const float* wrow = (wn < a.N) ? a.W + (size_t)wn * a.K : nullptr;
+
+  for (int k0 = 0; k0 < a.K; k0 += kBK) {
+    const int k = k0 + lk;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (arow && k < a.K) {
+      if (a.a_mode == A_PLAIN) av = __ldg(reinterpret_cast<const float4*>(arow + k));
+      else { const int seg = k / a_seg, j = k - seg * a_seg; av = __ldg(reinterpret_cast<const float4*>(arow + (size_t)seg * a_seg_stride + j)); }
+      if (grow) { const float4 g = __ldg(reinterpret_cast<const float4*>(grow + k)); av.x *= g.x; av.y *= g.y; av.z *= g.z; av.w *= g.w; }
+      if (a.a_mul) {
+        const int c = k % a.a_ch;
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(a.a_mul + c)), ad = __ldg(reinterpret_cast<const float4*>(a.a_add + c));
+        av.x = fmaxf(av.x * mu.x + ad.x, 0.f); av.y = fmaxf(av.y * mu.y + ad.y, 0.f);
+        av.z = fmaxf(av.z * mu.z + ad.z, 0.f); av.w = fmaxf(av.w * mu.w + ad.w, 0.f);
+      }
+    }
+    if (wrow && k < a.K) wv = __ldg(reinterpret_cast<const float4*>(wrow + k));
+    As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
+    Ws[lk + 0][lr] = wv.x; Ws[lk + 1][lr] = wv.y; Ws[lk + 2][lr] = wv.z; Ws[lk + 3][lr] = wv.w;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      const float4 af = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 wf = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float ar[4] = {af.x, af.y, af.z, af.w}, wr[4] = {wf.x, wf.y, wf.z, wf.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // epilogue
+  const int n = n0 + tx * 4;
+  if (n < a.N) {   // N is a multiple of 4 except the FC head (6522 = 4*1630 + 2): handled per element
+    float bs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bs[j] = (a.bias && n + j < a.N) ? __ldg(a.bias + n + j) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m >= a.M) continue;
+      float* c = a.C + (size_t)m * a.N + n;
+      const float* r = a.residual ? a.residual + (size_t)m * a.N + n : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n + j < a.N) {
+          float v = apply_act(acc[i][j] + bs[j], a.act);
+          if (r) v += __ldg(r + j);
+          c[j] = v;
+        }
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// 3x3 depthwise conv + bias + SiLU, NHWC, zero padding 1 on each side (stride 1 SAME, or the
+// reference's explicit PAD(1,1) + VALID stride 2).  One thread = 4 channels of one output pixel.
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+dw_conv_kernel(const DwArgs a) {
+  const int c4n = a.C / 4;
+  const long long total = (long long)a.B * a.Ho * a.Wo * c4n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % c4n);
+    long long r = idx / c4n;
+    const int wo = (int)(r % a.Wo); r /= a.Wo;
+    const int ho = (int)(r % a.Ho);
+    const int b = (int)(r / a.Ho);
+    const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias) + c4);
+    float4 acc = bz;
+    const float* inb = a.in + (size_t)b * a.H * a.W * a.C;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = ho * a.stride - 1 + kh;
+      if (hi < 0 || hi >= a.H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wo * a.stride - 1 + kw;
+        if (wi < 0 || wi >= a.W) continue;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)hi * a.W + wi) * a.C) + c4);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.w + (kh * 3 + kw) * a.C) + c4);
+        acc.x = fmaf(x.x, w.x, acc.x); acc.y = fmaf(x.y, w.y, acc.y); acc.z = fmaf(x.z, w.z, acc.z); acc.w = fmaf(x.w, w.w, acc.w);
+      }
+    }
+    acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w);
+    reinterpret_cast<float4*>(a.out)[idx] = acc;
+  }
+}
+
+// =================================================================================================
+// Squeeze-excite gate: gate[b][c] = sigmoid(W2 * silu(W1 * mean_hw(x[b]) + b1) + b2).  One CTA per chunk.
+// =================================================================================================
+constexpr int kSeThreads = 512;
+constexpr int kSeMaxC = 1536, kSeMaxS = 64;
+
+__global__ void __launch_bounds__(kSeThreads)
+se_gate_kernel(const SeArgs a) {
+  __shared__ float s_mean[kSeMaxC];
+  __shared__ float s_hidden[kSeMaxS];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* x = a.x + (size_t)b * a.HW * a.C;
+  // channel sums: consecutive threads -> consecutive channels (coalesced rows)
+  for (int c = tid; c < a.C; c += kSeThreads) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 4 <= a.HW; p += 4) {
+      s0 += __ldg(x + (size_t)(p + 0) * a.C + c); s1 += __ldg(x + (size_t)(p + 1) * a.C + c);
+      s2 += __ldg(x + (size_t)(p + 2) * a.C + c); s3 += __ldg(x + (size_t)(p + 3) * a.C + c);
+    }
+    for (; p < a.HW; ++p) s0 += __ldg(x + (size_t)p * a.C + c);
+    s_mean[c] = ((s0 + s1) + (s2 + s3)) / (float)a.HW;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int j = warp; j < a.Cse; j += kSeThreads / 32) {
+    const float* w = a.w1 + (size_t)j * a.C;
+    float s = 0.f;
+    for (int c = lane; c < a.C; c += 32) s = fmaf(s_mean[c], __ldg(w + c), s);
+    s = warp_sum(s);
+    if (lane == 0) s_hidden[j] = silu_f(s + __ldg(a.b1 + j));
+  }
+  __syncthreads();
+  for (int c = tid; c < a.C; c += kSeThreads) {
+    const float* w = a.w2 + (size_t)c * a.Cse;
+    float s = __ldg(a.b2 + c);
+    for (int j = 0; j < a.Cse; ++j) s = fmaf(s_hidden[j], __ldg(w + j), s);
+    a.gate[(size_t)b * a.C + c] = sigmoid_f(s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+row_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int rows, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * C) return;
+  const int b = idx / C, c = idx - b * C;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += __ldg(in + ((size_t)b * rows + r) * C + c);
+  out[idx] = s / (float)rows;
+}
+
+}  // namespace
+
+void launch_stem_mix(const StemMixDev& p, const float* in, float* stem_out_or_null, float* out, int B,
+                     cudaStream_t s, LaunchCounter& lc) {
+  dim3 grid(p.out_h, B);
+  stem_mix_kernel<<<grid, kStemThreads, 0, s>>>(p, in, stem_out_or_null, out);
+  BNB_LAUNCH_CHECK(lc);
+}
+
+void launch_pw_conv(const PwArgs& a, cudaStream_t s, LaunchCounter& lc) {
+  dim3 grid(ceil_div(a.M, kBM), ceil_div(a.N, kBN));
+  pw_conv_kernel<<<grid, 256, 0, s>>>(a);
+  BNB_LAUNCH_CHECK(lc);
+}
+
+void launch_dw_conv(const DwArgs& a, cudaStream_t s, LaunchCounter& lc) {
+  const long long total = (long long)a.B * a.Ho * a.Wo * (a.C / 4);
+  long long blocks = ceil_div_ll(total, 256);
+  const long long cap = (long long)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  dw_conv_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+  BNB_LAUNCH_CHECK(lc);
+}
+
+void launch_se_gate(const SeArgs& a, cudaStream_t s, LaunchCounter& lc) {
+  if (a.C > kSeMaxC || a.Cse > kSeMaxS) throw std::runtime_error("se_gate: channel count exceeds kernel limits");
+  se_gate_kernel<<<a.B, kSeThreads, 0, s>>>(a);
+  BNB_LAUNCH_CHECK(lc);
+}
+
+void launch_row_mean(const float* in, float* out, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc) {
+  row_mean_kernel<<<ceil_div(B * C, 256), 256, 0, s>>>(in, out, B, rows, C);
+  BNB_LAUNCH_CHECK(lc);
+}
+
+}  // namespace bnb

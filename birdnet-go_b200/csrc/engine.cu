@@ -1,0 +1,412 @@
+// engine.cu — weight upload, workspaces and the per-micro-batch kernel chain.
+//
+// Execution model: a batch of B independent 3 s chunks is cut into micro-batches of `micro_`
+// chunks; one micro-batch runs the whole kernel chain before the next starts, so every
+// producer->consumer activation pair (<= 2.4 MB per chunk) stays resident in the 126 MB L2 and HBM
+// sees little more than the PCM in and the logits out (SURVEY.md §7 "L2-resident batch tiling").
+// Host-buffer calls overlap the H2D copy of micro-batch i+1 (copy stream) with the compute of
+// micro-batch i (compute stream).
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace bnb {
+
+namespace {
+constexpr double kPi = 3.14159265358979323846;
+size_t fmt_bytes(int fmt) { return fmt == BNB_PCM_S16 ? 2 : 4; }
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+const float* Engine::up(const float* host, size_t n) { return up_t<float>(host, n); }
+
+template <class T>
+const T* Engine::up_t(const T* host, size_t n) {
+  void* d = nullptr;
+  BNB_CUDA(cudaMalloc(&d, std::max<size_t>(n * sizeof(T), 16)));
+  allocs_.push_back(d);
+  BNB_CUDA(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return static_cast<const T*>(d);
+}
+
+Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
+  int dev = opts.device;
+  if (dev < 0) BNB_CUDA(cudaGetDevice(&dev));
+  BNB_CUDA(cudaSetDevice(dev));
+  device_ = dev;
+  cudaDeviceProp prop{};
+  BNB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) throw std::runtime_error(std::string("device '") + prop.name + "' is not compute capability 10.x (sm_100a kernels only)");
+  device_name_ = std::string("CUDA:") + std::to_string(dev) + " " + prop.name;
+  max_batch_ = opts.max_batch > 0 ? opts.max_batch : 256;
+  micro_ = opts.micro_batch > 0 ? opts.micro_batch : 32;
+  if (micro_ > max_batch_) micro_ = max_batch_;
+  precision_ = opts.precision == BNB_PRECISION_DEFAULT ? BNB_PRECISION_F32 : opts.precision;
+  precision_name_ = precision_ == BNB_PRECISION_F16X3 ? "FP16x3(tcgen05)+FP32" : "FP32";
+
+  TfModel model = parse_tflite(tflite, len);
+  NetPlan P = build_plan(model);
+  // ---- kernel-specific geometry the sm_100a kernels are specialised for ---------------------------
+  const FrontendPlan& F = P.fe;
+  if (F.n_samples != 144000 || F.spec[0].frame_len != 2048 || F.spec[0].hop != 278 || F.spec[1].frame_len != 1024 ||
+      F.spec[1].hop != 280 || F.spec[0].n_frames != 511 || F.spec[0].n_mel != 96)
+    throw unsupported_model("frontend geometry differs from BirdNET v2.4 (144000 samples, 2048/278 + 1024/280 frames, 96 mel)");
+  if (P.stem.conv.kh != 4 || P.stem.conv.kw != 8 || P.stem.conv.cin != 2 || P.stem.conv.cout != 24 || P.stem.stride_h != 2 ||
+      P.stem.stride_w != 2 || P.stem.out_w != 256 || P.mix.conv.cout != 24)
+    throw unsupported_model("stem geometry differs from BirdNET v2.4 (4x8/s2, 2->24, 1x1 48->24)");
+  if (P.post.out_h != 1) throw unsupported_model("post conv must reduce the mel axis to 1");
+  for (const BlockPlan& b : P.blocks)
+    if (b.cin % 4 || b.cexp % 4 || b.cout % 4 || (b.has_se && (b.cexp > 1536 || b.cse > 64))) throw unsupported_model("block channel counts");
+  n_species_ = P.n_species(); n_samples_ = F.n_samples; emb_dim_ = P.emb_dim();
+
+  BNB_CUDA(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking));
+  BNB_CUDA(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
+  BNB_CUDA(cudaEventCreate(&ev_start_));
+  BNB_CUDA(cudaEventCreate(&ev_stop_));
+  upload_weights(P);
+  alloc_workspace();
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  if (compute_) cudaStreamSynchronize(compute_);
+  if (copy_) cudaStreamSynchronize(copy_);
+  for (void* p : allocs_) cudaFree(p);
+  for (auto& kv : keep_bufs_) cudaFree(kv.second.first);
+  if (h_in_) cudaFreeHost(h_in_);
+  if (h_out_) cudaFreeHost(h_out_);
+  for (cudaEvent_t e : ev_h2d_) cudaEventDestroy(e);
+  for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
+  if (ev_start_) cudaEventDestroy(ev_start_);
+  if (ev_stop_) cudaEventDestroy(ev_stop_);
+  if (compute_) cudaStreamDestroy(compute_);
+  if (copy_) cudaStreamDestroy(copy_);
+}
+
+// ------------------------------------------------------------------------------------------------
+void Engine::upload_weights(const NetPlan& P) {
+  // ---- frontend tables -----------------------------------------------------------------------------
+  const FrontendPlan& F = P.fe;
+  fe_.n_samples = F.n_samples; fe_.n_frames = F.spec[0].n_frames; fe_.n_mel = F.spec[0].n_mel;
+  fe_.eps = F.eps; fe_.center = F.center; fe_.gain = F.gain;
+  for (int s = 0; s < 2; ++s) {
+    const SpecPlan& S = F.spec[s];
+    fe_.pow_exp[s] = S.pow_exp; fe_.bn_scale[s] = F.bn_scale[s]; fe_.bn_shift[s] = F.bn_shift[s];
+    fe_.win[s] = up(S.window, (size_t)S.frame_len);
+    const int N = S.frame_len / 2;                  // complex FFT length: 1024 / 512
+    const int n2 = N / 32;                          // first-pass FFT size: 32 / 16
+    std::vector<float2> tw((size_t)n2 * 32), post((size_t)N);
+    for (int k2 = 0; k2 < n2; ++k2)
+      for (int l = 0; l < 32; ++l) {
+        const double a = -2.0 * kPi * (double)(l * k2) / (double)N;
+        tw[(size_t)k2 * 32 + l] = make_float2((float)cos(a), (float)sin(a));
+      }
+    for (int k = 0; k < N; ++k) {
+      const double a = kPi * (double)k / (double)N;
+      post[k] = make_float2((float)(0.5 * cos(a)), (float)(0.5 * sin(a)));
+    }
+    fe_.tw[s] = up_t<float2>(tw.data(), tw.size());
+    fe_.post[s] = up_t<float2>(post.data(), post.size());
+    // sparse mel rows: contiguous non-zero run per band
+    std::vector<int> start(S.n_mel, 0), cnt(S.n_mel, 0);
+    int stride = 1, max_bin = 0;
+    for (int m = 0; m < S.n_mel; ++m) {
+      int lo = -1, hi = -1;
+      for (int k = 0; k < S.n_bins; ++k) if (S.mel[(size_t)m * S.n_bins + k] != 0.f) { if (lo < 0) lo = k; hi = k; }
+      if (lo >= 0) { start[m] = lo; cnt[m] = hi - lo + 1; stride = std::max(stride, cnt[m]); max_bin = std::max(max_bin, hi); }
+    }
+    std::vector<float> w((size_t)S.n_mel * stride, 0.f);
+    for (int m = 0; m < S.n_mel; ++m) for (int i = 0; i < cnt[m]; ++i) w[(size_t)m * stride + i] = S.mel[(size_t)m * S.n_bins + start[m] + i];
+    const int group = (s == 0) ? 32 : 16;
+    fe_.nk1[s] = max_bin / group + 1;
+    if ((s == 0 && fe_.nk1[0] > 4) || (s == 1 && fe_.nk1[1] > 32) || max_bin >= N)
+      throw unsupported_model("mel matrix reaches beyond the spectrum range the frontend kernel computes");
+    fe_.mel_stride[s] = stride;
+    fe_.mel_start[s] = up_t<int>(start.data(), start.size());
+    fe_.mel_cnt[s] = up_t<int>(cnt.data(), cnt.size());
+    fe_.mel_w[s] = up(w.data(), w.size());
+  }
+  fe_tensor_ = F.out_tensor;
+  // ---- stem + pool mix ---------------------------------------------------------------------------------
+  {
+    const ConvW& c = P.stem.conv;   // OHWI [24][4][8][2] -> [kh][kw][ci][co]
+    std::vector<float> w((size_t)c.kh * c.kw * c.cin * c.cout);
+    for (int o = 0; o < c.cout; ++o) for (int kh = 0; kh < c.kh; ++kh) for (int kw = 0; kw < c.kw; ++kw) for (int ci = 0; ci < c.cin; ++ci)
+      w[(((size_t)kh * c.kw + kw) * c.cin + ci) * c.cout + o] = c.w[(((size_t)o * c.kh + kh) * c.kw + kw) * c.cin + ci];
+    stem_.w_stem = up(w.data(), w.size());
+    std::vector<float> zb(c.cout, 0.f);
+    stem_.b_stem = up(c.b ? c.b : zb.data(), (size_t)c.cout);
+    const ConvW& m = P.mix.conv;    // [24][48]; normalise concat order to (max | avg)
+    std::vector<float> wm((size_t)m.cout * m.cin);
+    const int half = m.cin / 2;
+    for (int o = 0; o < m.cout; ++o) for (int ci = 0; ci < m.cin; ++ci) {
+      int src = ci;
+      if (!P.mix.max_first) src = (ci < half) ? ci + half : ci - half;
+      wm[(size_t)o * m.cin + ci] = m.w[(size_t)o * m.cin + src];
+    }
+    stem_.w_mix = up(wm.data(), wm.size());
+    std::vector<float> zb2(m.cout, 0.f);
+    stem_.b_mix = up(m.b ? m.b : zb2.data(), (size_t)m.cout);
+    stem_.in_h = P.stem.in_h; stem_.in_w = P.stem.in_w; stem_.out_h = P.stem.out_h; stem_.out_w = P.stem.out_w;
+    stem_.pad_t = P.stem.pad_t; stem_.pad_l = P.stem.pad_l;
+    stem_tensor_ = P.stem.out_tensor; mix_tensor_ = P.mix.out_tensor;
+  }
+  // ---- blocks ----------------------------------------------------------------------------------------------
+  auto upconv = [&](const ConvW& c, size_t n) {
+    DevConv d; d.w = up(c.w, n);
+    std::vector<float> z((size_t)c.cout, 0.f);
+    d.b = up(c.b ? c.b : z.data(), (size_t)c.cout);
+    return d;
+  };
+  for (const BlockPlan& b : P.blocks) {
+    DevBlock d; d.g = b;
+    d.expand = upconv(b.expand, (size_t)b.cexp * b.cin);
+    d.dw = upconv(b.dw, (size_t)9 * b.cexp);
+    if (b.has_se) { d.se1 = upconv(b.se1, (size_t)b.cse * b.cexp); d.se2 = upconv(b.se2, (size_t)b.cexp * b.cse); }
+    d.proj = upconv(b.proj, (size_t)b.cout * b.cexp);
+    blocks_.push_back(d);
+  }
+  // ---- post + head ------------------------------------------------------------------------------------------
+  post_g_ = P.post;
+  post_mul_ = up(P.post.mul, (size_t)P.post.conv.cin);
+  post_add_ = up(P.post.add, (size_t)P.post.conv.cin);
+  post_conv_ = upconv(P.post.conv, (size_t)P.post.conv.cout * P.post.conv.kh * P.post.conv.kw * P.post.conv.cin);
+  fc_ = upconv(P.head.fc, (size_t)P.head.fc.cout * P.head.fc.cin);
+  logits_tensor_ = P.head.out_tensor;
+}
+
+void Engine::alloc_workspace() {
+  auto dmalloc = [&](size_t floats) { void* p = nullptr; BNB_CUDA(cudaMalloc(&p, std::max<size_t>(floats, 4) * sizeof(float))); allocs_.push_back(p); return static_cast<float*>(p); };
+  const size_t mb = (size_t)micro_;
+  cap_x_ = (size_t)stem_.out_h * (stem_.out_w / 2) * 24; cap_e_ = 0; cap_d_ = 0; cap_g_ = 0;
+  for (const DevBlock& b : blocks_) {
+    cap_e_ = std::max(cap_e_, (size_t)b.g.in_h * b.g.in_w * b.g.cexp);
+    cap_d_ = std::max(cap_d_, (size_t)b.g.out_h * b.g.out_w * b.g.cexp);
+    cap_x_ = std::max(cap_x_, (size_t)b.g.out_h * b.g.out_w * b.g.cout);
+    cap_g_ = std::max(cap_g_, (size_t)b.g.cexp);
+  }
+  ws_partial_ = dmalloc(mb * kMinMaxParts * 2);
+  ws_fe_ = dmalloc(mb * fe_.n_mel * fe_.n_frames * 2);
+  ws_x0_ = dmalloc(mb * cap_x_); ws_x1_ = dmalloc(mb * cap_x_);
+  ws_e_ = dmalloc(mb * cap_e_); ws_d_ = dmalloc(mb * cap_d_); ws_g_ = dmalloc(mb * cap_g_);
+  ws_pc_ = dmalloc(mb * post_g_.out_w * post_g_.conv.cout);
+  ws_emb_ = dmalloc(mb * emb_dim_);
+}
+
+float* Engine::scratch(int tensor_id, float* normal, size_t per_chunk, int n) {
+  if (!keep_ || tensor_id < 0) return normal;
+  auto it = keep_bufs_.find(tensor_id);
+  const size_t need = per_chunk * (size_t)micro_;
+  if (it == keep_bufs_.end() || it->second.second < need) {
+    if (it != keep_bufs_.end()) cudaFree(it->second.first);
+    void* p = nullptr;
+    BNB_CUDA(cudaMalloc(&p, need * sizeof(float)));
+    keep_bufs_[tensor_id] = {static_cast<float*>(p), need};
+    return static_cast<float*>(p);
+  }
+  (void)n;
+  return it->second.first;
+}
+
+// ------------------------------------------------------------------------------------------------
+void Engine::run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float* d_emb, cudaStream_t s) {
+  views_.clear();
+  // frontend
+  { ProfScope ps(this, C_MINMAX, s); launch_minmax(d_pcm, fmt, n, n_samples_, ws_partial_, s, lc_); }
+  const size_t fe_sz = (size_t)fe_.n_mel * fe_.n_frames * 2;
+  float* fe_out = scratch(fe_tensor_, ws_fe_, fe_sz, n);
+  { ProfScope ps(this, C_FRONTEND, s); launch_frontend(fe_, d_pcm, fmt, n, ws_partial_, fe_out, s, lc_); }
+  record(fe_tensor_, fe_out, fe_sz, n);
+  // stem + pool mix
+  const size_t stem_sz = (size_t)stem_.out_h * stem_.out_w * 24, mix_sz = stem_sz / 2;
+  float* stem_dump = keep_ ? scratch(stem_tensor_, nullptr, stem_sz, n) : nullptr;
+  float* cur = scratch(mix_tensor_, ws_x0_, mix_sz, n);
+  float* nxt_normal = ws_x1_;
+  { ProfScope ps(this, C_STEM_MIX, s); launch_stem_mix(stem_, fe_out, stem_dump, cur, n, s, lc_); }
+  if (stem_dump) record(stem_tensor_, stem_dump, stem_sz, n);
+  record(mix_tensor_, cur, mix_sz, n);
+  // MBConv blocks
+  for (const DevBlock& b : blocks_) {
+    const BlockPlan& g = b.g;
+    const int hw_in = g.in_h * g.in_w, hw_out = g.out_h * g.out_w;
+    float* e = scratch(g.exp_tensor, ws_e_, (size_t)hw_in * g.cexp, n);
+    PwArgs ex{};
+    ex.A = cur; ex.W = b.expand.w; ex.bias = b.expand.b; ex.C = e; ex.M = n * hw_in; ex.N = g.cexp; ex.K = g.cin;
+    ex.rows_per_chunk = hw_in; ex.act = ACT_SILU; ex.a_mode = A_PLAIN;
+    { ProfScope ps(this, C_PW_EXPAND, s); launch_pw_conv(ex, s, lc_); }
+    record(g.exp_tensor, e, (size_t)hw_in * g.cexp, n);
+    float* d = scratch(g.dw_tensor, ws_d_, (size_t)hw_out * g.cexp, n);
+    DwArgs dw{e, b.dw.w, b.dw.b, d, n, g.in_h, g.in_w, g.cexp, g.stride, g.out_h, g.out_w};
+    { ProfScope ps(this, C_DW, s); launch_dw_conv(dw, s, lc_); }
+    record(g.dw_tensor, d, (size_t)hw_out * g.cexp, n);
+    float* gate = nullptr;
+    if (g.has_se) {
+      gate = scratch(g.gate_tensor, ws_g_, (size_t)g.cexp, n);
+      SeArgs se{d, b.se1.w, b.se1.b, b.se2.w, b.se2.b, gate, n, hw_out, g.cexp, g.cse};
+      { ProfScope ps(this, C_SE, s); launch_se_gate(se, s, lc_); }
+      record(g.gate_tensor, gate, (size_t)g.cexp, n);
+    }
+    float* out = scratch(g.out_tensor, nxt_normal, (size_t)hw_out * g.cout, n);
+    PwArgs pj{};
+    pj.A = d; pj.W = b.proj.w; pj.bias = b.proj.b; pj.C = out; pj.M = n * hw_out; pj.N = g.cout; pj.K = g.cexp;
+    pj.rows_per_chunk = hw_out; pj.act = ACT_NONE; pj.a_mode = A_PLAIN; pj.gate = gate; pj.residual = g.residual ? cur : nullptr;
+    { ProfScope ps(this, C_PW_PROJECT, s); launch_pw_conv(pj, s, lc_); }
+    record(g.out_tensor, out, (size_t)hw_out * g.cout, n);
+    // ping-pong the two block buffers (in keep mode `out` is a private buffer; keep the pair intact)
+    if (!keep_) { nxt_normal = cur; }
+    cur = out;
+    if (!keep_) { /* cur now points at the former nxt_normal; nxt_normal at the former cur */ }
+  }
+  // post: relu(x*mul+add) -> KxK VALID conv + ReLU -> mean over the remaining time positions -> embedding
+  const PostPlan& q = post_g_;
+  float* pc = scratch(q.conv_tensor, ws_pc_, (size_t)q.out_w * q.conv.cout, n);
+  PwArgs pa{};
+  pa.A = cur; pa.W = post_conv_.w; pa.bias = post_conv_.b; pa.C = pc; pa.M = n * q.out_w; pa.N = q.conv.cout;
+  pa.K = q.conv.kh * q.conv.kw * q.conv.cin; pa.rows_per_chunk = q.out_w; pa.act = ACT_RELU; pa.a_mode = A_CONV3X3_ROW;
+  pa.a_mul = post_mul_; pa.a_add = post_add_; pa.a_ch = q.conv.cin; pa.in_w = q.in_w; pa.out_w = q.out_w; pa.cin = q.conv.cin; pa.kw = q.conv.kw;
+  { ProfScope ps(this, C_POST_CONV, s); launch_pw_conv(pa, s, lc_); }
+  record(q.conv_tensor, pc, (size_t)q.out_w * q.conv.cout, n);
+  float* emb = d_emb ? d_emb : ws_emb_;
+  { ProfScope ps(this, C_ROW_MEAN, s); launch_row_mean(pc, emb, n, q.out_w, q.conv.cout, s, lc_); }
+  record(q.emb_tensor, emb, (size_t)emb_dim_, n);
+  PwArgs fa{};
+  fa.A = emb; fa.W = fc_.w; fa.bias = fc_.b; fa.C = d_logits; fa.M = n; fa.N = n_species_; fa.K = emb_dim_;
+  fa.rows_per_chunk = 1; fa.act = ACT_NONE; fa.a_mode = A_PLAIN;
+  { ProfScope ps(this, C_FC, s); launch_pw_conv(fa, s, lc_); }
+  record(logits_tensor_, d_logits, (size_t)n_species_, n);
+}
+
+void Engine::predict_device(const void* d_pcm, int fmt, int B, float* d_logits, float* d_emb, cudaStream_t s) {
+  BNB_CUDA(cudaSetDevice(device_));
+  if (!s) s = compute_;
+  const size_t cb = (size_t)n_samples_ * fmt_bytes(fmt);
+  for (int i = 0; i < B; i += micro_) {
+    const int n = std::min(micro_, B - i);
+    run_micro(static_cast<const char*>(d_pcm) + (size_t)i * cb, fmt, n, d_logits + (size_t)i * n_species_,
+              d_emb ? d_emb + (size_t)i * emb_dim_ : nullptr, s);
+  }
+}
+
+void Engine::analyze_device(const void* d_pcm, int fmt, int B, float sensitivity, int k, int32_t* d_idx, float* d_conf,
+                            float* d_logits_or_null, cudaStream_t s) {
+  BNB_CUDA(cudaSetDevice(device_));
+  if (!s) s = compute_;
+  float* lg = d_logits_or_null;
+  if (!lg) { ensure_host_staging(); lg = d_logits_; }
+  predict_device(d_pcm, fmt, B, lg, nullptr, s);
+  { ProfScope ps(this, C_TOPK, s); launch_sigmoid_topk(lg, B, n_species_, sensitivity, k, d_idx, d_conf, s, lc_); }
+}
+
+// ------------------------------------------------------------------------------------------------
+void Engine::ensure_host_staging() {
+  if (d_in_) return;
+  const size_t mbs = (size_t)max_batch_;
+  auto dm = [&](size_t bytes) { void* p = nullptr; BNB_CUDA(cudaMalloc(&p, bytes)); allocs_.push_back(p); return p; };
+  d_in_ = dm(mbs * n_samples_ * 4);
+  d_logits_ = static_cast<float*>(dm(mbs * n_species_ * 4));
+  d_emb_ = static_cast<float*>(dm(mbs * emb_dim_ * 4));
+  topk_cap_ = 64;
+  d_idx_ = static_cast<int32_t*>(dm(mbs * topk_cap_ * 4));
+  d_conf_ = static_cast<float*>(dm(mbs * topk_cap_ * 4));
+  h_in_bytes_ = mbs * n_samples_ * 4;
+  h_out_bytes_ = mbs * ((size_t)n_species_ + emb_dim_ + 2 * topk_cap_) * 4;
+  BNB_CUDA(cudaHostAlloc(&h_in_, h_in_bytes_, cudaHostAllocDefault));
+  BNB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_out_), h_out_bytes_, cudaHostAllocDefault));
+  const int n_micro = ceil_div(max_batch_, micro_);
+  ev_h2d_.resize(n_micro);
+  for (auto& e : ev_h2d_) BNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
+namespace {
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+// Shared body of the two host entry points.  k == 0 -> logits (+emb) only.
+void Engine::predict_host(const void* pcm, int fmt, int B, float* logits, float* emb) {
+  analyze_host(pcm, fmt, B, 0.f, 0, nullptr, nullptr, logits);
+  if (emb) {
+    BNB_CUDA(cudaMemcpyAsync(emb, d_emb_, (size_t)B * emb_dim_ * 4, cudaMemcpyDeviceToHost, compute_));
+    BNB_CUDA(cudaStreamSynchronize(compute_));
+  }
+}
+
+void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, int k, int32_t* idx, float* conf, float* logits) {
+  BNB_CUDA(cudaSetDevice(device_));
+  ensure_host_staging();
+  if (k > topk_cap_) throw std::invalid_argument("k exceeds the top-k capacity (64)");
+  const size_t cb = (size_t)n_samples_ * fmt_bytes(fmt);
+  const bool src_pinned = is_pinned(pcm);
+  BNB_CUDA(cudaEventRecord(ev_start_, compute_));
+  // H2D per micro-batch on the copy stream; compute waits per micro-batch
+  int mi = 0;
+  for (int i = 0; i < B; i += micro_, ++mi) {
+    const int n = std::min(micro_, B - i);
+    const char* src = static_cast<const char*>(pcm) + (size_t)i * cb;
+    if (!src_pinned) {   // callee copies (process.go:280-291): stage through our pinned buffer
+      memcpy(static_cast<char*>(h_in_) + (size_t)i * cb, src, (size_t)n * cb);
+      src = static_cast<const char*>(h_in_) + (size_t)i * cb;
+    }
+    BNB_CUDA(cudaMemcpyAsync(static_cast<char*>(d_in_) + (size_t)i * cb, src, (size_t)n * cb, cudaMemcpyHostToDevice, copy_));
+    BNB_CUDA(cudaEventRecord(ev_h2d_[mi], copy_));
+    BNB_CUDA(cudaStreamWaitEvent(compute_, ev_h2d_[mi], 0));
+    run_micro(static_cast<const char*>(d_in_) + (size_t)i * cb, fmt, n, d_logits_ + (size_t)i * n_species_,
+              d_emb_ + (size_t)i * emb_dim_, compute_);
+  }
+  if (k > 0) {
+    { ProfScope ps(this, C_TOPK, compute_); launch_sigmoid_topk(d_logits_, B, n_species_, sensitivity, k, d_idx_, d_conf_, compute_, lc_); }
+    BNB_CUDA(cudaMemcpyAsync(idx, d_idx_, (size_t)B * k * 4, cudaMemcpyDeviceToHost, compute_));
+    BNB_CUDA(cudaMemcpyAsync(conf, d_conf_, (size_t)B * k * 4, cudaMemcpyDeviceToHost, compute_));
+  }
+  if (logits) BNB_CUDA(cudaMemcpyAsync(logits, d_logits_, (size_t)B * n_species_ * 4, cudaMemcpyDeviceToHost, compute_));
+  BNB_CUDA(cudaEventRecord(ev_stop_, compute_));
+  BNB_CUDA(cudaStreamSynchronize(compute_));
+  BNB_CUDA(cudaStreamSynchronize(copy_));
+  BNB_CUDA(cudaEventElapsedTime(&last_ms_, ev_start_, ev_stop_));
+}
+
+// ------------------------------------------------------------------------------------------------
+Engine::ProfScope::ProfScope(Engine* eng, int cat, cudaStream_t st) : e(eng), s(st), idx(-1) {
+  if (!e->profiling_) return;
+  if (e->prof_used_ + 2 > e->prof_ev_.size()) {
+    for (int i = 0; i < 2; ++i) { cudaEvent_t ev; BNB_CUDA(cudaEventCreate(&ev)); e->prof_ev_.push_back(ev); }
+  }
+  idx = (int)e->prof_used_; e->prof_used_ += 2; e->prof_cat_.push_back(cat);
+  cudaEventRecord(e->prof_ev_[idx], s);
+}
+Engine::ProfScope::~ProfScope() { if (idx >= 0) cudaEventRecord(e->prof_ev_[idx + 1], s); }
+
+void Engine::profile_begin() { profiling_ = true; prof_used_ = 0; prof_cat_.clear(); }
+
+int Engine::profile_end(float* ms, long long* launches, int cap) {
+  BNB_CUDA(cudaSetDevice(device_));
+  BNB_CUDA(cudaDeviceSynchronize());
+  profiling_ = false;
+  for (int i = 0; i < cap; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  for (size_t i = 0; i < prof_cat_.size(); ++i) {
+    float t = 0.f;
+    BNB_CUDA(cudaEventElapsedTime(&t, prof_ev_[2 * i], prof_ev_[2 * i + 1]));
+    const int c = prof_cat_[i];
+    if (c < cap) { ms[c] += t; launches[c]++; }
+  }
+  return C_COUNT;
+}
+
+long long Engine::read_tensor(int tensor, float* out, size_t cap) {
+  BNB_CUDA(cudaSetDevice(device_));
+  auto it = views_.find(tensor);
+  if (it == views_.end()) return BNB_ERR_INVALID_ARGUMENT;
+  const size_t n = it->second.per_chunk * (size_t)it->second.chunks;
+  if (n > cap) return BNB_ERR_INVALID_ARGUMENT;
+  BNB_CUDA(cudaDeviceSynchronize());
+  BNB_CUDA(cudaMemcpy(out, it->second.ptr, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return (long long)n;
+}
+
+}  // namespace bnb

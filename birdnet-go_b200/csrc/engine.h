@@ -1,0 +1,110 @@
+// engine.h — device-side state of one classifier handle (weights, workspaces, streams) and the
+// kernel chain that replaces `interpreter.Invoke()`
+// (/root/reference/internal/inference/tflite/classifier.go:107).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/birdnet_b200.h"
+#include "kernels.h"
+#include "net_plan.h"
+
+namespace bnb {
+
+struct DevConv { const float* w = nullptr; const float* b = nullptr; };
+
+struct DevBlock {
+  BlockPlan g;          // geometry + tensor ids (host weight pointers are dead after upload)
+  DevConv expand, dw, se1, se2, proj;
+};
+
+struct TensorView { const float* ptr = nullptr; size_t per_chunk = 0; int chunks = 0; };
+
+class Engine {
+ public:
+  Engine(const void* tflite, size_t len, const bnb_options& opts);
+  ~Engine();
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+
+  int n_species() const { return n_species_; }
+  int n_samples() const { return n_samples_; }
+  int emb_dim() const { return emb_dim_; }
+  int max_batch() const { return max_batch_; }
+  int device() const { return device_; }
+  const char* device_name() const { return device_name_.c_str(); }
+  const char* precision_name() const { return precision_name_.c_str(); }
+  long long launches() const { return lc_.n; }
+  float last_device_ms() const { return last_ms_; }
+
+  // device-resident inputs/outputs, enqueued on `s` (nullptr -> own compute stream), no sync
+  void predict_device(const void* d_pcm, int fmt, int B, float* d_logits, float* d_emb, cudaStream_t s);
+  void analyze_device(const void* d_pcm, int fmt, int B, float sensitivity, int k, int32_t* d_idx, float* d_conf,
+                      float* d_logits_or_null, cudaStream_t s);
+  // host buffers: pinned staging, H2D/compute overlap per micro-batch, D2H, synchronous
+  void predict_host(const void* pcm, int fmt, int B, float* logits, float* emb);
+  void analyze_host(const void* pcm, int fmt, int B, float sensitivity, int k, int32_t* idx, float* conf, float* logits);
+
+  void keep_intermediates(bool on) { keep_ = on; }
+  // per-category device timing (CUDA events around every launch); see bnb_profile_* in the C ABI
+  enum Cat : int { C_MINMAX = 0, C_FRONTEND, C_STEM_MIX, C_PW_EXPAND, C_DW, C_SE, C_PW_PROJECT, C_POST_CONV, C_ROW_MEAN, C_FC, C_TOPK, C_COUNT };
+  void profile_begin();
+  int profile_end(float* ms, long long* launches, int cap);
+  long long read_tensor(int tensor, float* out, size_t cap);
+
+ private:
+  void run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float* d_emb, cudaStream_t s);
+  float* scratch(int tensor_id, float* normal, size_t per_chunk, int n);
+  void record(int tensor_id, const float* p, size_t per_chunk, int n) { if (tensor_id >= 0) views_[tensor_id] = TensorView{p, per_chunk, n}; }
+  void upload_weights(const NetPlan& P);
+  void alloc_workspace();
+  void ensure_host_staging();
+  const float* up(const float* host, size_t n);  // copy into the weight arena, returns device ptr
+  template <class T> const T* up_t(const T* host, size_t n);
+
+  struct ProfScope {
+    Engine* e; cudaStream_t s; int idx;
+    ProfScope(Engine* eng, int cat, cudaStream_t st);
+    ~ProfScope();
+  };
+  bool profiling_ = false;
+  std::vector<cudaEvent_t> prof_ev_;          // pairs (start, stop)
+  std::vector<int> prof_cat_;
+  size_t prof_used_ = 0;
+
+  int device_ = 0, n_species_ = 0, n_samples_ = 0, emb_dim_ = 0, max_batch_ = 256, micro_ = 32, precision_ = BNB_PRECISION_F32;
+  std::string device_name_, precision_name_;
+  LaunchCounter lc_;
+  float last_ms_ = 0.f;
+  bool keep_ = false;
+
+  // weights
+  std::vector<void*> allocs_;                 // every cudaMalloc owned by the handle
+  FrontendDev fe_{};
+  StemMixDev stem_{};
+  int stem_tensor_ = -1, fe_tensor_ = -1, mix_tensor_ = -1;
+  std::vector<DevBlock> blocks_;
+  PostPlan post_g_{}; DevConv post_conv_; const float* post_mul_ = nullptr; const float* post_add_ = nullptr;
+  DevConv fc_; int logits_tensor_ = -1;
+
+  // workspaces (capacity: micro_ chunks)
+  float *ws_partial_ = nullptr, *ws_fe_ = nullptr, *ws_x0_ = nullptr, *ws_x1_ = nullptr, *ws_e_ = nullptr, *ws_d_ = nullptr,
+        *ws_g_ = nullptr, *ws_pc_ = nullptr, *ws_emb_ = nullptr;
+  size_t cap_x_ = 0, cap_e_ = 0, cap_d_ = 0, cap_g_ = 0;
+  std::map<int, std::pair<float*, size_t>> keep_bufs_;   // tensor id -> (device buffer, capacity in floats)
+  std::map<int, TensorView> views_;
+
+  // full-batch device buffers for the host path
+  void* d_in_ = nullptr; float* d_logits_ = nullptr; float* d_emb_ = nullptr; int32_t* d_idx_ = nullptr; float* d_conf_ = nullptr;
+  void* h_in_ = nullptr; float* h_out_ = nullptr; size_t h_in_bytes_ = 0, h_out_bytes_ = 0;
+  int topk_cap_ = 0;
+  cudaStream_t compute_ = nullptr, copy_ = nullptr;
+  std::vector<cudaEvent_t> ev_h2d_;
+  cudaEvent_t ev_start_ = nullptr, ev_stop_ = nullptr;
+};
+
+}  // namespace bnb

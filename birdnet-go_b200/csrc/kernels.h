@@ -1,0 +1,97 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (definitions in the .cu files).
+//
+// All activations are NHWC float32 with H = mel axis, W = time axis, exactly the layout of the
+// tensors in the reference's .tflite graph, so every intermediate can be compared 1:1 with the
+// oracle (tests/ use bnb_debug_read_tensor for that).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace bnb {
+
+// ---------------------------------------------------------------- frontend (frontend.cu)
+constexpr int kMinMaxParts = 8;       // partial min/max blocks per chunk
+constexpr int kFeFramesPerCta = 32;   // frames of each spectrogram handled by one CTA
+
+struct FrontendDev {
+  // geometry (validated against these fixed values at load time)
+  int n_samples;     // 144000
+  int n_frames;      // 511
+  int n_mel;         // 96
+  float eps, center, gain;
+  float pow_exp[2], bn_scale[2], bn_shift[2];
+  int nk1[2];        // number of 32-/16-bin groups of the real spectrum that the mel matrix touches
+  int mel_stride[2]; // padded non-zeros per mel band
+  // device tables
+  const float* win[2];       // [2048], [1024]
+  const float2* tw[2];       // [32][32], [16][32]: exp(-2*pi*i*l*k2/N), indexed [k2][l]
+  const float2* post[2];     // [N/2]: 0.5*(cos, sin)(pi*k/(N/2))  (N/2 = complex FFT length)
+  const int* mel_start[2];   // [96]
+  const int* mel_cnt[2];     // [96]
+  const float* mel_w[2];     // [96][mel_stride]
+};
+
+void launch_minmax(const void* pcm, int fmt, int B, int n_samples, float* partial, cudaStream_t s, LaunchCounter& lc);
+void launch_frontend(const FrontendDev& fe, const void* pcm, int fmt, int B, const float* partial, float* out,
+                     cudaStream_t s, LaunchCounter& lc);
+size_t frontend_smem_bytes();
+
+// ---------------------------------------------------------------- fp32 CUDA-core conv stack (conv_f32.cu)
+struct StemMixDev {
+  const float* w_stem;  // [kh=4][kw=8][ci=2][co=24]  (re-laid from OHWI at load)
+  const float* b_stem;  // [24]
+  const float* w_mix;   // [co=24][c=48]  concat order already normalised to (max, avg)
+  const float* b_mix;   // [24]
+  int in_h, in_w, out_h, out_w, pad_t, pad_l;   // 96, 511, 48, 256, 1, 3
+};
+void launch_stem_mix(const StemMixDev& p, const float* in, float* stem_out_or_null, float* out, int B,
+                     cudaStream_t s, LaunchCounter& lc);
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_SIGMOID = 3 };
+
+// A-operand addressing modes of the generic pointwise GEMM
+enum AMode : int {
+  A_PLAIN = 0,      // A[m][k] = in[m*K + k]
+  A_CONV3X3_ROW = 1 // post conv: kh x kw VALID over a [H=kh, W, C] map -> out [1, W-kw+1]; see conv_f32.cu
+};
+
+struct PwArgs {
+  const float* A; const float* W; const float* bias; float* C;
+  const float* residual;   // [M][N] or null
+  const float* gate;       // [M / rows_per_chunk][K] or null: A[m][k] *= gate[m / rows_per_chunk][k]
+  const float* a_mul; const float* a_add;  // optional per-k affine + ReLU on A (post block): relu(a*mul[c]+add[c]), c = k % a_ch
+  int a_ch;
+  int M, N, K;
+  int rows_per_chunk;
+  int act;
+  int a_mode;
+  int in_w, out_w, cin, kw;  // A_CONV3X3_ROW geometry
+};
+void launch_pw_conv(const PwArgs& a, cudaStream_t s, LaunchCounter& lc);
+
+struct DwArgs {
+  const float* in; const float* w; const float* bias; float* out;  // w: [3][3][C]
+  int B, H, W, C, stride, Ho, Wo;
+};
+void launch_dw_conv(const DwArgs& a, cudaStream_t s, LaunchCounter& lc);
+
+struct SeArgs {
+  const float* x;   // [B][HW][C]
+  const float* w1; const float* b1;  // [Cse][C]
+  const float* w2; const float* b2;  // [C][Cse]
+  float* gate;      // [B][C]
+  int B, HW, C, Cse;
+};
+void launch_se_gate(const SeArgs& a, cudaStream_t s, LaunchCounter& lc);
+
+// mean over `rows` consecutive rows: in [B][rows][C] -> out [B][C]
+void launch_row_mean(const float* in, float* out, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc);
+
+// ---------------------------------------------------------------- post-processing (post.cu)
+// conf = sigmoid(sensitivity * logit) (float64 exp like analyze.go:113-115), top-k descending, ties -> lower index
+void launch_sigmoid_topk(const float* logits, int B, int n, float sensitivity, int k, int32_t* idx, float* conf,
+                         cudaStream_t s, LaunchCounter& lc);
+
+}  // namespace bnb

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/birdnet_b200.h declares, parses the
+model into the expected layer plan, and fails closed without a GPU (no compute calls here)."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import birdnet_b200 as bb
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(REPO, "include", "birdnet_b200.h")).read()
+    return sorted(set(re.findall(r"BNB_API [^;(]*?\b(bnb_[a-z_0-9]+)\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (bnb_[a-z_0-9]+)", out))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    assert set(bb.SYMBOLS) == set(declared)          # the ctypes binding covers the whole header
+    lib = bb.load_library()
+    assert lib.bnb_abi_version() == 1
+
+
+def test_sass_is_sm100a(lib_path):
+    out = subprocess.run(["cuobjdump", "--list-elf", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_plan_extraction_matches_the_graph(lib_path):
+    d = json.loads(bb.describe_model(open(bb.DEFAULT_MODEL, "rb").read()))
+    assert d["n_samples"] == 144000 and d["n_species"] == 6522 and d["embedding_dim"] == 1024
+    assert [s["frame_len"] for s in d["spec"]] == [2048, 1024] and [s["hop"] for s in d["spec"]] == [278, 280]
+    assert all(s["n_frames"] == 511 and s["n_mel"] == 96 for s in d["spec"])
+    assert abs(d["spec"][0]["pow"] - 0.22952409) < 1e-6 and abs(d["spec"][1]["pow"] - 0.1905273) < 1e-6
+    assert d["frontend_out_tensor"] == 265 and d["stem"]["out_tensor"] == 266 and d["mix"]["out_tensor"] == 270
+    assert d["stem"]["pad"] == [1, 3] and d["stem"]["out"] == [48, 256]
+    b = d["blocks"]
+    assert len(b) == 16
+    assert [x["cexp"] for x in b] == [72] * 3 + [288] * 4 + [864] * 5 + [1536] * 4
+    assert [x["stride"] for x in b] == [2, 1, 1, 2, 1, 1, 1, 2, 1, 1, 1, 1, 2, 1, 1, 1]
+    assert [x["se"] for x in b] == [0] * 3 + [18] * 4 + [27] * 5 + [48] * 4
+    assert [x["residual"] for x in b] == [False, True, True, False, True, True, True, False, True, True, True, True, False, True, True, True]
+    assert b[0]["in"] == [48, 128, 24] and b[-1]["out"] == [3, 8, 192]
+    assert b[-1]["tensors"]["out"] == 541 and b[3]["tensors"]["gate"] == 311
+    assert d["post"]["out"] == [1, 6] and d["post"]["emb_tensor"] == 545 and d["head"]["out_tensor"] == 546
+    # MAC count of the plan == SURVEY §8(d): 328,305,984 per chunk
+    mac = 48 * 256 * 24 * 64 + 48 * 128 * 24 * 48
+    for x in b:
+        hin, win, cin = x["in"]; ho, wo, co = x["out"]
+        mac += hin * win * cin * x["cexp"] + ho * wo * x["cexp"] * 9 + ho * wo * x["cexp"] * co + (2 * x["cexp"] * x["se"])
+    mac += 6 * 1728 * 1024 + 1024 * 6522
+    assert mac == 328305984
+
+
+def test_rejects_garbage_and_foreign_models(lib_path):
+    with pytest.raises(bb.B200Error) as e:
+        bb.describe_model(b"\x1c\x00\x00\x00TFL3" + b"\x00" * 64)
+    assert e.value.status == bb.ERR_UNSUPPORTED_MODEL
+    with pytest.raises(bb.B200Error):
+        bb.describe_model(b"not a flatbuffer at all")
+    # the range-filter model in the reference is a valid TFLite file but not this topology; emulate by truncation
+    data = open(bb.DEFAULT_MODEL, "rb").read()
+    with pytest.raises(bb.B200Error):
+        bb.describe_model(data[: len(data) // 2])
+
+
+def test_create_fails_closed_without_gpu(lib_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(bb.B200Unavailable) as e:
+        bb.B200Classifier()
+    assert e.value.status == bb.ERR_NO_DEVICE          # caller falls back to TFLite (birdnet.go:321-335)
+    lib = bb.load_library()
+    assert lib.bnb_num_species(None) == bb.ERR_INVALID_ARGUMENT
+    lib.bnb_classifier_destroy(None)                   # Close() on nil is a no-op
+    assert "NULL" in bb.last_error() or bb.last_error()

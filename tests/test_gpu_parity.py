@@ -1,0 +1,160 @@
+"""GPU: parity of the CUDA path (through the C ABI) against the float64 oracle and the golden fixtures.
+
+Tolerance (BASELINE.json north_star): max |sigmoid(gpu) - sigmoid(oracle)| <= 1e-3 and equal
+top-1; raw-logit differences are reported (two correct fp32 implementations differ by ~1.5e-3 there)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import birdnet_b200 as bb
+import birdnet_oracle as bo
+
+pytestmark = pytest.mark.gpu
+SIG_TOL = 1e-3
+PRECISIONS = [bb.PRECISION_F32, bb.PRECISION_F16X3]
+
+
+def _sig(x):
+    return bo.sigmoid_sensitivity(x, 1.0).astype(np.float64)
+
+
+@pytest.fixture(scope="module", params=PRECISIONS, ids=["f32", "f16x3"])
+def clf(request, lib_path):
+    c = bb.B200Classifier(max_batch=128, micro_batch=16, precision=request.param)
+    yield c
+    c.close()
+
+
+def test_runtime_info(clf):
+    dev, backend, prec = clf.runtime_info()
+    assert dev.startswith("CUDA:") and "B200" in dev
+    assert clf.num_species() == 6522 and clf.n_samples == 144000 and clf.emb_dim == 1024
+
+
+def test_soundscape_sliding_window_parity(clf, golden, audio):
+    """BASELINE config 2: soundscape.wav, 3 s window / 1.5 s overlap -> 79 chunks."""
+    chunks = bo.slice_chunks(audio["soundscape"], 72000)
+    assert chunks.shape[0] == 79
+    logits, emb = clf.predict_batch(chunks, with_embeddings=True)
+    ref = golden["soundscape_logits"].astype(np.float64)
+    ds = np.abs(_sig(logits) - _sig(ref)).max()
+    dl = np.abs(logits - ref).max()
+    print("soundscape: max|dsigmoid|=%.3e max|dlogit|=%.3e" % (ds, dl))
+    assert ds <= SIG_TOL
+    assert (logits.argmax(1) == ref.argmax(1)).all()
+    assert np.abs(emb - golden["soundscape_emb"]).max() <= 2e-2 * np.abs(golden["soundscape_emb"]).max()
+
+
+def test_published_detections_through_the_gpu(clf, audio):
+    """The reference's own table (doc/wiki/file-analysis.md:20-44) reproduced by the CUDA path."""
+    labels = bo.read_labels()
+    chunks = bo.slice_chunks(audio["soundscape"], 144000)
+    idx, conf = clf.analyze_batch(chunks, sensitivity=bo.GOLDEN_SENSITIVITY, k=10)
+    for t0, name, c in bo.GOLDEN_TABLE:
+        i = int(round(t0 / 3.0))
+        assert labels[idx[i, 0]].split("_", 1)[1] == name
+        assert abs(float(conf[i, 0]) - c) <= 1e-3, (t0, conf[i, 0], c)
+
+
+def test_tawnyowl_batch1_dropin(clf, golden, audio):
+    """BASELINE config 1: batch-1 Predict() on tawnyowl.wav chunk by chunk."""
+    chunks = bo.slice_chunks(audio["tawnyowl"], 144000)
+    for i in range(len(chunks)):
+        lg, emb = clf.predict_with_embeddings(chunks[i])
+        ref = golden["tawnyowl_logits"][i].astype(np.float64)
+        assert np.abs(_sig(lg) - _sig(ref)).max() <= SIG_TOL
+        assert int(lg.argmax()) == int(ref.argmax())
+    assert int(clf.predict(chunks[0]).argmax()) == 5760      # Strix aluco_Tawny Owl
+
+
+def test_silence_and_edge_inputs(clf, golden):
+    z = clf.predict(np.zeros(144000, np.float32))
+    assert np.abs(_sig(z) - _sig(golden["zeros_logits"][0])).max() <= SIG_TOL and int(z.argmax()) == 2143
+    # constant (max == min), full-scale square wave, single impulse: compared with the oracle live
+    rng = np.random.default_rng(5)
+    x = np.zeros((4, 144000), np.float32)
+    x[0] = 0.25
+    x[1] = np.where(np.arange(144000) % 96 < 48, 1.0, -1.0)
+    x[2, 70000] = 1.0
+    x[3] = np.clip(rng.standard_normal(144000) * 0.5, -1, 1)
+    ref = bo.Oracle(dtype=torch.float64).predict_batch(x)
+    got = clf.predict_batch(x)
+    assert np.isfinite(got).all()
+    assert np.abs(_sig(got) - _sig(ref)).max() <= SIG_TOL
+
+
+def test_int16_ingest_equals_float_path(clf, audio):
+    chunks = bo.slice_chunks(audio["soundscape"], 144000)[:6]
+    pcm16 = np.round(chunks * 32768.0).astype(np.int16)        # soundscape.wav is 16-bit: exact round trip
+    assert np.array_equal(pcm16.astype(np.float32) / np.float32(32768), chunks)
+    a = clf.predict_batch(chunks)
+    b = clf.predict_batch(pcm16)
+    assert np.array_equal(a, b)
+
+
+def test_batch_composition_is_irrelevant(clf, audio):
+    """Chunks are independent: micro-batch boundaries, batch size and order must not change a single bit."""
+    chunks = bo.slice_chunks(audio["soundscape"], 72000)[:37]
+    full = clf.predict_batch(chunks)
+    one = np.stack([clf.predict(c) for c in chunks[:3]])
+    assert np.array_equal(full[:3], one)
+    perm = np.random.default_rng(1).permutation(len(chunks))
+    assert np.array_equal(clf.predict_batch(chunks[perm]), full[perm])
+    assert clf.predict_batch(chunks[:0]).shape == (0, 6522)
+
+
+def test_topk_matches_reference_postprocessing(clf, audio):
+    chunks = bo.slice_chunks(audio["soundscape"], 144000)[:8]
+    idx, conf, logits = clf.analyze_batch(chunks, sensitivity=1.5, k=10, want_logits=True)
+    want_conf = bo.sigmoid_sensitivity(logits, 1.5)
+    widx, wconf = bo.top_k(want_conf, 10)
+    assert np.array_equal(idx, widx)
+    assert np.abs(conf - wconf).max() <= 1e-7
+    assert (np.diff(conf, axis=1) <= 0).all()
+
+
+def test_error_behaviour(clf):
+    with pytest.raises(bb.B200Error) as e:
+        clf.predict(np.zeros(1000, np.float32))
+    assert e.value.status == bb.ERR_INVALID_ARGUMENT and "input size mismatch" in str(e.value)
+    with pytest.raises(bb.B200Error):
+        clf.predict_batch(np.zeros((clf.max_batch + 1, 144000), np.float32))
+    c2 = bb.B200Classifier(max_batch=2, precision=bb.PRECISION_F32)
+    c2.close(); c2.close()                                   # idempotent Close()
+    with pytest.raises(bb.B200Error) as e:
+        c2.predict(np.zeros(144000, np.float32))
+    assert e.value.status == bb.ERR_CLOSED
+    with pytest.raises(bb.B200Error) as e:
+        bb.B200Classifier(model_data=open(bb.DEFAULT_MODEL, "rb").read()[:1 << 20])
+    assert e.value.status == bb.ERR_UNSUPPORTED_MODEL
+
+
+def test_intermediate_tensors_match_oracle(lib_path, audio):
+    """Frontend output and every block output vs the float64 oracle (fp32 truth path)."""
+    c = bb.B200Classifier(max_batch=4, micro_batch=4, precision=bb.PRECISION_F32)
+    c.keep_intermediates(True)
+    chunks = np.stack([audio["tawnyowl"][:144000], audio["soundscape"][:144000]])
+    plan = json.loads(bb.describe_model(open(bb.DEFAULT_MODEL, "rb").read()))
+    ids = [plan["frontend_out_tensor"], plan["stem"]["out_tensor"], plan["mix"]["out_tensor"]] + [b["tensors"]["out"] for b in plan["blocks"]] + [545]
+    ref = bo.Oracle(dtype=torch.float64).run(chunks, fetch=tuple(ids), batch=2)
+    c.predict_batch(chunks)
+    for t in ids:
+        r = np.asarray(ref[t], np.float64).reshape(2, -1)
+        g = c.read_tensor(t).reshape(2, -1)
+        rel = np.abs(g - r).max() / np.abs(r).max()
+        assert rel < 2e-4, (t, rel)
+    c.close()
+
+
+def test_full_size_property_linearity_of_batching(clf):
+    """BASELINE config 3 shape (synthetic pink noise + chirp): duplicated chunks give identical rows, and
+    gain-invariance of the min/max normalisation: logits(x) == logits(0.5 x) up to fp32 rounding."""
+    from bench import synth_chunks
+    x = synth_chunks(24, seed0=1234)
+    y = clf.predict_batch(np.concatenate([x, x[:8]]))
+    assert np.array_equal(y[:8], y[24:])
+    z = clf.predict_batch((x[:8] * np.float32(0.5)))
+    assert np.abs(_sig(z) - _sig(y[:8])).max() <= SIG_TOL
