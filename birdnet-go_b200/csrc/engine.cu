@@ -44,7 +44,7 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
   max_batch_ = opts.max_batch > 0 ? opts.max_batch : 256;
   micro_ = opts.micro_batch > 0 ? opts.micro_batch : 32;
   if (micro_ > max_batch_) micro_ = max_batch_;
-  precision_ = opts.precision == BNB_PRECISION_DEFAULT ? BNB_PRECISION_F32 : opts.precision;
+  precision_ = opts.precision == BNB_PRECISION_DEFAULT ? BNB_PRECISION_F16X3 : opts.precision;
   precision_name_ = precision_ == BNB_PRECISION_F16X3 ? "FP16x3(tcgen05)+FP32" : "FP32";
 
   TfModel model = parse_tflite(tflite, len);
@@ -108,6 +108,19 @@ void Engine::upload_weights(const NetPlan& P) {
       const double a = kPi * (double)k / (double)N;
       post[k] = make_float2((float)(0.5 * cos(a)), (float)(0.5 * sin(a)));
     }
+    // Re DFT of the window itself, from the file's fp32 constants, in double: W[k] = sum_n w[n] cos(2 pi k n / L)
+    std::vector<float> wdft((size_t)N);
+    {
+      const int L = S.frame_len;
+      std::vector<double> ct((size_t)L);
+      for (int i = 0; i < L; ++i) ct[i] = cos(2.0 * kPi * (double)i / (double)L);
+      for (int k = 0; k < N; ++k) {
+        double acc = 0.0;
+        for (int n = 0; n < L; ++n) acc += (double)S.window[n] * ct[(size_t)(((long long)k * n) % L)];
+        wdft[k] = (float)acc;
+      }
+    }
+    fe_.win_dft[s] = up(wdft.data(), wdft.size());
     fe_.tw[s] = up_t<float2>(tw.data(), tw.size());
     fe_.post[s] = up_t<float2>(post.data(), post.size());
     // sparse mel rows: contiguous non-zero run per band
@@ -155,26 +168,33 @@ void Engine::upload_weights(const NetPlan& P) {
     stem_tensor_ = P.stem.out_tensor; mix_tensor_ = P.mix.out_tensor;
   }
   // ---- blocks ----------------------------------------------------------------------------------------------
-  auto upconv = [&](const ConvW& c, size_t n) {
+  const bool tc = (precision_ == BNB_PRECISION_F16X3);
+  auto upconv = [&](const ConvW& c, size_t n, bool gemm = false) {
     DevConv d; d.w = up(c.w, n);
-    std::vector<float> z((size_t)c.cout, 0.f);
-    d.b = up(c.b ? c.b : z.data(), (size_t)c.cout);
+    std::vector<float> z((size_t)c.cout + 16, 0.f);      // +16: the tensor-core epilogue reads bias in float4s up to n_pad
+    if (c.b) memcpy(z.data(), c.b, (size_t)c.cout * sizeof(float));
+    d.b = up(z.data(), z.size());
+    if (gemm && tc) {                                    // fp16 hi/lo split + swizzled smem image for pw_tc.cu
+      std::vector<uint8_t> img;
+      d.tc = pw_tc_prepare(c.w, c.cout, (int)(n / (size_t)c.cout), &img);
+      d.tc_img = up_t<uint8_t>(img.data(), img.size());
+    }
     return d;
   };
   for (const BlockPlan& b : P.blocks) {
     DevBlock d; d.g = b;
-    d.expand = upconv(b.expand, (size_t)b.cexp * b.cin);
+    d.expand = upconv(b.expand, (size_t)b.cexp * b.cin, true);
     d.dw = upconv(b.dw, (size_t)9 * b.cexp);
     if (b.has_se) { d.se1 = upconv(b.se1, (size_t)b.cse * b.cexp); d.se2 = upconv(b.se2, (size_t)b.cexp * b.cse); }
-    d.proj = upconv(b.proj, (size_t)b.cout * b.cexp);
+    d.proj = upconv(b.proj, (size_t)b.cout * b.cexp, true);
     blocks_.push_back(d);
   }
   // ---- post + head ------------------------------------------------------------------------------------------
   post_g_ = P.post;
   post_mul_ = up(P.post.mul, (size_t)P.post.conv.cin);
   post_add_ = up(P.post.add, (size_t)P.post.conv.cin);
-  post_conv_ = upconv(P.post.conv, (size_t)P.post.conv.cout * P.post.conv.kh * P.post.conv.kw * P.post.conv.cin);
-  fc_ = upconv(P.head.fc, (size_t)P.head.fc.cout * P.head.fc.cin);
+  post_conv_ = upconv(P.post.conv, (size_t)P.post.conv.cout * P.post.conv.kh * P.post.conv.kw * P.post.conv.cin, true);
+  fc_ = upconv(P.head.fc, (size_t)P.head.fc.cout * P.head.fc.cin, true);
   logits_tensor_ = P.head.out_tensor;
 }
 
@@ -212,6 +232,12 @@ float* Engine::scratch(int tensor_id, float* normal, size_t per_chunk, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+void Engine::pw(const PwArgs& a, const DevConv& c, int cat, cudaStream_t s) {
+  ProfScope ps(this, cat, s);
+  if (c.tc_img) launch_pw_tc(c.tc, a, c.tc_img, s, lc_);
+  else launch_pw_conv(a, s, lc_);
+}
+
 void Engine::run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float* d_emb, cudaStream_t s) {
   views_.clear();
   // frontend
@@ -236,7 +262,7 @@ void Engine::run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float
     PwArgs ex{};
     ex.A = cur; ex.W = b.expand.w; ex.bias = b.expand.b; ex.C = e; ex.M = n * hw_in; ex.N = g.cexp; ex.K = g.cin;
     ex.rows_per_chunk = hw_in; ex.act = ACT_SILU; ex.a_mode = A_PLAIN;
-    { ProfScope ps(this, C_PW_EXPAND, s); launch_pw_conv(ex, s, lc_); }
+    pw(ex, b.expand, C_PW_EXPAND, s);
     record(g.exp_tensor, e, (size_t)hw_in * g.cexp, n);
     float* d = scratch(g.dw_tensor, ws_d_, (size_t)hw_out * g.cexp, n);
     DwArgs dw{e, b.dw.w, b.dw.b, d, n, g.in_h, g.in_w, g.cexp, g.stride, g.out_h, g.out_w};
@@ -253,7 +279,7 @@ void Engine::run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float
     PwArgs pj{};
     pj.A = d; pj.W = b.proj.w; pj.bias = b.proj.b; pj.C = out; pj.M = n * hw_out; pj.N = g.cout; pj.K = g.cexp;
     pj.rows_per_chunk = hw_out; pj.act = ACT_NONE; pj.a_mode = A_PLAIN; pj.gate = gate; pj.residual = g.residual ? cur : nullptr;
-    { ProfScope ps(this, C_PW_PROJECT, s); launch_pw_conv(pj, s, lc_); }
+    pw(pj, b.proj, C_PW_PROJECT, s);
     record(g.out_tensor, out, (size_t)hw_out * g.cout, n);
     // ping-pong the two block buffers (in keep mode `out` is a private buffer; keep the pair intact)
     if (!keep_) { nxt_normal = cur; }
@@ -267,7 +293,7 @@ void Engine::run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float
   pa.A = cur; pa.W = post_conv_.w; pa.bias = post_conv_.b; pa.C = pc; pa.M = n * q.out_w; pa.N = q.conv.cout;
   pa.K = q.conv.kh * q.conv.kw * q.conv.cin; pa.rows_per_chunk = q.out_w; pa.act = ACT_RELU; pa.a_mode = A_CONV3X3_ROW;
   pa.a_mul = post_mul_; pa.a_add = post_add_; pa.a_ch = q.conv.cin; pa.in_w = q.in_w; pa.out_w = q.out_w; pa.cin = q.conv.cin; pa.kw = q.conv.kw;
-  { ProfScope ps(this, C_POST_CONV, s); launch_pw_conv(pa, s, lc_); }
+  pw(pa, post_conv_, C_POST_CONV, s);
   record(q.conv_tensor, pc, (size_t)q.out_w * q.conv.cout, n);
   float* emb = d_emb ? d_emb : ws_emb_;
   { ProfScope ps(this, C_ROW_MEAN, s); launch_row_mean(pc, emb, n, q.out_w, q.conv.cout, s, lc_); }
@@ -275,7 +301,7 @@ void Engine::run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float
   PwArgs fa{};
   fa.A = emb; fa.W = fc_.w; fa.bias = fc_.b; fa.C = d_logits; fa.M = n; fa.N = n_species_; fa.K = emb_dim_;
   fa.rows_per_chunk = 1; fa.act = ACT_NONE; fa.a_mode = A_PLAIN;
-  { ProfScope ps(this, C_FC, s); launch_pw_conv(fa, s, lc_); }
+  pw(fa, fc_, C_FC, s);
   record(logits_tensor_, d_logits, (size_t)n_species_, n);
 }
 

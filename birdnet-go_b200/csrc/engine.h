@@ -12,10 +12,11 @@
 #include "../../include/birdnet_b200.h"
 #include "kernels.h"
 #include "net_plan.h"
+#include "pw_tc.h"
 
 namespace bnb {
 
-struct DevConv { const float* w = nullptr; const float* b = nullptr; };
+struct DevConv { const float* w = nullptr; const float* b = nullptr; PwTcLayer tc; const uint8_t* tc_img = nullptr; };
 
 struct DevBlock {
   BlockPlan g;          // geometry + tensor ids (host weight pointers are dead after upload)
@@ -57,6 +58,7 @@ class Engine {
   long long read_tensor(int tensor, float* out, size_t cap);
 
  private:
+  void pw(const PwArgs& a, const DevConv& c, int cat, cudaStream_t s);
   void run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float* d_emb, cudaStream_t s);
   float* scratch(int tensor_id, float* normal, size_t per_chunk, int n);
   void record(int tensor_id, const float* p, size_t per_chunk, int n) { if (tensor_id >= 0) views_[tensor_id] = TensorView{p, per_chunk, n}; }

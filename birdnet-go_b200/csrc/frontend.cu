@@ -34,7 +34,7 @@ constexpr int kWarps = 16;
 constexpr int kScratchPerWarp = 32 * 33;        // padded 32x32 transpose tile
 constexpr int kPost1 = 128;                     // post-processing table entries kept in smem (spec 0)
 constexpr int kPost2 = 512;
-constexpr int kSmemFloats = kSpanMax + 2048 + 1024 + 2048 + 1024 + 2 * kPost1 + 2 * kPost2 + kWarps * kScratchPerWarp + 96 * 32 * 2;
+constexpr int kSmemFloats = kSpanMax + 2048 + 1024 + 2048 + 1024 + 2 * kPost1 + 2 * kPost2 + kPost1 + kPost2 + kWarps * kScratchPerWarp + 96 * 32 * 2;
 
 __host__ __device__ constexpr int brev(int k, int bits) {
   int r = 0;
@@ -93,12 +93,13 @@ __device__ __forceinline__ float2 cmul(float2 v, float2 t) {
 }
 
 struct Smem {
-  float* span; float* win1; float* win2; float2* tw1; float2* tw2; float2* post1; float2* post2; float* scratch; float* stage;
+  float* span; float* win1; float* win2; float2* tw1; float2* tw2; float2* post1; float2* post2; float* dc1; float* dc2; float* scratch; float* stage;
   __device__ explicit Smem(float* base) {
     span = base; win1 = span + kSpanMax; win2 = win1 + 2048;
     tw1 = reinterpret_cast<float2*>(win2 + 1024); tw2 = tw1 + 1024;
     post1 = tw2 + 512; post2 = post1 + kPost1;
-    scratch = reinterpret_cast<float*>(post2 + kPost2); stage = scratch + kWarps * kScratchPerWarp;
+    dc1 = reinterpret_cast<float*>(post2 + kPost2); dc2 = dc1 + kPost1;
+    scratch = dc2 + kPost2; stage = scratch + kWarps * kScratchPerWarp;
   }
 };
 
@@ -127,12 +128,20 @@ __device__ __forceinline__ float mel_out(const float* bins, const int* start, co
 __device__ __forceinline__ void spec0_frame(const FrontendDev& P, const Smem& S, int warp, int lane, int tl) {
   float2 a[32];
   const float* xs = S.span + 278 * tl;
+  // DC compensation: X[k] = mu*W[k] + DFT((x - mu) w)[k] holds for any mu; with mu = frame mean the fp32
+  // rounding noise of the FFT scales with the AC part only (silent / DC-offset frames would otherwise drown
+  // the 1e-6-level bins the x^0.23 compression amplifies).  W = DFT of the model's own window constants (fp64 at load).
+  float mu = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const int n = lane + 32 * j;
-    const float2 v = *reinterpret_cast<const float2*>(xs + 2 * n);
-    const float2 w = *reinterpret_cast<const float2*>(S.win1 + 2 * n);
-    a[j] = make_float2(v.x * w.x, v.y * w.y);
+    a[j] = *reinterpret_cast<const float2*>(xs + 2 * (lane + 32 * j));
+    mu += a[j].x + a[j].y;
+  }
+  mu = warp_sum(mu) * (1.0f / 2048.0f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float2 w = *reinterpret_cast<const float2*>(S.win1 + 2 * (lane + 32 * j));
+    a[j] = make_float2((a[j].x - mu) * w.x, (a[j].y - mu) * w.y);
   }
   fft_dif<32, 0>(a);                                    // a[brev5(k2)] = sum_j z[l+32j] W32^(j k2)
 #pragma unroll
@@ -156,7 +165,7 @@ __device__ __forceinline__ void spec0_frame(const FrontendDev& P, const Smem& S,
       const float znx = __shfl_sync(0xffffffffu, mine.x, src), zny = __shfl_sync(0xffffffffu, mine.y, src);
       const int k = lane + 32 * k1;
       const float2 cs = S.post1[k];
-      sc[k] = 0.5f * (zk.x + znx) + cs.x * (zk.y + zny) - cs.y * (zk.x - znx);
+      sc[k] = fmaf(mu, S.dc1[k], 0.5f * (zk.x + znx) + cs.x * (zk.y + zny) - cs.y * (zk.x - znx));
     }
   }
   __syncwarp();
@@ -174,14 +183,20 @@ __device__ __forceinline__ void spec1_pair(const FrontendDev& P, const Smem& S, 
   float2 a[32];
   const float* xa = S.span + 2 * t0 + 280 * ta;         // 280*(t0+ta) - 278*t0
   const float* xb = b_valid ? xa + 280 : xa;
+  float mua = 0.f, mub = 0.f;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int n = lane + 32 * j;
-    const float2 w = *reinterpret_cast<const float2*>(S.win2 + 2 * n);
-    const float2 va = *reinterpret_cast<const float2*>(xa + 2 * n);
-    const float2 vb = *reinterpret_cast<const float2*>(xb + 2 * n);
-    a[j] = make_float2(va.x * w.x, va.y * w.y);
-    a[16 + j] = make_float2(vb.x * w.x, vb.y * w.y);
+    a[j] = *reinterpret_cast<const float2*>(xa + 2 * n);
+    a[16 + j] = *reinterpret_cast<const float2*>(xb + 2 * n);
+    mua += a[j].x + a[j].y; mub += a[16 + j].x + a[16 + j].y;
+  }
+  mua = warp_sum(mua) * (1.0f / 1024.0f); mub = warp_sum(mub) * (1.0f / 1024.0f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 w = *reinterpret_cast<const float2*>(S.win2 + 2 * (lane + 32 * j));
+    a[j] = make_float2((a[j].x - mua) * w.x, (a[j].y - mua) * w.y);
+    a[16 + j] = make_float2((a[16 + j].x - mub) * w.x, (a[16 + j].y - mub) * w.y);
   }
   fft_dif<16, 0>(a);                                    // a[f*16 + brev4(k2)] = A_f[l][k2]
   fft_dif<16, 16>(a);
@@ -203,6 +218,7 @@ __device__ __forceinline__ void spec1_pair(const FrontendDev& P, const Smem& S, 
   fft_dif<32, 0>(a);                                    // lane = k2 + 16 f: a[brev5(k1)] = Z_f[k2 + 16 k1]
   const int f = lane >> 4, k2 = lane & 15;
   const int src = ((16 - k2) & 15) + 16 * f;
+  const float mu = f ? mub : mua;
 #pragma unroll
   for (int k1 = 0; k1 < 32; ++k1) {
     if (k1 < P.nk1[1]) {
@@ -211,7 +227,7 @@ __device__ __forceinline__ void spec1_pair(const FrontendDev& P, const Smem& S, 
       const float znx = __shfl_sync(0xffffffffu, mine.x, src), zny = __shfl_sync(0xffffffffu, mine.y, src);
       const int k = k2 + 16 * k1;
       const float2 cs = S.post2[k];
-      sc[f * 512 + k] = 0.5f * (zk.x + znx) + cs.x * (zk.y + zny) - cs.y * (zk.x - znx);
+      sc[f * 512 + k] = fmaf(mu, S.dc2[k], 0.5f * (zk.x + znx) + cs.x * (zk.y + zny) - cs.y * (zk.x - znx));
     }
   }
   __syncwarp();
@@ -277,6 +293,8 @@ frontend_kernel(const FrontendDev P, const void* __restrict__ pcm, const float* 
   for (int i = tid; i < 512; i += blockDim.x) S.tw2[i] = __ldg(P.tw[1] + i);
   for (int i = tid; i < kPost1; i += blockDim.x) S.post1[i] = __ldg(P.post[0] + i);
   for (int i = tid; i < kPost2; i += blockDim.x) S.post2[i] = __ldg(P.post[1] + i);
+  for (int i = tid; i < kPost1; i += blockDim.x) S.dc1[i] = __ldg(P.win_dft[0] + i);
+  for (int i = tid; i < kPost2; i += blockDim.x) S.dc2[i] = __ldg(P.win_dft[1] + i);
   __syncthreads();
 
   // spectrogram 0: frames warp and warp+16; spectrogram 1: frames (2 warp, 2 warp + 1)

@@ -28,6 +28,7 @@ struct FrontendDev {
   const float* win[2];       // [2048], [1024]
   const float2* tw[2];       // [32][32], [16][32]: exp(-2*pi*i*l*k2/N), indexed [k2][l]
   const float2* post[2];     // [N/2]: 0.5*(cos, sin)(pi*k/(N/2))  (N/2 = complex FFT length)
+  const float* win_dft[2];   // [N/2]: Re DFT of the window constants (fp64 at load) for the DC compensation
   const int* mel_start[2];   // [96]
   const int* mel_cnt[2];     // [96]
   const float* mel_w[2];     // [96][mel_stride]

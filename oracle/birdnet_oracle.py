@@ -146,7 +146,7 @@ class Oracle:
         chunks = np.ascontiguousarray(chunks, np.float32)
         if chunks.ndim != 2 or chunks.shape[1] != NUM_SAMPLES:
             raise ValueError("input size mismatch: expected %d samples, got %s" % (NUM_SAMPLES, chunks.shape[1:]))
-        want = list(fetch) + [T_LOGITS]
+        want = list(dict.fromkeys(list(fetch) + [T_LOGITS]))
         acc = {k: [] for k in want}
         for i in range(0, len(chunks), batch):
             r = self.interp.run(torch.from_numpy(chunks[i:i + batch]), fetch=fetch)

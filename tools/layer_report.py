@@ -38,6 +38,7 @@ def main():
     ids += [544, plan["post"]["emb_tensor"], plan["head"]["out_tensor"]]
     ref = bo.Oracle(dtype=torch.float64).run(chunks, fetch=tuple(ids), batch=4)
     clf = bb.B200Classifier(max_batch=8, micro_batch=8, precision=prec)
+    logits = None
     clf.keep_intermediates(True)
     logits = clf.predict_batch(chunks)
     lines = ["precision=%s device=%s" % (a.precision, clf.runtime_info())]
