@@ -214,19 +214,30 @@ pw_conv_kernel(const PwArgs a) {
 // 3x3 depthwise conv + bias + SiLU, NHWC, zero padding 1 on each side (stride 1 SAME, or the
 // reference's explicit PAD(1,1) + VALID stride 2).  One thread = 4 channels of one output pixel.
 // =================================================================================================
-__global__ void __launch_bounds__(256)
+// Grid (parts, B, channel groups).  A thread owns 4 channels (its 9 taps + bias live in registers) and walks
+// over the output pixels of its part; the SiLU outputs are also summed per channel so the squeeze-excite mean
+// comes for free: partial[b][part][c] (deterministic, no atomics), reduced by se_mlp_kernel.
+constexpr int kDwMaxThreads = 256;
+
+__global__ void __launch_bounds__(kDwMaxThreads)
 dw_conv_kernel(const DwArgs a) {
+  __shared__ float4 s_red[kDwMaxThreads];
+  const int c4_per_cta = a.c4_per_cta, lanes = blockDim.x / c4_per_cta;    // pixel lanes per CTA
+  const int cl = threadIdx.x % c4_per_cta, pl = threadIdx.x / c4_per_cta;
+  const int c4 = blockIdx.z * c4_per_cta + cl, b = blockIdx.y, part = blockIdx.x;
   const int c4n = a.C / 4;
-  const long long total = (long long)a.B * a.Ho * a.Wo * c4n;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(idx % c4n);
-    long long r = idx / c4n;
-    const int wo = (int)(r % a.Wo); r /= a.Wo;
-    const int ho = (int)(r % a.Ho);
-    const int b = (int)(r / a.Ho);
-    const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias) + c4);
+  const int npix = a.Ho * a.Wo, per = (npix + gridDim.x - 1) / gridDim.x;
+  const int p_begin = part * per, p_end = min(npix, p_begin + per);
+  float4 w[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const float4*>(a.w + t * a.C) + c4);
+  const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias) + c4);
+  const float4* inb = reinterpret_cast<const float4*>(a.in + (size_t)b * a.H * a.W * a.C) + c4;
+  float4* outb = reinterpret_cast<float4*>(a.out + (size_t)b * npix * a.C) + c4;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = p_begin + pl; p < p_end; p += lanes) {
+    const int ho = p / a.Wo, wo = p - ho * a.Wo;
     float4 acc = bz;
-    const float* inb = a.in + (size_t)b * a.H * a.W * a.C;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int hi = ho * a.stride - 1 + kh;
@@ -235,20 +246,29 @@ dw_conv_kernel(const DwArgs a) {
       for (int kw = 0; kw < 3; ++kw) {
         const int wi = wo * a.stride - 1 + kw;
         if (wi < 0 || wi >= a.W) continue;
-        const float4 x = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)hi * a.W + wi) * a.C) + c4);
-        const float4 w = __ldg(reinterpret_cast<const float4*>(a.w + (kh * 3 + kw) * a.C) + c4);
-        acc.x = fmaf(x.x, w.x, acc.x); acc.y = fmaf(x.y, w.y, acc.y); acc.z = fmaf(x.z, w.z, acc.z); acc.w = fmaf(x.w, w.w, acc.w);
+        const float4 x = __ldg(inb + (size_t)(hi * a.W + wi) * c4n);
+        const float4 ww = w[kh * 3 + kw];
+        acc.x = fmaf(x.x, ww.x, acc.x); acc.y = fmaf(x.y, ww.y, acc.y); acc.z = fmaf(x.z, ww.z, acc.z); acc.w = fmaf(x.w, ww.w, acc.w);
       }
     }
     acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w);
-    reinterpret_cast<float4*>(a.out)[idx] = acc;
+    outb[(size_t)p * c4n] = acc;
+    sum.x += acc.x; sum.y += acc.y; sum.z += acc.z; sum.w += acc.w;
+  }
+  if (a.partial != nullptr) {
+    s_red[threadIdx.x] = sum;
+    __syncthreads();
+    if (pl == 0) {
+      for (int l = 1; l < lanes; ++l) { const float4 o = s_red[l * c4_per_cta + cl]; sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w; }
+      reinterpret_cast<float4*>(a.partial + ((size_t)b * gridDim.x + part) * a.C)[c4] = sum;
+    }
   }
 }
 
 // =================================================================================================
 // Squeeze-excite gate: gate[b][c] = sigmoid(W2 * silu(W1 * mean_hw(x[b]) + b1) + b2).  One CTA per chunk.
 // =================================================================================================
-constexpr int kSeThreads = 512;
+constexpr int kSeThreads = 256;
 constexpr int kSeMaxC = 1536, kSeMaxS = 64;
 
 __global__ void __launch_bounds__(kSeThreads)
@@ -256,17 +276,11 @@ se_gate_kernel(const SeArgs a) {
   __shared__ float s_mean[kSeMaxC];
   __shared__ float s_hidden[kSeMaxS];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* x = a.x + (size_t)b * a.HW * a.C;
-  // channel sums: consecutive threads -> consecutive channels (coalesced rows)
+  // channel means from the per-part sums the depthwise kernel left behind
   for (int c = tid; c < a.C; c += kSeThreads) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int p = 0;
-    for (; p + 4 <= a.HW; p += 4) {
-      s0 += __ldg(x + (size_t)(p + 0) * a.C + c); s1 += __ldg(x + (size_t)(p + 1) * a.C + c);
-      s2 += __ldg(x + (size_t)(p + 2) * a.C + c); s3 += __ldg(x + (size_t)(p + 3) * a.C + c);
-    }
-    for (; p < a.HW; ++p) s0 += __ldg(x + (size_t)p * a.C + c);
-    s_mean[c] = ((s0 + s1) + (s2 + s3)) / (float)a.HW;
+    float s = 0.f;
+    for (int p = 0; p < a.parts; ++p) s += __ldg(a.partial + ((size_t)b * a.parts + p) * a.C + c);
+    s_mean[c] = s / (float)a.HW;
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
@@ -279,9 +293,8 @@ se_gate_kernel(const SeArgs a) {
   }
   __syncthreads();
   for (int c = tid; c < a.C; c += kSeThreads) {
-    const float* w = a.w2 + (size_t)c * a.Cse;
     float s = __ldg(a.b2 + c);
-    for (int j = 0; j < a.Cse; ++j) s = fmaf(s_hidden[j], __ldg(w + j), s);
+    for (int j = 0; j < a.Cse; ++j) s = fmaf(s_hidden[j], __ldg(a.w2t + (size_t)j * a.C + c), s);   // w2t: [Cse][C] (transposed at load)
     a.gate[(size_t)b * a.C + c] = sigmoid_f(s);
   }
 }
@@ -311,12 +324,30 @@ void launch_pw_conv(const PwArgs& a, cudaStream_t s, LaunchCounter& lc) {
   BNB_LAUNCH_CHECK(lc);
 }
 
-void launch_dw_conv(const DwArgs& a, cudaStream_t s, LaunchCounter& lc) {
-  const long long total = (long long)a.B * a.Ho * a.Wo * (a.C / 4);
-  long long blocks = ceil_div_ll(total, 256);
-  const long long cap = (long long)kNumSMs * 32;
-  if (blocks > cap) blocks = cap;
-  dw_conv_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+int dw_parts(int B, int Ho, int Wo, int C) {
+  // enough CTAs to fill the machine (~4 per SM), at least ~8 pixels per pixel-lane
+  const int c4n = C / 4;
+  const int groups = (c4n + kDwMaxThreads - 1) / kDwMaxThreads;
+  const int c4_per_cta = c4n / groups;
+  const int lanes = kDwMaxThreads / c4_per_cta > 0 ? kDwMaxThreads / c4_per_cta : 1;
+  const int npix = Ho * Wo;
+  int parts = (4 * kNumSMs + B * groups - 1) / (B * groups);
+  const int max_parts = (npix + 8 * lanes - 1) / (8 * lanes);
+  if (parts > max_parts) parts = max_parts;
+  if (parts < 1) parts = 1;
+  return parts;
+}
+
+void launch_dw_conv(const DwArgs& a0, cudaStream_t s, LaunchCounter& lc) {
+  DwArgs a = a0;
+  const int c4n = a.C / 4;
+  const int groups = (c4n + kDwMaxThreads - 1) / kDwMaxThreads;
+  if (c4n % groups) throw std::runtime_error("dw_conv: channel count not divisible into CTA groups");
+  a.c4_per_cta = c4n / groups;
+  const int lanes = kDwMaxThreads / a.c4_per_cta > 0 ? kDwMaxThreads / a.c4_per_cta : 1;
+  const int parts = a.parts > 0 ? a.parts : dw_parts(a.B, a.Ho, a.Wo, a.C);
+  dim3 grid(parts, a.B, groups);
+  dw_conv_kernel<<<grid, lanes * a.c4_per_cta, 0, s>>>(a);
   BNB_LAUNCH_CHECK(lc);
 }
 

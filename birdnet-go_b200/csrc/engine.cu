@@ -185,7 +185,14 @@ void Engine::upload_weights(const NetPlan& P) {
     DevBlock d; d.g = b;
     d.expand = upconv(b.expand, (size_t)b.cexp * b.cin, true);
     d.dw = upconv(b.dw, (size_t)9 * b.cexp);
-    if (b.has_se) { d.se1 = upconv(b.se1, (size_t)b.cse * b.cexp); d.se2 = upconv(b.se2, (size_t)b.cexp * b.cse); }
+    if (b.has_se) {
+      d.se1 = upconv(b.se1, (size_t)b.cse * b.cexp);
+      ConvW t = b.se2;                                   // second SE FC stored transposed [Cse][C] for coalesced reads
+      std::vector<float> wt((size_t)b.cse * b.cexp);
+      for (int c = 0; c < b.cexp; ++c) for (int j = 0; j < b.cse; ++j) wt[(size_t)j * b.cexp + c] = b.se2.w[(size_t)c * b.cse + j];
+      t.w = wt.data();
+      d.se2 = upconv(t, (size_t)b.cexp * b.cse);
+    }
     d.proj = upconv(b.proj, (size_t)b.cout * b.cexp, true);
     blocks_.push_back(d);
   }
@@ -200,26 +207,43 @@ void Engine::upload_weights(const NetPlan& P) {
 
 void Engine::alloc_workspace() {
   auto dmalloc = [&](size_t floats) { void* p = nullptr; BNB_CUDA(cudaMalloc(&p, std::max<size_t>(floats, 4) * sizeof(float))); allocs_.push_back(p); return static_cast<float*>(p); };
-  const size_t mb = (size_t)micro_;
-  cap_x_ = (size_t)stem_.out_h * (stem_.out_w / 2) * 24; cap_e_ = 0; cap_d_ = 0; cap_g_ = 0;
-  for (const DevBlock& b : blocks_) {
-    cap_e_ = std::max(cap_e_, (size_t)b.g.in_h * b.g.in_w * b.g.cexp);
-    cap_d_ = std::max(cap_d_, (size_t)b.g.out_h * b.g.out_w * b.g.cexp);
-    cap_x_ = std::max(cap_x_, (size_t)b.g.out_h * b.g.out_w * b.g.cout);
-    cap_g_ = std::max(cap_g_, (size_t)b.g.cexp);
+  // Phase split: blocks whose input map has >= 256 pixels per chunk run per micro-batch (their activations are MBs per
+  // chunk and must stay in L2); the rest (<= 96 pixels per chunk) run once over the whole batch so that their GEMMs have
+  // enough rows to fill 148 SMs.
+  split_ = (int)blocks_.size();
+  for (size_t i = 0; i < blocks_.size(); ++i) if (blocks_[i].g.in_h * blocks_[i].g.in_w < 256) { split_ = (int)i; break; }
+  if (split_ == 0) split_ = 1;
+  for (int ph = 0; ph < 2; ++ph) {
+    Work& w = work_[ph];
+    w.cap_n = ph == 0 ? (size_t)micro_ : (size_t)max_batch_;
+    size_t cx = ph == 0 ? (size_t)stem_.out_h * (stem_.out_w / 2) * 24 : 0, ce = 0, cd = 0, cg = 0;
+    const int lo = ph == 0 ? 0 : split_, hi = ph == 0 ? split_ : (int)blocks_.size();
+    for (int i = lo; i < hi; ++i) {
+      const BlockPlan& g = blocks_[i].g;
+      ce = std::max(ce, (size_t)g.in_h * g.in_w * g.cexp);
+      cd = std::max(cd, (size_t)g.out_h * g.out_w * g.cexp);
+      cx = std::max(cx, (size_t)g.out_h * g.out_w * g.cout);
+      cx = std::max(cx, (size_t)g.in_h * g.in_w * g.cin);
+      cg = std::max(cg, (size_t)g.cexp);
+    }
+    w.x0 = dmalloc(w.cap_n * cx); w.x1 = dmalloc(w.cap_n * cx);
+    w.e = dmalloc(w.cap_n * ce); w.d = dmalloc(w.cap_n * cd); w.g = dmalloc(w.cap_n * cg);
+    w.sep = dmalloc(w.cap_n * kMaxDwParts * cg);
   }
+  const size_t mb = (size_t)micro_, bb = (size_t)max_batch_;
   ws_partial_ = dmalloc(mb * kMinMaxParts * 2);
   ws_fe_ = dmalloc(mb * fe_.n_mel * fe_.n_frames * 2);
-  ws_x0_ = dmalloc(mb * cap_x_); ws_x1_ = dmalloc(mb * cap_x_);
-  ws_e_ = dmalloc(mb * cap_e_); ws_d_ = dmalloc(mb * cap_d_); ws_g_ = dmalloc(mb * cap_g_);
-  ws_pc_ = dmalloc(mb * post_g_.out_w * post_g_.conv.cout);
-  ws_emb_ = dmalloc(mb * emb_dim_);
+  const BlockPlan& gs = blocks_[split_ - 1].g;
+  mid_sz_ = (size_t)gs.out_h * gs.out_w * gs.cout;
+  ws_mid_ = dmalloc(bb * mid_sz_);
+  ws_pc_ = dmalloc(bb * post_g_.out_w * post_g_.conv.cout);
+  ws_emb_ = dmalloc(bb * emb_dim_);
 }
 
 float* Engine::scratch(int tensor_id, float* normal, size_t per_chunk, int n) {
   if (!keep_ || tensor_id < 0) return normal;
   auto it = keep_bufs_.find(tensor_id);
-  const size_t need = per_chunk * (size_t)micro_;
+  const size_t need = per_chunk * (size_t)std::max(micro_, n);
   if (it == keep_bufs_.end() || it->second.second < need) {
     if (it != keep_bufs_.end()) cudaFree(it->second.first);
     void* p = nullptr;
@@ -227,7 +251,6 @@ float* Engine::scratch(int tensor_id, float* normal, size_t per_chunk, int n) {
     keep_bufs_[tensor_id] = {static_cast<float*>(p), need};
     return static_cast<float*>(p);
   }
-  (void)n;
   return it->second.first;
 }
 
@@ -238,40 +261,30 @@ void Engine::pw(const PwArgs& a, const DevConv& c, int cat, cudaStream_t s) {
   else launch_pw_conv(a, s, lc_);
 }
 
-void Engine::run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float* d_emb, cudaStream_t s) {
-  views_.clear();
-  // frontend
-  { ProfScope ps(this, C_MINMAX, s); launch_minmax(d_pcm, fmt, n, n_samples_, ws_partial_, s, lc_); }
-  const size_t fe_sz = (size_t)fe_.n_mel * fe_.n_frames * 2;
-  float* fe_out = scratch(fe_tensor_, ws_fe_, fe_sz, n);
-  { ProfScope ps(this, C_FRONTEND, s); launch_frontend(fe_, d_pcm, fmt, n, ws_partial_, fe_out, s, lc_); }
-  record(fe_tensor_, fe_out, fe_sz, n);
-  // stem + pool mix
-  const size_t stem_sz = (size_t)stem_.out_h * stem_.out_w * 24, mix_sz = stem_sz / 2;
-  float* stem_dump = keep_ ? scratch(stem_tensor_, nullptr, stem_sz, n) : nullptr;
-  float* cur = scratch(mix_tensor_, ws_x0_, mix_sz, n);
-  float* nxt_normal = ws_x1_;
-  { ProfScope ps(this, C_STEM_MIX, s); launch_stem_mix(stem_, fe_out, stem_dump, cur, n, s, lc_); }
-  if (stem_dump) record(stem_tensor_, stem_dump, stem_sz, n);
-  record(mix_tensor_, cur, mix_sz, n);
-  // MBConv blocks
-  for (const DevBlock& b : blocks_) {
+float* Engine::run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream_t s) {
+  float* nxt_normal = (cur == w.x0) ? w.x1 : w.x0;
+  for (int bi = lo; bi < hi; ++bi) {
+    const DevBlock& b = blocks_[bi];
     const BlockPlan& g = b.g;
     const int hw_in = g.in_h * g.in_w, hw_out = g.out_h * g.out_w;
-    float* e = scratch(g.exp_tensor, ws_e_, (size_t)hw_in * g.cexp, n);
+    float* e = scratch(g.exp_tensor, w.e, (size_t)hw_in * g.cexp, n);
     PwArgs ex{};
     ex.A = cur; ex.W = b.expand.w; ex.bias = b.expand.b; ex.C = e; ex.M = n * hw_in; ex.N = g.cexp; ex.K = g.cin;
     ex.rows_per_chunk = hw_in; ex.act = ACT_SILU; ex.a_mode = A_PLAIN;
     pw(ex, b.expand, C_PW_EXPAND, s);
     record(g.exp_tensor, e, (size_t)hw_in * g.cexp, n);
-    float* d = scratch(g.dw_tensor, ws_d_, (size_t)hw_out * g.cexp, n);
-    DwArgs dw{e, b.dw.w, b.dw.b, d, n, g.in_h, g.in_w, g.cexp, g.stride, g.out_h, g.out_w};
+    float* d = scratch(g.dw_tensor, w.d, (size_t)hw_out * g.cexp, n);
+    DwArgs dw{};
+    dw.in = e; dw.w = b.dw.w; dw.bias = b.dw.b; dw.out = d; dw.B = n; dw.H = g.in_h; dw.W = g.in_w; dw.C = g.cexp;
+    dw.stride = g.stride; dw.Ho = g.out_h; dw.Wo = g.out_w;
+    dw.parts = std::min(kMaxDwParts, dw_parts(n, g.out_h, g.out_w, g.cexp));
+    dw.partial = g.has_se ? w.sep : nullptr;
     { ProfScope ps(this, C_DW, s); launch_dw_conv(dw, s, lc_); }
     record(g.dw_tensor, d, (size_t)hw_out * g.cexp, n);
     float* gate = nullptr;
     if (g.has_se) {
-      gate = scratch(g.gate_tensor, ws_g_, (size_t)g.cexp, n);
-      SeArgs se{d, b.se1.w, b.se1.b, b.se2.w, b.se2.b, gate, n, hw_out, g.cexp, g.cse};
+      gate = scratch(g.gate_tensor, w.g, (size_t)g.cexp, n);
+      SeArgs se{w.sep, b.se1.w, b.se1.b, b.se2.w, b.se2.b, gate, n, hw_out, g.cexp, g.cse, dw.parts};
       { ProfScope ps(this, C_SE, s); launch_se_gate(se, s, lc_); }
       record(g.gate_tensor, gate, (size_t)g.cexp, n);
     }
@@ -281,12 +294,35 @@ void Engine::run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float
     pj.rows_per_chunk = hw_out; pj.act = ACT_NONE; pj.a_mode = A_PLAIN; pj.gate = gate; pj.residual = g.residual ? cur : nullptr;
     pw(pj, b.proj, C_PW_PROJECT, s);
     record(g.out_tensor, out, (size_t)hw_out * g.cout, n);
-    // ping-pong the two block buffers (in keep mode `out` is a private buffer; keep the pair intact)
-    if (!keep_) { nxt_normal = cur; }
+    if (!keep_) nxt_normal = cur;      // ping-pong (in keep mode `out` is a private buffer)
     cur = out;
-    if (!keep_) { /* cur now points at the former nxt_normal; nxt_normal at the former cur */ }
   }
-  // post: relu(x*mul+add) -> KxK VALID conv + ReLU -> mean over the remaining time positions -> embedding
+  return cur;
+}
+
+// frontend -> stem -> blocks [0, split_) for one micro-batch; result (the split-point tensor) goes to `mid`
+void Engine::run_front(const void* d_pcm, int fmt, int n, float* mid, cudaStream_t s) {
+  Work& w = work_[0];
+  { ProfScope ps(this, C_MINMAX, s); launch_minmax(d_pcm, fmt, n, n_samples_, ws_partial_, s, lc_); }
+  const size_t fe_sz = (size_t)fe_.n_mel * fe_.n_frames * 2;
+  float* fe_out = scratch(fe_tensor_, ws_fe_, fe_sz, n);
+  { ProfScope ps(this, C_FRONTEND, s); launch_frontend(fe_, d_pcm, fmt, n, ws_partial_, fe_out, s, lc_); }
+  record(fe_tensor_, fe_out, fe_sz, n);
+  const size_t stem_sz = (size_t)stem_.out_h * stem_.out_w * 24, mix_sz = stem_sz / 2;
+  float* stem_dump = keep_ ? scratch(stem_tensor_, nullptr, stem_sz, n) : nullptr;
+  float* cur = scratch(mix_tensor_, w.x0, mix_sz, n);
+  { ProfScope ps(this, C_STEM_MIX, s); launch_stem_mix(stem_, fe_out, stem_dump, cur, n, s, lc_); }
+  if (stem_dump) record(stem_tensor_, stem_dump, stem_sz, n);
+  record(mix_tensor_, cur, mix_sz, n);
+  float* out = run_blocks(0, split_, cur, n, w, s);
+  BNB_CUDA(cudaMemcpyAsync(mid, out, (size_t)n * mid_sz_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+
+// blocks [split_, end) -> post conv -> embedding -> FC head over `n` chunks at once
+void Engine::run_back(const float* mid, int n, float* d_logits, float* d_emb, cudaStream_t s) {
+  Work& w = work_[1];
+  BNB_CUDA(cudaMemcpyAsync(w.x0, mid, (size_t)n * mid_sz_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  float* cur = run_blocks(split_, (int)blocks_.size(), w.x0, n, w, s);
   const PostPlan& q = post_g_;
   float* pc = scratch(q.conv_tensor, ws_pc_, (size_t)q.out_w * q.conv.cout, n);
   PwArgs pa{};
@@ -308,11 +344,15 @@ void Engine::run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float
 void Engine::predict_device(const void* d_pcm, int fmt, int B, float* d_logits, float* d_emb, cudaStream_t s) {
   BNB_CUDA(cudaSetDevice(device_));
   if (!s) s = compute_;
+  views_.clear();
   const size_t cb = (size_t)n_samples_ * fmt_bytes(fmt);
-  for (int i = 0; i < B; i += micro_) {
-    const int n = std::min(micro_, B - i);
-    run_micro(static_cast<const char*>(d_pcm) + (size_t)i * cb, fmt, n, d_logits + (size_t)i * n_species_,
-              d_emb ? d_emb + (size_t)i * emb_dim_ : nullptr, s);
+  for (int j = 0; j < B; j += max_batch_) {                       // back-phase capacity
+    const int nb = std::min(max_batch_, B - j);
+    for (int i = 0; i < nb; i += micro_) {
+      const int n = std::min(micro_, nb - i);
+      run_front(static_cast<const char*>(d_pcm) + (size_t)(j + i) * cb, fmt, n, ws_mid_ + (size_t)i * mid_sz_, s);
+    }
+    run_back(ws_mid_, nb, d_logits + (size_t)j * n_species_, d_emb ? d_emb + (size_t)j * emb_dim_ : nullptr, s);
   }
 }
 
@@ -369,6 +409,7 @@ void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, in
   if (k > topk_cap_) throw std::invalid_argument("k exceeds the top-k capacity (64)");
   const size_t cb = (size_t)n_samples_ * fmt_bytes(fmt);
   const bool src_pinned = is_pinned(pcm);
+  views_.clear();
   BNB_CUDA(cudaEventRecord(ev_start_, compute_));
   // H2D per micro-batch on the copy stream; compute waits per micro-batch
   int mi = 0;
@@ -382,9 +423,9 @@ void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, in
     BNB_CUDA(cudaMemcpyAsync(static_cast<char*>(d_in_) + (size_t)i * cb, src, (size_t)n * cb, cudaMemcpyHostToDevice, copy_));
     BNB_CUDA(cudaEventRecord(ev_h2d_[mi], copy_));
     BNB_CUDA(cudaStreamWaitEvent(compute_, ev_h2d_[mi], 0));
-    run_micro(static_cast<const char*>(d_in_) + (size_t)i * cb, fmt, n, d_logits_ + (size_t)i * n_species_,
-              d_emb_ + (size_t)i * emb_dim_, compute_);
+    run_front(static_cast<const char*>(d_in_) + (size_t)i * cb, fmt, n, ws_mid_ + (size_t)i * mid_sz_, compute_);
   }
+  run_back(ws_mid_, B, d_logits_, d_emb_, compute_);
   if (k > 0) {
     { ProfScope ps(this, C_TOPK, compute_); launch_sigmoid_topk(d_logits_, B, n_species_, sensitivity, k, d_idx_, d_conf_, compute_, lc_); }
     BNB_CUDA(cudaMemcpyAsync(idx, d_idx_, (size_t)B * k * 4, cudaMemcpyDeviceToHost, compute_));

@@ -59,7 +59,11 @@ class Engine {
 
  private:
   void pw(const PwArgs& a, const DevConv& c, int cat, cudaStream_t s);
-  void run_micro(const void* d_pcm, int fmt, int n, float* d_logits, float* d_emb, cudaStream_t s);
+  static constexpr int kMaxDwParts = 32;
+  struct Work { float *x0 = nullptr, *x1 = nullptr, *e = nullptr, *d = nullptr, *g = nullptr, *sep = nullptr; size_t cap_n = 0; };
+  float* run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream_t s);
+  void run_front(const void* d_pcm, int fmt, int n, float* mid, cudaStream_t s);
+  void run_back(const float* mid, int n, float* d_logits, float* d_emb, cudaStream_t s);
   float* scratch(int tensor_id, float* normal, size_t per_chunk, int n);
   void record(int tensor_id, const float* p, size_t per_chunk, int n) { if (tensor_id >= 0) views_[tensor_id] = TensorView{p, per_chunk, n}; }
   void upload_weights(const NetPlan& P);
@@ -94,9 +98,10 @@ class Engine {
   DevConv fc_; int logits_tensor_ = -1;
 
   // workspaces (capacity: micro_ chunks)
-  float *ws_partial_ = nullptr, *ws_fe_ = nullptr, *ws_x0_ = nullptr, *ws_x1_ = nullptr, *ws_e_ = nullptr, *ws_d_ = nullptr,
-        *ws_g_ = nullptr, *ws_pc_ = nullptr, *ws_emb_ = nullptr;
-  size_t cap_x_ = 0, cap_e_ = 0, cap_d_ = 0, cap_g_ = 0;
+  float *ws_partial_ = nullptr, *ws_fe_ = nullptr, *ws_mid_ = nullptr, *ws_pc_ = nullptr, *ws_emb_ = nullptr;
+  Work work_[2];          // [0] front phase (micro-batch), [1] back phase (whole batch)
+  int split_ = 0;         // first block of the back phase
+  size_t mid_sz_ = 0;     // floats per chunk of the split-point tensor
   std::map<int, std::pair<float*, size_t>> keep_bufs_;   // tensor id -> (device buffer, capacity in floats)
   std::map<int, TensorView> views_;
 

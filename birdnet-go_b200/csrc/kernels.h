@@ -75,15 +75,19 @@ void launch_pw_conv(const PwArgs& a, cudaStream_t s, LaunchCounter& lc);
 struct DwArgs {
   const float* in; const float* w; const float* bias; float* out;  // w: [3][3][C]
   int B, H, W, C, stride, Ho, Wo;
+  float* partial;   // [B][parts][C] per-part channel sums of the output (for squeeze-excite) or null
+  int parts;        // pixel partitions per chunk (0 = let the launcher choose via dw_parts)
+  int c4_per_cta;   // set by the launcher
 };
+int dw_parts(int B, int Ho, int Wo, int C);
 void launch_dw_conv(const DwArgs& a, cudaStream_t s, LaunchCounter& lc);
 
 struct SeArgs {
-  const float* x;   // [B][HW][C]
-  const float* w1; const float* b1;  // [Cse][C]
-  const float* w2; const float* b2;  // [C][Cse]
+  const float* partial;  // [B][parts][C] channel sums from the depthwise kernel
+  const float* w1; const float* b1;   // [Cse][C]
+  const float* w2t; const float* b2;  // [Cse][C]  (second FC transposed at load)
   float* gate;      // [B][C]
-  int B, HW, C, Cse;
+  int B, HW, C, Cse, parts;
 };
 void launch_se_gate(const SeArgs& a, cudaStream_t s, LaunchCounter& lc);
 

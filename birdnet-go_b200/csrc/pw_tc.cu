@@ -98,17 +98,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-struct SmemLayout {
-  uint32_t a_hi, a_lo, b_hi, b_lo;   // byte offsets of stage 0 from the 1024-aligned base
-  uint32_t stage_bytes;
-};
-
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
   if (act == ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 
+// Shared-memory stage: [A: 32 KB][B hi: bn*128][B lo: bn*128].  The A buffer first receives the RAW fp32 rows
+// (128 rows x 256 B, one cp.async.bulk per row, fully asynchronous => many stages of global latency in flight), is
+// read into registers by the 4 producer warps, and is then overwritten IN PLACE by the fp16 hi (16 KB) and lo (16 KB)
+// 128B-swizzled K-major tiles the MMA consumes.
 __global__ void __launch_bounds__(kThreads, 1)
 pw_tc_kernel(const PwTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -117,18 +116,19 @@ pw_tc_kernel(const PwTcArgs a) {
   uint8_t* base_ptr = smem_raw + (base - raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const uint32_t a_bytes = kBM * 128u;                     // one fp16 [128][64] slab
-  const uint32_t b_bytes = (uint32_t)a.bn_max * 128u;      // one fp16 [bn_max][64] slab
+  const uint32_t a_bytes = kBM * 128u;                     // one fp16 [128][64] slab (16 KB); raw fp32 uses 2 of them
+  const uint32_t b_bytes = (uint32_t)a.bn * 128u;          // one fp16 [bn][64] slab
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  const uint32_t bars = base + (uint32_t)a.stages * stage_bytes;   // full[S], empty[S], tfull[2], tempty[2], tmem ptr
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
-  auto tfull_bar = [&](int b) { return bars + 8u * (2 * a.stages + b); };
-  auto tempty_bar = [&](int b) { return bars + 8u * (2 * a.stages + 2 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (size_t)a.stages * stage_bytes + 8u * (2 * a.stages + 4));
+  const uint32_t bars = base + (uint32_t)a.stages * stage_bytes;   // rawfull[S], full[S], empty[S], tfull[2], tempty[2], tmem ptr
+  auto raw_bar = [&](int s) { return bars + 8u * s; };
+  auto full_bar = [&](int s) { return bars + 8u * (a.stages + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * a.stages + s); };
+  auto tfull_bar = [&](int b) { return bars + 8u * (3 * a.stages + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (3 * a.stages + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (size_t)a.stages * stage_bytes + 8u * (3 * a.stages + 4));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), kProdThreads + 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(raw_bar(s), 1); mbar_init(full_bar(s), kProdThreads + 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -144,86 +144,129 @@ pw_tc_kernel(const PwTcArgs a) {
   const int m_tiles = (a.M + kBM - 1) / kBM;
   const int total_tiles = m_tiles * a.n_tiles;
   const int k_stages = (a.K + kBK - 1) / kBK;
+  const int a_seg = a.a_mode == A_PLAIN ? 0 : a.kw * a.cin;    // im2col: K = (K/a_seg) segments of kw*cin contiguous floats
 
   if (warp >= kProdWarp0) {
-    // ============================== A producers ==============================================
+    // ============================== A converters (4 warps) ====================================
     const int pt = threadIdx.x - kProdWarp0 * 32;           // 0..127
-    uint32_t it = 0;                                        // global stage counter
+    const int c = pt & 7, r0 = pt >> 3;                     // this thread: 16-byte chunk c of rows r0 + 16*q
+    uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / a.n_tiles) * kBM;
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
         const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        uint8_t* hi = base_ptr + (size_t)s * stage_bytes;
-        uint8_t* lo = hi + a_bytes;
+        uint8_t* buf = base_ptr + (size_t)s * stage_bytes;
+        const int k = ks * kBK + c * 8;
+        const bool k_live = k < a.k_pad;                     // chunk read by some MMA of this stage
+        float v[8][8];
+        mbar_wait(raw_bar(s), ph);
+        if (k_live) {
+          float g[8];
 #pragma unroll
-        for (int q8 = 0; q8 < 8; ++q8) {
-          const int q = q8 * kProdThreads + pt;             // chunk id: row = q / 8, 16-byte chunk c = q % 8
-          const int r = q >> 3, c = q & 7;
-          const int m = m0 + r, k = ks * kBK + c * 8;
-          if (k >= a.k_pad) continue;                        // columns no MMA of this stage reads
-          float v[8];
+          for (int q = 0; q < 8; ++q) {
+            const int r = r0 + 16 * q, m = m0 + r;
+            if (m < a.M && k < a.K) {
+              const float4 x0 = *reinterpret_cast<const float4*>(buf + r * 256 + c * 32);
+              float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (k + 4 < a.K) x1 = *reinterpret_cast<const float4*>(buf + r * 256 + c * 32 + 16);
+              v[q][0] = x0.x; v[q][1] = x0.y; v[q][2] = x0.z; v[q][3] = x0.w;
+              v[q][4] = x1.x; v[q][5] = x1.y; v[q][6] = x1.z; v[q][7] = x1.w;
+            } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.f;
-          if (m < a.M && k < a.K) {
-            const float* src;
-            if (a.a_mode == A_PLAIN) src = a.A + (size_t)m * a.K + k;
-            else {
-              const int bidx = m / a.out_w, wo = m - bidx * a.out_w;
-              const int a_seg = a.kw * a.cin, seg = k / a_seg, j = k - seg * a_seg;
-              src = a.A + ((size_t)bidx * (a.K / a_seg) * a.in_w + wo) * a.cin + (size_t)seg * a.in_w * a.cin + j;
+              for (int i = 0; i < 8; ++i) v[q][i] = 0.f;
             }
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(src));
-            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
-            if (k + 4 < a.K) {                               // K is a multiple of 4, not necessarily of 8
-              const float4 x1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-              v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-            }
-            if (a.gate) {
-              const float* g = a.gate + (size_t)(m / a.rows_per_chunk) * a.K + k;
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(g));
-              v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-              if (k + 4 < a.K) {
-                const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
-                v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+          }
+          if (a.gate) {
+            int last_chunk = -1;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int m = m0 + r0 + 16 * q;
+              if (m < a.M && k < a.K) {
+                const int chunk = m / a.rows_per_chunk;
+                if (chunk != last_chunk) {
+                  const float* gp = a.gate + (size_t)chunk * a.K + k;
+                  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
+                  float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (k + 4 < a.K) g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
+                  g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+                  last_chunk = chunk;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[q][i] *= g[i];
               }
             }
-            if (a.a_mul) {
-              const int ch = k % a.a_ch;
+          }
+          if (a.a_mul) {
+            const int ch = k % a.a_ch;
+            float mu[8], ad[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (k + i < a.K) v[i] = fmaxf(fmaf(v[i], __ldg(a.a_mul + ch + i), __ldg(a.a_add + ch + i)), 0.f);
+            for (int i = 0; i < 8; ++i) { mu[i] = (k + i < a.K) ? __ldg(a.a_mul + ch + i) : 0.f; ad[i] = (k + i < a.K) ? __ldg(a.a_add + ch + i) : 0.f; }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (m0 + r0 + 16 * q < a.M)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[q][i] = fmaxf(fmaf(v[q][i], mu[i], ad[i]), 0.f);
+          }
+        }
+        // every converter has finished READING the raw rows before anyone overwrites them with the fp16 tiles
+        asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");
+        if (k_live) {
+          uint8_t* hi = buf;
+          uint8_t* lo = buf + a_bytes;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int r = r0 + 16 * q;
+            uint32_t ph_[4], pl_[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __half h0 = __float2half_rn(v[q][2 * i]), h1 = __float2half_rn(v[q][2 * i + 1]);
+              const __half l0 = __float2half_rn(v[q][2 * i] - __half2float(h0)), l1 = __float2half_rn(v[q][2 * i + 1] - __half2float(h1));
+              ph_[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              pl_[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
             }
+            const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(hi + off) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
+            *reinterpret_cast<uint4*>(lo + off) = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
           }
-          uint32_t ph_[4], pl_[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-            const __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
-            ph_[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            pl_[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-          }
-          const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(hi + off) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
-          *reinterpret_cast<uint4*>(lo + off) = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
         }
         fence_proxy_async();
         mbar_arrive(full_bar(s));
       }
     }
   } else if (warp == kLoadWarp) {
-    // ============================== B loader ===================================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % a.n_tiles;
-        for (int ks = 0; ks < k_stages; ++ks, ++it) {
-          const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          const uint32_t dst = base + (uint32_t)s * stage_bytes + 2 * a_bytes;
-          const uint8_t* src = a.Wimg + ((size_t)nt * k_stages + ks) * (size_t)(2 * b_bytes);
-          mbar_arrive_expect_tx(full_bar(s), 2 * b_bytes);
-          bulk_g2s(dst, src, 2 * b_bytes, full_bar(s));
+    // ============================== loader warp: async bulk copies of A rows (fp32) and B slabs ==
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % a.n_tiles, m0 = (tile / a.n_tiles) * kBM;
+      const int n0 = nt * a.bn;
+      const uint32_t bn_bytes = (uint32_t)min(a.bn, a.n_pad - n0) * 128u;
+      const int rows = min(kBM, a.M - m0);
+      for (int ks = 0; ks < k_stages; ++ks, ++it) {
+        const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const int k0 = ks * kBK;
+        const uint32_t row_bytes = (uint32_t)min(kBK, a.K - k0) * 4u;
+        const uint32_t dst = base + (uint32_t)s * stage_bytes;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(raw_bar(s), row_bytes * (uint32_t)rows);
+          mbar_arrive_expect_tx(full_bar(s), 2 * bn_bytes);
+          const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
+          bulk_g2s(dst + 2 * a_bytes, wsrc, bn_bytes, full_bar(s));
+          bulk_g2s(dst + 2 * a_bytes + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, full_bar(s));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = lane + 32 * j, m = m0 + r;
+          if (r < rows) {
+            const float* src;
+            if (a.a_mode == A_PLAIN) src = a.A + (size_t)m * a.K + k0;
+            else {
+              const int bidx = m / a.out_w, wo = m - bidx * a.out_w;
+              const int seg = k0 / a_seg, j0 = k0 - seg * a_seg;
+              src = a.A + ((size_t)bidx * (a.K / a_seg) * a.in_w + wo) * a.cin + (size_t)seg * a.in_w * a.cin + j0;
+            }
+            bulk_g2s(dst + (uint32_t)r * 256u, src, row_bytes, raw_bar(s));
+          }
         }
       }
     }
@@ -233,8 +276,8 @@ pw_tc_kernel(const PwTcArgs a) {
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int nt = tile % a.n_tiles;
-        const int n0 = nt * a.bn_max;
-        const int bn = min(a.bn_max, a.n_pad - n0);
+        const int n0 = nt * a.bn;
+        const int bn = min(a.bn, a.n_pad - n0);
         const uint32_t idesc = make_idesc((uint32_t)bn);
         const int buf = tcount & 1;
         mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);
@@ -264,8 +307,8 @@ pw_tc_kernel(const PwTcArgs a) {
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
-      const int n0 = nt * a.bn_max;
-      const int bn = min(a.bn_max, a.n_pad - n0);
+      const int n0 = nt * a.bn;
+      const int bn = min(a.bn, a.n_pad - n0);
       const int buf = tcount & 1;
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
       tc_fence_after();
@@ -331,60 +374,68 @@ PwTcLayer pw_tc_prepare(const float* w, int N, int K, std::vector<uint8_t>* imag
   L.N = N; L.K = K;
   L.n_pad = (N + 15) / 16 * 16;
   L.k_pad = (K + 15) / 16 * 16;
-  L.n_tiles = (L.n_pad + 255) / 256;
-  L.bn_max = ((L.n_pad + L.n_tiles - 1) / L.n_tiles + 15) / 16 * 16;
-  L.n_tiles = (L.n_pad + L.bn_max - 1) / L.bn_max;
   L.k_stages = (K + kBK - 1) / kBK;
-  const size_t slab = (size_t)L.bn_max * 128;              // one fp16 [bn_max][64] swizzled slab
-  image->assign((size_t)L.n_tiles * L.k_stages * 2 * slab, 0);
-  for (int nt = 0; nt < L.n_tiles; ++nt)
-    for (int ks = 0; ks < L.k_stages; ++ks) {
-      uint8_t* hi = image->data() + ((size_t)nt * L.k_stages + ks) * 2 * slab;
-      uint8_t* lo = hi + slab;
-      for (int r = 0; r < L.bn_max; ++r) {
-        const int n = nt * L.bn_max + r;
-        if (n >= N) continue;
-        for (int kc = 0; kc < kBK; ++kc) {
-          const int k = ks * kBK + kc;
-          if (k >= K) break;
-          const float x = w[(size_t)n * K + k];
-          const __half h = __float2half_rn(x);
-          const __half l = __float2half_rn(x - __half2float(h));
-          const int c = kc >> 3, e = kc & 7;
-          const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((c ^ (r & 7)) << 4) + (size_t)e * 2;
-          const unsigned short hb = __half_as_ushort(h), lb = __half_as_ushort(l);
-          memcpy(hi + off, &hb, 2); memcpy(lo + off, &lb, 2);
-        }
+  // image layout: [k_stage][hi | lo][n_pad rows][128 B], rows 128B-swizzled in 8-row groups, so ANY row range
+  // [n0, n0 + bn) (multiples of 8) of one k-stage is one contiguous byte range => the N tiling is a launch-time choice.
+  const size_t plane = (size_t)L.n_pad * 128;
+  image->assign((size_t)L.k_stages * 2 * plane, 0);
+  for (int ks = 0; ks < L.k_stages; ++ks) {
+    uint8_t* hi = image->data() + (size_t)ks * 2 * plane;
+    uint8_t* lo = hi + plane;
+    for (int n = 0; n < N; ++n)
+      for (int kc = 0; kc < kBK; ++kc) {
+        const int k = ks * kBK + kc;
+        if (k >= K) break;
+        const float x = w[(size_t)n * K + k];
+        const __half h = __float2half_rn(x);
+        const __half l = __float2half_rn(x - __half2float(h));
+        const int c = kc >> 3, e = kc & 7;
+        const size_t off = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)((c ^ (n & 7)) << 4) + (size_t)e * 2;
+        const unsigned short hb = __half_as_ushort(h), lb = __half_as_ushort(l);
+        memcpy(hi + off, &hb, 2); memcpy(lo + off, &lb, 2);
       }
-    }
-  // pipeline depth from the shared-memory budget
-  const size_t stage = 2 * (size_t)kBM * 128 + 2 * slab;
-  int stages = (int)((220 * 1024) / stage);
-  if (stages > 4) stages = 4;
-  if (stages < 2) stages = 2;
-  L.stages = stages;
-  L.smem_bytes = (size_t)stages * stage + 1024 /*alignment*/ + 8 * (2 * stages + 4) + 16;
+  }
   return L;
+}
+
+// N tiling for a given M: fill the 148 SMs, keep >= 3 pipeline stages when K is long.
+static void choose_tiling(const PwTcLayer& L, int M, int* bn_out, int* stages_out) {
+  const int m_tiles = (M + kBM - 1) / kBM;
+  int n_tiles = (L.n_pad + 255) / 256;
+  auto bn_of = [&](int nt) { return ((L.n_pad + nt - 1) / nt + 15) / 16 * 16; };
+  int bn = bn_of(n_tiles);
+  if (L.k_stages >= 3) while (bn > 128) { ++n_tiles; bn = bn_of(n_tiles); }            // deeper ring for long K
+  while (m_tiles * ((L.n_pad + bn - 1) / bn) < kNumSMs && bn > 64) { ++n_tiles; bn = bn_of(n_tiles); }
+  const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
+  int stages = (int)((220 * 1024) / stage);
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  *bn_out = bn; *stages_out = stages;
 }
 
 void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, cudaStream_t s, LaunchCounter& lc) {
   static size_t max_set = 0;
-  if (L.smem_bytes > 227 * 1024) throw std::runtime_error("pw_tc: shared memory budget exceeded");
-  if (L.smem_bytes > max_set) {
-    BNB_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes));
-    max_set = L.smem_bytes;
+  if (p.a_mode != A_PLAIN && ((p.kw * p.cin) % kBK) != 0) throw std::runtime_error("pw_tc: im2col segment must be a multiple of 64");
+  int bn = 0, stages = 0;
+  choose_tiling(L, p.M, &bn, &stages);
+  const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
+  const size_t smem_bytes = (size_t)stages * stage + 1024 /*alignment*/ + 8 * (3 * stages + 4) + 16;
+  if (smem_bytes > 227 * 1024) throw std::runtime_error("pw_tc: shared memory budget exceeded");
+  if (smem_bytes > max_set) {
+    BNB_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    max_set = smem_bytes;
   }
   PwTcArgs a{};
   a.A = p.A; a.Wimg = d_image; a.bias = p.bias; a.C = p.C; a.residual = p.residual; a.gate = p.gate;
   a.a_mul = p.a_mul; a.a_add = p.a_add; a.a_ch = p.a_ch;
   a.M = p.M; a.N = p.N; a.K = p.K; a.rows_per_chunk = p.rows_per_chunk; a.act = p.act; a.a_mode = p.a_mode;
   a.in_w = p.in_w; a.out_w = p.out_w; a.cin = p.cin; a.kw = p.kw;
-  a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.n_tiles = L.n_tiles; a.bn_max = L.bn_max; a.stages = L.stages;
+  a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.bn = bn; a.n_tiles = (L.n_pad + bn - 1) / bn; a.stages = stages;
   a.c_vec4 = (p.N % 4 == 0) ? 1 : 0;
   const int m_tiles = (p.M + kBM - 1) / kBM;
-  const int tiles = m_tiles * L.n_tiles;
+  const int tiles = m_tiles * a.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  pw_tc_kernel<<<grid, kThreads, L.smem_bytes, s>>>(a);
+  pw_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(a);
   BNB_LAUNCH_CHECK(lc);
 }
 

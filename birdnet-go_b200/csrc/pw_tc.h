@@ -10,15 +10,14 @@
 namespace bnb {
 
 struct PwTcLayer {
-  int N = 0, K = 0, n_pad = 0, k_pad = 0, n_tiles = 0, bn_max = 0, k_stages = 0, stages = 0;
-  size_t smem_bytes = 0;
+  int N = 0, K = 0, n_pad = 0, k_pad = 0, k_stages = 0;
 };
 
 struct PwTcArgs {
   const float* A; const uint8_t* Wimg; const float* bias; float* C; const float* residual; const float* gate;
   const float* a_mul; const float* a_add; int a_ch;
   int M, N, K, rows_per_chunk, act, a_mode, in_w, out_w, cin, kw;
-  int n_pad, k_pad, n_tiles, bn_max, stages, c_vec4;
+  int n_pad, k_pad, n_tiles, bn, stages, c_vec4;
 };
 
 // Split W[N][K] (fp32, K-major = the OHWI / [O,I] layout of the .tflite) into fp16 hi/lo and lay both out as

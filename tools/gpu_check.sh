@@ -8,6 +8,7 @@ echo "== layer report f16x3"; timeout 300 python tools/layer_report.py --precisi
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5
 echo "== pytest gpu"; timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.txt
 echo "== bench f16x3"; timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 2500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+for mb in 16 64; do echo "== bench f16x3 micro $mb"; timeout 300 python bench.py --steps 10 --warmup 3 --micro-batch $mb --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['kernel_ms_per_step'])"; done
 echo "== bench f32"; timeout 600 python bench.py --steps 5 --warmup 3 --precision f32 --no-cpu-baseline > gpurun_out/bench_f32.json 2> gpurun_out/bench_f32.err; tail -c 1500 gpurun_out/bench_f32.json; tail -5 gpurun_out/bench_f32.err
 if [ "$1" == "full" ]; then
 echo "== sanitizer"; timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "
