@@ -1,0 +1,225 @@
+// birdnet_host.hpp — C++ mirror of the reference's host-side surface for the hot path, on top of the C ABI.
+//
+// The reference is Go; there is no Go toolchain in the build image, so the host side above
+// include/birdnet_b200.h is mirrored in C++ with the same names, argument meaning and error behaviour:
+//
+//   inference::Classifier / EmbeddingExtractor   /root/reference/internal/inference/backend.go:8-29
+//   B200Classifier (a 4th backend)               shaped like tflite/classifier.go:29-134
+//   BirdNET::Predict                             /root/reference/internal/classifier/analyze.go:25-110
+//   customSigmoid / getTopKResults               analyze.go:113-115, 197-208, 220-253
+//   convert16BitToFloat32                        /root/reference/internal/analysis/process.go:479-497
+//   AnalysisBuffer (overwrite ring + overlap)    /root/reference/internal/audiocore/buffer/analysis.go:30-251
+//   Results / ResultsQueue message               /root/reference/internal/classifier/queue.go:10-28
+//
+// Header-only; link with -lbirdnet_b200.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/birdnet_b200.h"
+
+namespace birdnet {
+
+struct Error : std::runtime_error {
+  int status;
+  Error(int st, const std::string& m) : std::runtime_error(m), status(st) {}
+};
+// mirror of ErrOpenVINOUnavailable (openvino/openvino.go:31): the caller falls back to TFLite
+struct ErrB200Unavailable : Error { using Error::Error; };
+
+namespace inference {
+
+// backend.go:8-19 — NOT thread-safe; callers synchronize.
+class Classifier {
+ public:
+  virtual ~Classifier() = default;
+  virtual std::vector<float> Predict(const std::vector<float>& samples) = 0;  // raw logits, label order
+  virtual int NumSpecies() const = 0;
+  virtual void Close() = 0;
+};
+// backend.go:23-29
+class EmbeddingExtractor : public Classifier {
+ public:
+  virtual void PredictWithEmbeddings(const std::vector<float>& samples, std::vector<float>* logits, std::vector<float>* emb) = 0;
+};
+
+struct B200Options { int Device = -1; int MaxBatch = 256; int MicroBatch = 0; int Precision = BNB_PRECISION_DEFAULT; };
+
+class B200Classifier final : public EmbeddingExtractor {
+ public:
+  // NewB200Classifier(modelData, opts): modelData = bytes of the embedded .tflite (tflite/classifier.go:38-40)
+  B200Classifier(const std::vector<uint8_t>& modelData, const B200Options& o = B200Options()) {
+    if (modelData.empty()) throw Error(BNB_ERR_INVALID_ARGUMENT, "cannot create model from data (0 bytes)");
+    bnb_options opts{};
+    opts.struct_size = sizeof(opts); opts.device = o.Device; opts.max_batch = o.MaxBatch; opts.micro_batch = o.MicroBatch; opts.precision = o.Precision;
+    int rc = bnb_classifier_create(modelData.data(), modelData.size(), &opts, &h_);
+    if (rc == BNB_ERR_NO_DEVICE) throw ErrB200Unavailable(rc, std::string("b200: unavailable: ") + bnb_last_error());
+    if (rc != BNB_OK) throw Error(rc, std::string("b200: classifier_create failed: status=") + std::to_string(rc) + ": " + bnb_last_error());
+    numSpecies_ = bnb_num_species(h_); numSamples_ = bnb_num_samples(h_); embDim_ = bnb_embedding_dim(h_);
+  }
+  ~B200Classifier() override { Close(); }
+
+  std::vector<float> Predict(const std::vector<float>& samples) override {
+    check_open();
+    if ((int)samples.size() != numSamples_)   // same text as tflite/classifier.go:102-104
+      throw Error(BNB_ERR_INVALID_ARGUMENT, "input size mismatch: expected " + std::to_string(numSamples_) + " samples, got " + std::to_string(samples.size()));
+    std::vector<float> out((size_t)numSpecies_);   // freshly allocated, tflite/classifier.go:115-118
+    check(bnb_predict(h_, samples.data(), samples.size(), out.data()), "predict");
+    return out;
+  }
+  void PredictWithEmbeddings(const std::vector<float>& samples, std::vector<float>* logits, std::vector<float>* emb) override {
+    check_open();
+    if ((int)samples.size() != numSamples_)
+      throw Error(BNB_ERR_INVALID_ARGUMENT, "input size mismatch: expected " + std::to_string(numSamples_) + " samples, got " + std::to_string(samples.size()));
+    logits->assign((size_t)numSpecies_, 0.f); emb->assign((size_t)embDim_, 0.f);
+    check(bnb_predict_with_embeddings(h_, samples.data(), samples.size(), logits->data(), emb->data()), "predict_with_embeddings");
+  }
+  // batched surface (the only precedent is onnx PredictBatch, onnx/classifier.go:372-430)
+  void PredictBatch(const void* pcm, int format, int B, std::vector<float>* logits) {
+    check_open();
+    logits->assign((size_t)B * numSpecies_, 0.f);
+    check(bnb_predict_batch(h_, pcm, format, B, logits->data(), nullptr), "predict_batch");
+  }
+  void AnalyzeBatch(const void* pcm, int format, int B, float sensitivity, int k, std::vector<int32_t>* idx, std::vector<float>* conf) {
+    check_open();
+    idx->assign((size_t)B * k, 0); conf->assign((size_t)B * k, 0.f);
+    check(bnb_analyze_batch(h_, pcm, format, B, sensitivity, k, idx->data(), conf->data(), nullptr), "analyze_batch");
+  }
+  int NumSpecies() const override { return numSpecies_; }
+  int NumSamples() const { return numSamples_; }
+  int EmbeddingDim() const { return embDim_; }
+  std::string Device() const { return h_ ? bnb_runtime_device(h_) : ""; }
+  std::string Precision() const { return h_ ? bnb_runtime_precision(h_) : ""; }
+  float LastInvokeMs() const { return h_ ? bnb_last_device_ms(h_) : -1.f; }
+  void Close() override { if (h_) { bnb_classifier_destroy(h_); h_ = nullptr; } }   // idempotent (tflite/classifier.go:129-134)
+
+ private:
+  void check_open() const { if (!h_) throw Error(BNB_ERR_CLOSED, "classifier is closed"); }
+  void check(int rc, const char* op) const {
+    if (rc != BNB_OK) throw Error(rc, std::string("b200: ") + op + " failed: status=" + std::to_string(rc) + ": " + bnb_last_error());
+  }
+  bnb_classifier* h_ = nullptr;
+  int numSpecies_ = 0, numSamples_ = 0, embDim_ = 0;
+};
+
+}  // namespace inference
+
+// datastore.Results as used on this path
+struct Result { std::string Species; float Confidence = 0.f; };
+
+// analyze.go:113-115
+inline double customSigmoid(double x, double sensitivity) { return 1.0 / (1.0 + std::exp(-sensitivity * x)); }
+// analyze.go:186-194
+inline std::vector<float> applySigmoidToPredictions(const std::vector<float>& predictions, double sensitivity) {
+  std::vector<float> c(predictions.size());
+  for (size_t i = 0; i < predictions.size(); ++i) c[i] = (float)customSigmoid((double)predictions[i], sensitivity);
+  return c;
+}
+// analyze.go:125-137
+inline std::vector<Result> pairLabelsAndConfidence(const std::vector<std::string>& labels, const std::vector<float>& preds) {
+  if (labels.size() != preds.size())
+    throw std::invalid_argument("mismatched labels and predictions lengths: " + std::to_string(labels.size()) + " vs " + std::to_string(preds.size()));
+  std::vector<Result> r(labels.size());
+  for (size_t i = 0; i < labels.size(); ++i) { r[i].Species = labels[i]; r[i].Confidence = preds[i]; }
+  return r;
+}
+// analyze.go:220-253: k best by descending confidence, returned as a fresh copy (never aliases the scratch buffer)
+inline std::vector<Result> getTopKResults(std::vector<Result> results, int k) {
+  if (results.empty() || k <= 0) return {};
+  const size_t n = std::min((size_t)k, results.size());
+  auto gt = [](const Result& a, const Result& b) { return a.Confidence > b.Confidence; };
+  std::partial_sort(results.begin(), results.begin() + n, results.end(), gt);
+  return std::vector<Result>(results.begin(), results.begin() + n);
+}
+// process.go:479-497
+inline std::vector<float> convert16BitToFloat32(const uint8_t* sample, size_t nbytes) {
+  const size_t length = nbytes / 2;
+  std::vector<float> out(length);
+  const float divisor = 32768.0f;
+  for (size_t i = 0; i < length; ++i) {
+    const int16_t s = (int16_t)((uint16_t)sample[i * 2] | ((uint16_t)sample[i * 2 + 1] << 8));
+    out[i] = (float)s / divisor;
+  }
+  return out;
+}
+
+constexpr int defaultTopKResults = 10;   // tracing.go:59
+
+// BirdNET model instance: lock, backend call, sensitivity-sigmoid, label pairing, top-10 (analyze.go:25-110)
+class BirdNET {
+ public:
+  BirdNET(std::unique_ptr<inference::Classifier> backend, std::vector<std::string> labels, double sensitivity = 1.0)
+      : classifier_(std::move(backend)), labels_(std::move(labels)), sensitivity_(sensitivity) {
+    if ((int)labels_.size() != classifier_->NumSpecies())   // validateModelAndLabels, birdnet.go:1248-1282
+      throw std::invalid_argument("mismatched labels and predictions lengths: " + std::to_string(labels_.size()) + " vs " + std::to_string(classifier_->NumSpecies()));
+  }
+  std::vector<Result> Predict(const std::vector<std::vector<float>>& sample) {
+    if (sample.empty() || sample[0].empty()) throw std::invalid_argument("empty audio sample");
+    std::lock_guard<std::mutex> lk(mu_);                      // bn.mu held for the whole native call (birdnet.go:111-119)
+    if (!classifier_) throw std::runtime_error("classifier backend is not initialized");
+    const std::vector<float> predictions = classifier_->Predict(sample[0]);   // only sample[0] is used (analyze.go:60)
+    const std::vector<float> confidence = applySigmoidToPredictions(predictions, sensitivity_);
+    return getTopKResults(pairLabelsAndConfidence(labels_, confidence), defaultTopKResults);
+  }
+  void Delete() { std::lock_guard<std::mutex> lk(mu_); if (classifier_) { classifier_->Close(); classifier_.reset(); } }
+  const std::vector<std::string>& Labels() const { return labels_; }
+
+ private:
+  std::unique_ptr<inference::Classifier> classifier_;
+  std::vector<std::string> labels_;
+  double sensitivity_;
+  std::mutex mu_;
+};
+
+// Overwrite-mode byte ring + overlap prefix: consecutive reads share `overlapSize` bytes (analysis.go:30-251).
+class AnalysisBuffer {
+ public:
+  AnalysisBuffer(int capacity, int overlapSize, int readSize, const std::string& sourceID)
+      : ring_((size_t)std::max(capacity, 1)), overlap_(overlapSize), read_(readSize) {
+    if (capacity <= 0) throw std::invalid_argument("invalid analysis buffer capacity: " + std::to_string(capacity) + ", must be greater than 0");
+    if (overlapSize < 0) throw std::invalid_argument("invalid overlap size: " + std::to_string(overlapSize) + ", must be >= 0");
+    if (readSize <= 0) throw std::invalid_argument("invalid read size: " + std::to_string(readSize) + ", must be greater than 0");
+    if (readSize < overlapSize) throw std::invalid_argument("read size " + std::to_string(readSize) + " must be >= overlap size " + std::to_string(overlapSize));
+    if (capacity < readSize) throw std::invalid_argument("capacity " + std::to_string(capacity) + " must be >= read size " + std::to_string(readSize));
+    if (sourceID.empty()) throw std::invalid_argument("source ID must not be empty");
+  }
+  // Write: when the ring is full the oldest bytes are overwritten (analysis.go:152-174)
+  void Write(const uint8_t* data, size_t n) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (n > ring_.size() - len_) ++overwrites_;
+    if (n >= ring_.size()) { data += n - ring_.size(); n = ring_.size(); head_ = 0; len_ = 0; }
+    for (size_t i = 0; i < n; ++i) {
+      ring_[(head_ + len_) % ring_.size()] = data[i];
+      if (len_ < ring_.size()) ++len_; else head_ = (head_ + 1) % ring_.size();
+    }
+  }
+  // Read: empty vector = "try again later"; else [overlap prefix | readSize fresh bytes] (analysis.go:187-251)
+  std::vector<uint8_t> Read() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if ((int)len_ < read_) return {};
+    std::vector<uint8_t> window((size_t)overlap_ + read_, 0);
+    if (overlap_ > 0 && (int)prev_.size() == overlap_) std::memcpy(window.data(), prev_.data(), (size_t)overlap_);
+    for (int i = 0; i < read_; ++i) { window[(size_t)overlap_ + i] = ring_[head_]; head_ = (head_ + 1) % ring_.size(); }
+    len_ -= (size_t)read_;
+    if (overlap_ > 0) prev_.assign(window.end() - overlap_, window.end());
+    return window;
+  }
+  int64_t OverwriteCount() const { return overwrites_; }
+
+ private:
+  std::vector<uint8_t> ring_;
+  size_t head_ = 0, len_ = 0;
+  std::vector<uint8_t> prev_;
+  int overlap_, read_;
+  int64_t overwrites_ = 0;
+  std::mutex mu_;
+};
+
+}  // namespace birdnet

@@ -1,0 +1,128 @@
+// host_test.cc — exercises the C++ host mirror (birdnet_host.hpp) the way the reference's Go tests exercise the
+// corresponding Go code:
+//   AnalysisBuffer overlap/content/overwrite    <- internal/audiocore/buffer/analysis_test.go:23-300
+//   sigmoid / pair labels / top-k / alias-safety <- internal/classifier/analyze_test.go:14-822
+//   16-bit PCM conversion                        <- internal/analysis/process_alloc_test.go:38
+// and, with a GPU, the drop-in path end to end:
+//   host_test analyze <model.tflite> <labels.txt> <wav> [sensitivity] [threshold]
+//     -> one line per 3 s chunk whose top-1 confidence >= threshold (the doc/wiki/file-analysis.md table)
+//
+//   g++ -std=c++17 -O2 host_test.cc -I../../include -L../lib -lbirdnet_b200 -Wl,-rpath,'$ORIGIN/../lib' -o host_test
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+
+#include "birdnet_host.hpp"
+
+using namespace birdnet;
+
+static int g_fail = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); ++g_fail; } } while (0)
+
+static void test_analysis_buffer() {
+  // TestAnalysisBuffer_OverlapRead: second window starts with the tail of the first
+  AnalysisBuffer ab(64, 4, 8, "src");
+  CHECK(ab.Read().empty());                                 // not enough data yet -> "try again later"
+  std::vector<uint8_t> d(16);
+  for (int i = 0; i < 16; ++i) d[i] = (uint8_t)(i + 1);
+  ab.Write(d.data(), d.size());
+  auto w1 = ab.Read();
+  CHECK(w1.size() == 12);
+  CHECK(w1[0] == 0 && w1[3] == 0 && w1[4] == 1 && w1[11] == 8);   // first window: zero overlap prefix
+  auto w2 = ab.Read();
+  CHECK(w2.size() == 12 && w2[0] == 5 && w2[3] == 8 && w2[4] == 9 && w2[11] == 16);
+  CHECK(ab.Read().empty());
+  // BirdNET geometry: 288000-byte windows, 50 % overlap (model.go:41-46): 144000 prefix + 144000 fresh
+  AnalysisBuffer big(3 * 288000, 144000, 144000, "mic");
+  std::vector<uint8_t> pcm(288000);
+  for (size_t i = 0; i < pcm.size(); ++i) pcm[i] = (uint8_t)(i * 7);
+  big.Write(pcm.data(), pcm.size());
+  auto a = big.Read(), b = big.Read();
+  CHECK(a.size() == 288000 && b.size() == 288000);
+  CHECK(std::memcmp(b.data(), a.data() + 144000, 144000) == 0);  // content parity across consecutive reads
+  // overwrite mode: writing more than the capacity keeps the newest bytes
+  AnalysisBuffer small(8, 0, 4, "s");
+  std::vector<uint8_t> x(12);
+  for (int i = 0; i < 12; ++i) x[i] = (uint8_t)i;
+  small.Write(x.data(), 6); small.Write(x.data() + 6, 6);
+  CHECK(small.OverwriteCount() >= 1);
+  auto r = small.Read();
+  CHECK(r.size() == 4 && r[0] == 4 && r[3] == 7);
+  // constructor validation (analysis.go:55-111)
+  int thrown = 0;
+  try { AnalysisBuffer bad(10, 8, 4, "s"); } catch (const std::invalid_argument&) { ++thrown; }
+  try { AnalysisBuffer bad(2, 0, 4, "s"); } catch (const std::invalid_argument&) { ++thrown; }
+  try { AnalysisBuffer bad(10, 0, 4, ""); } catch (const std::invalid_argument&) { ++thrown; }
+  CHECK(thrown == 3);
+}
+
+static void test_postprocessing() {
+  CHECK(std::fabs(customSigmoid(0.0, 1.0) - 0.5) < 1e-12);
+  CHECK(std::fabs(customSigmoid(1.4766, 1.5) - 0.9016) < 1e-4);       // doc table row 1
+  auto c = applySigmoidToPredictions({0.f, 10.f, -10.f}, 1.0);
+  CHECK(c.size() == 3 && std::fabs(c[0] - 0.5f) < 1e-7 && c[1] > 0.9999f && c[2] < 1e-4f);
+  std::vector<std::string> labels = {"a", "b", "c", "d"};
+  auto paired = pairLabelsAndConfidence(labels, {0.1f, 0.9f, 0.5f, 0.3f});
+  auto top = getTopKResults(paired, 2);
+  CHECK(top.size() == 2 && top[0].Species == "b" && top[1].Species == "c");
+  CHECK(paired[0].Species == "a");                                     // input not aliased / mutated
+  CHECK(getTopKResults(paired, 10).size() == 4 && getTopKResults(paired, 0).empty() && getTopKResults({}, 3).empty());
+  bool threw = false;
+  try { pairLabelsAndConfidence(labels, {0.1f}); } catch (const std::invalid_argument&) { threw = true; }
+  CHECK(threw);
+  const uint8_t raw[] = {0x00, 0x00, 0x01, 0x00, 0xff, 0xff, 0xff, 0x7f, 0x00, 0x80};
+  auto f = convert16BitToFloat32(raw, sizeof(raw));
+  CHECK(f.size() == 5 && f[0] == 0.f && f[1] == 1.f / 32768.f && f[2] == -1.f / 32768.f && f[3] == 32767.f / 32768.f && f[4] == -1.f);
+}
+
+static std::vector<uint8_t> slurp(const char* p) {
+  std::ifstream f(p, std::ios::binary);
+  if (!f) throw std::runtime_error(std::string("cannot open ") + p);
+  return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), {});
+}
+
+static int analyze(int argc, char** argv) {
+  const double sensitivity = argc > 5 ? atof(argv[5]) : 1.5;
+  const double threshold = argc > 6 ? atof(argv[6]) : 0.1;
+  auto model = slurp(argv[2]);
+  std::vector<std::string> labels;
+  { std::ifstream f(argv[3]); std::string ln; while (std::getline(f, ln)) if (!ln.empty()) labels.push_back(ln); }
+  auto wav = slurp(argv[4]);
+  // minimal RIFF walk: 16-bit mono PCM
+  size_t p = 12, data_off = 0, data_len = 0; int bits = 0;
+  while (p + 8 <= wav.size()) {
+    uint32_t sz; std::memcpy(&sz, &wav[p + 4], 4);
+    if (!std::memcmp(&wav[p], "fmt ", 4)) { uint16_t b; std::memcpy(&b, &wav[p + 8 + 14], 2); bits = b; }
+    if (!std::memcmp(&wav[p], "data", 4)) { data_off = p + 8; data_len = sz; }
+    p += 8 + sz + (sz & 1);
+  }
+  if (bits != 16 || !data_off) throw std::runtime_error("expected 16-bit PCM wav");
+  std::unique_ptr<inference::Classifier> backend;
+  try { backend.reset(new inference::B200Classifier(model)); }
+  catch (const ErrB200Unavailable& e) { std::printf("UNAVAILABLE %s\n", e.what()); return 3; }   // caller would fall back to TFLite
+  BirdNET bn(std::move(backend), labels, sensitivity);
+  const size_t win = 144000 * 2;
+  for (size_t off = 0, i = 0; off + win <= data_len; off += win, ++i) {
+    auto chunk = convert16BitToFloat32(&wav[data_off + off], win);
+    auto res = bn.Predict({chunk});
+    if (!res.empty() && res[0].Confidence >= threshold)
+      std::printf("%.1f\t%s\t%.4f\n", 3.0 * (double)i, res[0].Species.c_str(), res[0].Confidence);
+  }
+  // error behaviour of the drop-in boundary
+  bool threw = false;
+  try { bn.Predict({std::vector<float>(1000, 0.f)}); } catch (const Error& e) { threw = std::string(e.what()).find("input size mismatch") != std::string::npos; }
+  std::printf("size-mismatch-error %s\n", threw ? "ok" : "MISSING");
+  bn.Delete(); bn.Delete();
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  try {
+    if (argc > 4 && std::string(argv[1]) == "analyze") return analyze(argc, argv);
+    test_analysis_buffer();
+    test_postprocessing();
+    std::printf(g_fail ? "FAILED %d\n" : "OK\n", g_fail);
+    return g_fail ? 1 : 0;
+  } catch (const std::exception& e) { std::printf("EXCEPTION %s\n", e.what()); return 2; }
+}
