@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--precision", default="default", choices=["default", "f32", "f16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -242,7 +243,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     prec = {"default": bb.PRECISION_DEFAULT, "f32": bb.PRECISION_F32, "f16x3": bb.PRECISION_F16X3}[a.precision]
-    clf = bb.B200Classifier(device=local, max_batch=a.batch, micro_batch=a.micro_batch, precision=prec)
+    clf = bb.B200Classifier(device=local, max_batch=a.batch, micro_batch=a.micro_batch, precision=prec, lanes=a.lanes)
     B = a.batch
     host = soundscape_batch(B)
     if world > 1:

@@ -115,7 +115,7 @@ class B200Classifier:
     """inference.Classifier + EmbeddingExtractor backed by libbirdnet_b200 (NOT thread-safe: backend.go:7)."""
 
     def __init__(self, model_data: bytes | None = None, device=-1, max_batch=256, micro_batch=0,
-                 precision=PRECISION_DEFAULT, use_graphs=0):
+                 precision=PRECISION_DEFAULT, use_graphs=0, lanes=0):
         lib = load_library()
         if model_data is None:
             with open(DEFAULT_MODEL, "rb") as f:
@@ -123,6 +123,7 @@ class B200Classifier:
         o = Options()
         o.struct_size = C.sizeof(Options)
         o.device, o.max_batch, o.micro_batch, o.precision, o.use_graphs = device, max_batch, micro_batch, precision, use_graphs
+        o.reserved[0] = lanes      # concurrent front-phase streams (0 = library default)
         h = C.c_void_p()
         _check(lib.bnb_classifier_create(model_data, len(model_data), C.byref(o), C.byref(h)))
         self._lib, self._h = lib, h

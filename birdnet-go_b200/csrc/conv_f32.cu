@@ -299,6 +299,26 @@ se_gate_kernel(const SeArgs a) {
   }
 }
 
+// relu(x*mul+add) + im2col for the final KxK VALID conv: in [B][kh][in_w][cin] -> out [B*out_w][kh*kw*cin]
+__global__ void __launch_bounds__(256)
+post_prep_kernel(const float* __restrict__ in, const float* __restrict__ mul, const float* __restrict__ add, float* __restrict__ out,
+                 int B, int kh, int kw, int in_w, int out_w, int cin) {
+  const int c4n = cin / 4, K4 = kh * kw * c4n;
+  const long long total = (long long)B * out_w * K4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k4 = (int)(idx % K4);
+    const long long row = idx / K4;
+    const int wo = (int)(row % out_w), b = (int)(row / out_w);
+    const int c4 = k4 % c4n, t = k4 / c4n, x = t % kw, y = t / kw;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * kh + y) * in_w + wo + x) * cin) + c4);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mul) + c4), a = __ldg(reinterpret_cast<const float4*>(add) + c4);
+    float4 o;
+    o.x = fmaxf(fmaf(v.x, m.x, a.x), 0.f); o.y = fmaxf(fmaf(v.y, m.y, a.y), 0.f);
+    o.z = fmaxf(fmaf(v.z, m.z, a.z), 0.f); o.w = fmaxf(fmaf(v.w, m.w, a.w), 0.f);
+    reinterpret_cast<float4*>(out)[idx] = o;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 row_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int rows, int C) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,6 +374,15 @@ void launch_dw_conv(const DwArgs& a0, cudaStream_t s, LaunchCounter& lc) {
 void launch_se_gate(const SeArgs& a, cudaStream_t s, LaunchCounter& lc) {
   if (a.C > kSeMaxC || a.Cse > kSeMaxS) throw std::runtime_error("se_gate: channel count exceeds kernel limits");
   se_gate_kernel<<<a.B, kSeThreads, 0, s>>>(a);
+  BNB_LAUNCH_CHECK(lc);
+}
+
+void launch_post_prep(const float* in, const float* mul, const float* add, float* out, int B, int kh, int kw, int in_w, int out_w,
+                      int cin, cudaStream_t s, LaunchCounter& lc) {
+  const long long total = (long long)B * out_w * kh * kw * (cin / 4);
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  post_prep_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, mul, add, out, B, kh, kw, in_w, out_w, cin);
   BNB_LAUNCH_CHECK(lc);
 }
 

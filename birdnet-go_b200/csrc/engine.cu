@@ -43,6 +43,7 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
   device_name_ = std::string("CUDA:") + std::to_string(dev) + " " + prop.name;
   max_batch_ = opts.max_batch > 0 ? opts.max_batch : 256;
   micro_ = opts.micro_batch > 0 ? opts.micro_batch : 32;
+  n_lanes_ = opts.reserved[0] > 0 ? std::min<int>(opts.reserved[0], kMaxLanes) : 2;
   if (micro_ > max_batch_) micro_ = max_batch_;
   precision_ = opts.precision == BNB_PRECISION_DEFAULT ? BNB_PRECISION_F16X3 : opts.precision;
   precision_name_ = precision_ == BNB_PRECISION_F16X3 ? "FP16x3(tcgen05)+FP32" : "FP32";
@@ -64,6 +65,11 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
 
   BNB_CUDA(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking));
   BNB_CUDA(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
+  for (int i = 0; i < n_lanes_; ++i) {
+    BNB_CUDA(cudaStreamCreateWithFlags(&lanes_[i].stream, cudaStreamNonBlocking));
+    BNB_CUDA(cudaEventCreateWithFlags(&lanes_[i].done, cudaEventDisableTiming));
+  }
+  BNB_CUDA(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
   BNB_CUDA(cudaEventCreate(&ev_start_));
   BNB_CUDA(cudaEventCreate(&ev_stop_));
   upload_weights(P);
@@ -72,8 +78,9 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
 
 Engine::~Engine() {
   cudaSetDevice(device_);
-  if (compute_) cudaStreamSynchronize(compute_);
-  if (copy_) cudaStreamSynchronize(copy_);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < n_lanes_; ++i) { if (lanes_[i].stream) cudaStreamDestroy(lanes_[i].stream); if (lanes_[i].done) cudaEventDestroy(lanes_[i].done); }
+  if (ev_in_) cudaEventDestroy(ev_in_);
   for (void* p : allocs_) cudaFree(p);
   for (auto& kv : keep_bufs_) cudaFree(kv.second.first);
   if (h_in_) cudaFreeHost(h_in_);
@@ -213,11 +220,10 @@ void Engine::alloc_workspace() {
   split_ = (int)blocks_.size();
   for (size_t i = 0; i < blocks_.size(); ++i) if (blocks_[i].g.in_h * blocks_[i].g.in_w < 256) { split_ = (int)i; break; }
   if (split_ == 0) split_ = 1;
-  for (int ph = 0; ph < 2; ++ph) {
-    Work& w = work_[ph];
-    w.cap_n = ph == 0 ? (size_t)micro_ : (size_t)max_batch_;
-    size_t cx = ph == 0 ? (size_t)stem_.out_h * (stem_.out_w / 2) * 24 : 0, ce = 0, cd = 0, cg = 0;
-    const int lo = ph == 0 ? 0 : split_, hi = ph == 0 ? split_ : (int)blocks_.size();
+  const size_t mb = (size_t)micro_, bb = (size_t)max_batch_;
+  auto alloc_work = [&](Work& w, size_t cap_n, int lo, int hi, size_t cx) {
+    w.cap_n = cap_n;
+    size_t ce = 0, cd = 0, cg = 0;
     for (int i = lo; i < hi; ++i) {
       const BlockPlan& g = blocks_[i].g;
       ce = std::max(ce, (size_t)g.in_h * g.in_w * g.cexp);
@@ -226,17 +232,21 @@ void Engine::alloc_workspace() {
       cx = std::max(cx, (size_t)g.in_h * g.in_w * g.cin);
       cg = std::max(cg, (size_t)g.cexp);
     }
-    w.x0 = dmalloc(w.cap_n * cx); w.x1 = dmalloc(w.cap_n * cx);
-    w.e = dmalloc(w.cap_n * ce); w.d = dmalloc(w.cap_n * cd); w.g = dmalloc(w.cap_n * cg);
-    w.sep = dmalloc(w.cap_n * kMaxDwParts * cg);
+    w.x0 = dmalloc(cap_n * cx); w.x1 = dmalloc(cap_n * cx);
+    w.e = dmalloc(cap_n * ce); w.d = dmalloc(cap_n * cd); w.g = dmalloc(cap_n * cg);
+    w.sep = dmalloc(cap_n * kMaxDwParts * cg);
+  };
+  for (int l = 0; l < n_lanes_; ++l) {
+    alloc_work(lanes_[l].w, mb, 0, split_, (size_t)stem_.out_h * (stem_.out_w / 2) * 24);
+    lanes_[l].partial = dmalloc(mb * kMinMaxParts * 2);
+    lanes_[l].fe = dmalloc(mb * fe_.n_mel * fe_.n_frames * 2);
   }
-  const size_t mb = (size_t)micro_, bb = (size_t)max_batch_;
-  ws_partial_ = dmalloc(mb * kMinMaxParts * 2);
-  ws_fe_ = dmalloc(mb * fe_.n_mel * fe_.n_frames * 2);
+  alloc_work(work_back_, bb, split_, (int)blocks_.size(), 0);
   const BlockPlan& gs = blocks_[split_ - 1].g;
   mid_sz_ = (size_t)gs.out_h * gs.out_w * gs.cout;
   ws_mid_ = dmalloc(bb * mid_sz_);
   ws_pc_ = dmalloc(bb * post_g_.out_w * post_g_.conv.cout);
+  ws_im2col_ = dmalloc(bb * post_g_.out_w * post_g_.conv.kh * post_g_.conv.kw * post_g_.conv.cin);
   ws_emb_ = dmalloc(bb * emb_dim_);
 }
 
@@ -301,8 +311,9 @@ float* Engine::run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream
 }
 
 // frontend -> stem -> blocks [0, split_) for one micro-batch; result (the split-point tensor) goes to `mid`
-void Engine::run_front(const void* d_pcm, int fmt, int n, float* mid, cudaStream_t s) {
-  Work& w = work_[0];
+void Engine::run_front(const void* d_pcm, int fmt, int n, float* mid, Lane& L, cudaStream_t s) {
+  Work& w = L.w;
+  float* ws_partial_ = L.partial; float* ws_fe_ = L.fe;
   { ProfScope ps(this, C_MINMAX, s); launch_minmax(d_pcm, fmt, n, n_samples_, ws_partial_, s, lc_); }
   const size_t fe_sz = (size_t)fe_.n_mel * fe_.n_frames * 2;
   float* fe_out = scratch(fe_tensor_, ws_fe_, fe_sz, n);
@@ -320,7 +331,7 @@ void Engine::run_front(const void* d_pcm, int fmt, int n, float* mid, cudaStream
 
 // blocks [split_, end) -> post conv -> embedding -> FC head over `n` chunks at once
 void Engine::run_back(const float* mid, int n, float* d_logits, float* d_emb, cudaStream_t s) {
-  Work& w = work_[1];
+  Work& w = work_back_;
   BNB_CUDA(cudaMemcpyAsync(w.x0, mid, (size_t)n * mid_sz_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
   float* cur = run_blocks(split_, (int)blocks_.size(), w.x0, n, w, s);
   const PostPlan& q = post_g_;
@@ -329,6 +340,10 @@ void Engine::run_back(const float* mid, int n, float* d_logits, float* d_emb, cu
   pa.A = cur; pa.W = post_conv_.w; pa.bias = post_conv_.b; pa.C = pc; pa.M = n * q.out_w; pa.N = q.conv.cout;
   pa.K = q.conv.kh * q.conv.kw * q.conv.cin; pa.rows_per_chunk = q.out_w; pa.act = ACT_RELU; pa.a_mode = A_CONV3X3_ROW;
   pa.a_mul = post_mul_; pa.a_add = post_add_; pa.a_ch = q.conv.cin; pa.in_w = q.in_w; pa.out_w = q.out_w; pa.cin = q.conv.cin; pa.kw = q.conv.kw;
+  if (post_conv_.tc_img) {      // tensor-core GEMM wants a plain matrix: materialise relu(affine) + im2col (40 KB/chunk)
+    { ProfScope ps(this, C_POST_CONV, s); launch_post_prep(cur, post_mul_, post_add_, ws_im2col_, n, q.conv.kh, q.conv.kw, q.in_w, q.out_w, q.conv.cin, s, lc_); }
+    pa.A = ws_im2col_; pa.a_mode = A_PLAIN; pa.a_mul = nullptr; pa.a_add = nullptr;
+  }
   pw(pa, post_conv_, C_POST_CONV, s);
   record(q.conv_tensor, pc, (size_t)q.out_w * q.conv.cout, n);
   float* emb = d_emb ? d_emb : ws_emb_;
@@ -346,12 +361,19 @@ void Engine::predict_device(const void* d_pcm, int fmt, int B, float* d_logits, 
   if (!s) s = compute_;
   views_.clear();
   const size_t cb = (size_t)n_samples_ * fmt_bytes(fmt);
+  const int lanes = keep_ ? 1 : n_lanes_;
   for (int j = 0; j < B; j += max_batch_) {                       // back-phase capacity
     const int nb = std::min(max_batch_, B - j);
-    for (int i = 0; i < nb; i += micro_) {
+    // fan the micro-batches out over the lane streams, join before the back phase
+    BNB_CUDA(cudaEventRecord(ev_in_, s));
+    for (int l = 0; l < lanes; ++l) BNB_CUDA(cudaStreamWaitEvent(lanes_[l].stream, ev_in_, 0));
+    int mi = 0;
+    for (int i = 0; i < nb; i += micro_, ++mi) {
       const int n = std::min(micro_, nb - i);
-      run_front(static_cast<const char*>(d_pcm) + (size_t)(j + i) * cb, fmt, n, ws_mid_ + (size_t)i * mid_sz_, s);
+      Lane& L = lanes_[mi % lanes];
+      run_front(static_cast<const char*>(d_pcm) + (size_t)(j + i) * cb, fmt, n, ws_mid_ + (size_t)i * mid_sz_, L, L.stream);
     }
+    for (int l = 0; l < lanes; ++l) { BNB_CUDA(cudaEventRecord(lanes_[l].done, lanes_[l].stream)); BNB_CUDA(cudaStreamWaitEvent(s, lanes_[l].done, 0)); }
     run_back(ws_mid_, nb, d_logits + (size_t)j * n_species_, d_emb ? d_emb + (size_t)j * emb_dim_ : nullptr, s);
   }
 }
@@ -410,7 +432,9 @@ void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, in
   const size_t cb = (size_t)n_samples_ * fmt_bytes(fmt);
   const bool src_pinned = is_pinned(pcm);
   views_.clear();
+  const int lanes = keep_ ? 1 : n_lanes_;
   BNB_CUDA(cudaEventRecord(ev_start_, compute_));
+  for (int l = 0; l < lanes; ++l) BNB_CUDA(cudaStreamWaitEvent(lanes_[l].stream, ev_start_, 0));   // previous call's back phase is done (stream order)
   // H2D per micro-batch on the copy stream; compute waits per micro-batch
   int mi = 0;
   for (int i = 0; i < B; i += micro_, ++mi) {
@@ -422,9 +446,11 @@ void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, in
     }
     BNB_CUDA(cudaMemcpyAsync(static_cast<char*>(d_in_) + (size_t)i * cb, src, (size_t)n * cb, cudaMemcpyHostToDevice, copy_));
     BNB_CUDA(cudaEventRecord(ev_h2d_[mi], copy_));
-    BNB_CUDA(cudaStreamWaitEvent(compute_, ev_h2d_[mi], 0));
-    run_front(static_cast<const char*>(d_in_) + (size_t)i * cb, fmt, n, ws_mid_ + (size_t)i * mid_sz_, compute_);
+    Lane& L = lanes_[mi % lanes];
+    BNB_CUDA(cudaStreamWaitEvent(L.stream, ev_h2d_[mi], 0));
+    run_front(static_cast<const char*>(d_in_) + (size_t)i * cb, fmt, n, ws_mid_ + (size_t)i * mid_sz_, L, L.stream);
   }
+  for (int l = 0; l < lanes; ++l) { BNB_CUDA(cudaEventRecord(lanes_[l].done, lanes_[l].stream)); BNB_CUDA(cudaStreamWaitEvent(compute_, lanes_[l].done, 0)); }
   run_back(ws_mid_, B, d_logits_, d_emb_, compute_);
   if (k > 0) {
     { ProfScope ps(this, C_TOPK, compute_); launch_sigmoid_topk(d_logits_, B, n_species_, sensitivity, k, d_idx_, d_conf_, compute_, lc_); }

@@ -61,8 +61,10 @@ class Engine {
   void pw(const PwArgs& a, const DevConv& c, int cat, cudaStream_t s);
   static constexpr int kMaxDwParts = 32;
   struct Work { float *x0 = nullptr, *x1 = nullptr, *e = nullptr, *d = nullptr, *g = nullptr, *sep = nullptr; size_t cap_n = 0; };
+  static constexpr int kMaxLanes = 4;
+  struct Lane { Work w; float* partial = nullptr; float* fe = nullptr; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; };
   float* run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream_t s);
-  void run_front(const void* d_pcm, int fmt, int n, float* mid, cudaStream_t s);
+  void run_front(const void* d_pcm, int fmt, int n, float* mid, Lane& L, cudaStream_t s);
   void run_back(const float* mid, int n, float* d_logits, float* d_emb, cudaStream_t s);
   float* scratch(int tensor_id, float* normal, size_t per_chunk, int n);
   void record(int tensor_id, const float* p, size_t per_chunk, int n) { if (tensor_id >= 0) views_[tensor_id] = TensorView{p, per_chunk, n}; }
@@ -98,8 +100,11 @@ class Engine {
   DevConv fc_; int logits_tensor_ = -1;
 
   // workspaces (capacity: micro_ chunks)
-  float *ws_partial_ = nullptr, *ws_fe_ = nullptr, *ws_mid_ = nullptr, *ws_pc_ = nullptr, *ws_emb_ = nullptr;
-  Work work_[2];          // [0] front phase (micro-batch), [1] back phase (whole batch)
+  float *ws_mid_ = nullptr, *ws_pc_ = nullptr, *ws_emb_ = nullptr, *ws_im2col_ = nullptr;
+  Lane lanes_[kMaxLanes]; // front phase: micro-batches round-robin over `n_lanes_` streams so kernel ramps/tails overlap
+  int n_lanes_ = 2;
+  cudaEvent_t ev_in_ = nullptr;
+  Work work_back_;        // back phase (whole batch)
   int split_ = 0;         // first block of the back phase
   size_t mid_sz_ = 0;     // floats per chunk of the split-point tensor
   std::map<int, std::pair<float*, size_t>> keep_bufs_;   // tensor id -> (device buffer, capacity in floats)

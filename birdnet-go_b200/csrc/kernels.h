@@ -91,6 +91,10 @@ struct SeArgs {
 };
 void launch_se_gate(const SeArgs& a, cudaStream_t s, LaunchCounter& lc);
 
+// relu(x*mul+add) + im2col of the final KxK VALID conv input (tensor-core path: the GEMM then sees a plain [M][K] matrix)
+void launch_post_prep(const float* in, const float* mul, const float* add, float* out, int B, int kh, int kw, int in_w, int out_w,
+                      int cin, cudaStream_t s, LaunchCounter& lc);
+
 // mean over `rows` consecutive rows: in [B][rows][C] -> out [B][C]
 void launch_row_mean(const float* in, float* out, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc);
 

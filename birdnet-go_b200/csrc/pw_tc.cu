@@ -17,7 +17,12 @@
 //                           affine+ReLU -> hi/lo fp16 split -> 16 B st.shared into the swizzled K-major tile
 //   accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile t overlaps the
 //   main loop of tile t+1.
+#include <cuda.h>
 #include <cuda_fp16.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "kernels.h"
 #include "pw_tc.h"
@@ -65,6 +70,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// one 2-D TMA tile load (tensor map in kernel-parameter space): coordinates (c0 = innermost = k, c1 = row)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 format, version 1).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -109,7 +120,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // read into registers by the 4 producer warps, and is then overwritten IN PLACE by the fp16 hi (16 KB) and lo (16 KB)
 // 128B-swizzled K-major tiles the MMA consumes.
 __global__ void __launch_bounds__(kThreads, 1)
-pw_tc_kernel(const PwTcArgs a) {
+pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -144,7 +155,7 @@ pw_tc_kernel(const PwTcArgs a) {
   const int m_tiles = (a.M + kBM - 1) / kBM;
   const int total_tiles = m_tiles * a.n_tiles;
   const int k_stages = (a.K + kBK - 1) / kBK;
-  const int a_seg = a.a_mode == A_PLAIN ? 0 : a.kw * a.cin;    // im2col: K = (K/a_seg) segments of kw*cin contiguous floats
+  const int pitch = a.box_k * 4;                               // bytes per raw fp32 row in the landing buffer
 
   if (warp >= kProdWarp0) {
     // ============================== A converters (4 warps) ====================================
@@ -166,9 +177,9 @@ pw_tc_kernel(const PwTcArgs a) {
           for (int q = 0; q < 8; ++q) {
             const int r = r0 + 16 * q, m = m0 + r;
             if (m < a.M && k < a.K) {
-              const float4 x0 = *reinterpret_cast<const float4*>(buf + r * 256 + c * 32);
+              const float4 x0 = *reinterpret_cast<const float4*>(buf + r * pitch + c * 32);
               float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (k + 4 < a.K) x1 = *reinterpret_cast<const float4*>(buf + r * 256 + c * 32 + 16);
+              if (k + 4 < a.K) x1 = *reinterpret_cast<const float4*>(buf + r * pitch + c * 32 + 16);
               v[q][0] = x0.x; v[q][1] = x0.y; v[q][2] = x0.z; v[q][3] = x0.w;
               v[q][4] = x1.x; v[q][5] = x1.y; v[q][6] = x1.z; v[q][7] = x1.w;
             } else {
@@ -195,17 +206,6 @@ pw_tc_kernel(const PwTcArgs a) {
                 for (int i = 0; i < 8; ++i) v[q][i] *= g[i];
               }
             }
-          }
-          if (a.a_mul) {
-            const int ch = k % a.a_ch;
-            float mu[8], ad[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { mu[i] = (k + i < a.K) ? __ldg(a.a_mul + ch + i) : 0.f; ad[i] = (k + i < a.K) ? __ldg(a.a_add + ch + i) : 0.f; }
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (m0 + r0 + 16 * q < a.M)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[q][i] = fmaxf(fmaf(v[q][i], mu[i], ad[i]), 0.f);
           }
         }
         // every converter has finished READING the raw rows before anyone overwrites them with the fp16 tiles
@@ -240,34 +240,20 @@ pw_tc_kernel(const PwTcArgs a) {
       const int nt = tile % a.n_tiles, m0 = (tile / a.n_tiles) * kBM;
       const int n0 = nt * a.bn;
       const uint32_t bn_bytes = (uint32_t)min(a.bn, a.n_pad - n0) * 128u;
-      const int rows = min(kBM, a.M - m0);
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
         const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
-        const int k0 = ks * kBK;
-        const uint32_t row_bytes = (uint32_t)min(kBK, a.K - k0) * 4u;
         const uint32_t dst = base + (uint32_t)s * stage_bytes;
         if (lane == 0) {
-          mbar_arrive_expect_tx(raw_bar(s), row_bytes * (uint32_t)rows);
+          // A: ONE 2-D TMA request per stage (box = box_k x 128 rows of fp32; out-of-range rows / columns arrive as zeros)
+          mbar_arrive_expect_tx(raw_bar(s), (uint32_t)a.box_k * 4u * kBM);
+          tma_load_2d(dst, &a_map, ks * kBK, m0, raw_bar(s));
           mbar_arrive_expect_tx(full_bar(s), 2 * bn_bytes);
           const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
           bulk_g2s(dst + 2 * a_bytes, wsrc, bn_bytes, full_bar(s));
           bulk_g2s(dst + 2 * a_bytes + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, full_bar(s));
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = lane + 32 * j, m = m0 + r;
-          if (r < rows) {
-            const float* src;
-            if (a.a_mode == A_PLAIN) src = a.A + (size_t)m * a.K + k0;
-            else {
-              const int bidx = m / a.out_w, wo = m - bidx * a.out_w;
-              const int seg = k0 / a_seg, j0 = k0 - seg * a_seg;
-              src = a.A + ((size_t)bidx * (a.K / a_seg) * a.in_w + wo) * a.cin + (size_t)seg * a.in_w * a.cin + j0;
-            }
-            bulk_g2s(dst + (uint32_t)r * 256u, src, row_bytes, raw_bar(s));
-          }
-        }
+        __syncwarp();
       }
     }
   } else if (warp == kMmaWarp) {
@@ -413,9 +399,43 @@ static void choose_tiling(const PwTcLayer& L, int M, int* bn_out, int* stages_ou
   *bn_out = bn; *stages_out = stages;
 }
 
+// 2-D tensor map over the fp32 activation matrix A[M][K] (K contiguous): box = box_k x 128 rows, no swizzle.
+// cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
+static CUtensorMap encode_a_map(const float* A, int M, int K, int box_k) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  static std::mutex mu;
+  static std::map<std::tuple<const float*, int, int>, CUtensorMap> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    BNB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("pw_tc: cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeFn>(p);
+  }
+  auto key = std::make_tuple(A, M, K);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)kBM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("pw_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  return m;
+}
+
 void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, cudaStream_t s, LaunchCounter& lc) {
   static size_t max_set = 0;
-  if (p.a_mode != A_PLAIN && ((p.kw * p.cin) % kBK) != 0) throw std::runtime_error("pw_tc: im2col segment must be a multiple of 64");
+  if (p.a_mode != A_PLAIN || p.a_mul) throw std::runtime_error("pw_tc: A must be a plain [M][K] matrix (run the prep kernel first)");
   int bn = 0, stages = 0;
   choose_tiling(L, p.M, &bn, &stages);
   const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
@@ -427,15 +447,15 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   }
   PwTcArgs a{};
   a.A = p.A; a.Wimg = d_image; a.bias = p.bias; a.C = p.C; a.residual = p.residual; a.gate = p.gate;
-  a.a_mul = p.a_mul; a.a_add = p.a_add; a.a_ch = p.a_ch;
-  a.M = p.M; a.N = p.N; a.K = p.K; a.rows_per_chunk = p.rows_per_chunk; a.act = p.act; a.a_mode = p.a_mode;
-  a.in_w = p.in_w; a.out_w = p.out_w; a.cin = p.cin; a.kw = p.kw;
+  a.M = p.M; a.N = p.N; a.K = p.K; a.rows_per_chunk = p.rows_per_chunk; a.act = p.act;
+  a.box_k = p.K < kBK ? p.K : kBK;
   a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.bn = bn; a.n_tiles = (L.n_pad + bn - 1) / bn; a.stages = stages;
   a.c_vec4 = (p.N % 4 == 0) ? 1 : 0;
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int tiles = m_tiles * a.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  pw_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(a);
+  const CUtensorMap amap = encode_a_map(p.A, p.M, p.K, a.box_k);
+  pw_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(a, amap);
   BNB_LAUNCH_CHECK(lc);
 }
 

@@ -15,9 +15,8 @@ struct PwTcLayer {
 
 struct PwTcArgs {
   const float* A; const uint8_t* Wimg; const float* bias; float* C; const float* residual; const float* gate;
-  const float* a_mul; const float* a_add; int a_ch;
-  int M, N, K, rows_per_chunk, act, a_mode, in_w, out_w, cin, kw;
-  int n_pad, k_pad, n_tiles, bn, stages, c_vec4;
+  int M, N, K, rows_per_chunk, act;
+  int n_pad, k_pad, n_tiles, bn, stages, c_vec4, box_k;
 };
 
 // Split W[N][K] (fp32, K-major = the OHWI / [O,I] layout of the .tflite) into fp16 hi/lo and lay both out as
