@@ -255,7 +255,8 @@ def main():
     d_conf = torch.empty((B, TOP_K), dtype=torch.float32, device="cuda")
     g_idx = torch.empty((world * B, TOP_K), dtype=torch.int32, device="cuda") if world > 1 else None
     g_conf = torch.empty((world * B, TOP_K), dtype=torch.float32, device="cuda") if world > 1 else None
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # an explicit stream: the library enqueues on it, the CUDA events below time it
+    torch.cuda.set_stream(stream)
 
     def step(i):
         clf.analyze_batch_device(d_in[i & 1].data_ptr(), bb.PCM_F32, B, 1.0, TOP_K, d_idx.data_ptr(), d_conf.data_ptr(), d_logits.data_ptr(), stream.cuda_stream)
@@ -305,6 +306,11 @@ def main():
         if rc != 0:
             raise RuntimeError(bb.last_error())
 
+    # raw pinned H2D bandwidth of this box (context for e2e)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(3):
+        d_in[0].copy_(pin[0], non_blocking=True)
+    torch.cuda.synchronize(); h2d_gbs = 3 * B * N_SAMPLES * 4 / (time.perf_counter() - t0) / 1e9
     for i in range(3):
         e2e_step(i)
     barrier()
@@ -333,7 +339,7 @@ def main():
             "data": "soundscape.wav (reference repo fixture) tiled; weights = reference BirdNET_GLOBAL_6K_V2.4_Model_FP32.tflite",
             "config": config, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * N_SAMPLES * 4), "d2h_bytes_per_step": int(B * TOP_K * 8),
-                    "api": "bnb_analyze_batch(float32 PCM in pinned host memory) -> top-10 (idx, conf)"},
+                    "api": "bnb_analyze_batch(float32 PCM in pinned host memory) -> top-10 (idx, conf)", "h2d_gbs_measured": h2d_gbs},
             "roofline": {"bound": "tensor", "kernel": "pointwise 1x1 conv GEMMs (expand + project, %d launches/step)" % (pw_launches // max(1, a.steps)),
                          "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
                          "peak_source": which + " bf16 dense (sustained)", "share_of_step": pw_ms / total_ms if total_ms else None},

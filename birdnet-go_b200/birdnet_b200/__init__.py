@@ -68,6 +68,7 @@ SYMBOLS = {
     "bnb_last_device_ms": (C.c_float, [C.c_void_p]),
     "bnb_profile_begin": (C.c_int, [C.c_void_p]),
     "bnb_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "bnb_profile_launches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bnb_describe_model": (C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "bnb_debug_read_tensor": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "bnb_debug_keep_intermediates": (C.c_int, [C.c_void_p, C.c_int]),
@@ -224,6 +225,13 @@ class B200Classifier:
         cnt = np.zeros(n, np.int64)
         _check(self._lib.bnb_profile_end(self._h, _ptr(ms), _ptr(cnt), n))
         return {c: (float(ms[i]), int(cnt[i])) for i, c in enumerate(self.PROFILE_CATEGORIES)}
+
+    def profile_launches(self, cap=1 << 16):
+        """[(category, ms)] per launch of the region closed by the last profile_end(), in issue order."""
+        ms = np.zeros(cap, np.float32)
+        cat = np.zeros(cap, np.int32)
+        n = _check(self._lib.bnb_profile_launches(self._h, _ptr(ms), _ptr(cat), cap))
+        return [(self.PROFILE_CATEGORIES[int(cat[i])], float(ms[i])) for i in range(n)]
 
     def keep_intermediates(self, on=True):
         _check(self._lib.bnb_debug_keep_intermediates(self._h, int(on)))

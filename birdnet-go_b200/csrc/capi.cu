@@ -181,6 +181,12 @@ int bnb_profile_end(bnb_classifier* h, float* ms, int64_t* launches, int cap) {
   return rc != BNB_OK ? rc : n;
 }
 
+int bnb_profile_launches(bnb_classifier* h, float* ms, int32_t* cat, int cap) {
+  if (int rc = check_handle(h)) return rc;
+  if (!ms || !cat || cap <= 0) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL ms/cat or cap <= 0");
+  return h->eng->profile_launches(ms, cat, cap);
+}
+
 int bnb_describe_model(const void* tflite, size_t tflite_len, char* json, size_t cap) {
   if (!tflite || !json) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL pointer");
   std::string s;

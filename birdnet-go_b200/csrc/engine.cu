@@ -482,13 +482,21 @@ int Engine::profile_end(float* ms, long long* launches, int cap) {
   BNB_CUDA(cudaDeviceSynchronize());
   profiling_ = false;
   for (int i = 0; i < cap; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  prof_last_ms_.assign(prof_cat_.size(), 0.f);
   for (size_t i = 0; i < prof_cat_.size(); ++i) {
     float t = 0.f;
     BNB_CUDA(cudaEventElapsedTime(&t, prof_ev_[2 * i], prof_ev_[2 * i + 1]));
+    prof_last_ms_[i] = t;
     const int c = prof_cat_[i];
     if (c < cap) { ms[c] += t; launches[c]++; }
   }
   return C_COUNT;
+}
+
+int Engine::profile_launches(float* ms, int* cat, int cap) const {
+  const int n = (int)std::min<size_t>(prof_last_ms_.size(), (size_t)cap);
+  for (int i = 0; i < n; ++i) { ms[i] = prof_last_ms_[i]; cat[i] = prof_cat_[i]; }
+  return n;
 }
 
 long long Engine::read_tensor(int tensor, float* out, size_t cap) {

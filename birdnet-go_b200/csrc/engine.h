@@ -55,6 +55,7 @@ class Engine {
   enum Cat : int { C_MINMAX = 0, C_FRONTEND, C_STEM_MIX, C_PW_EXPAND, C_DW, C_SE, C_PW_PROJECT, C_POST_CONV, C_ROW_MEAN, C_FC, C_TOPK, C_COUNT };
   void profile_begin();
   int profile_end(float* ms, long long* launches, int cap);
+  int profile_launches(float* ms, int* cat, int cap) const;   // per launch, in issue order, of the last profile_end
   long long read_tensor(int tensor, float* out, size_t cap);
 
  private:
@@ -82,6 +83,7 @@ class Engine {
   bool profiling_ = false;
   std::vector<cudaEvent_t> prof_ev_;          // pairs (start, stop)
   std::vector<int> prof_cat_;
+  std::vector<float> prof_last_ms_;
   size_t prof_used_ = 0;
 
   int device_ = 0, n_species_ = 0, n_samples_ = 0, emb_dim_ = 0, max_batch_ = 256, micro_ = 32, precision_ = BNB_PRECISION_F32;

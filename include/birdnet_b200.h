@@ -143,6 +143,9 @@ BNB_API float bnb_last_device_ms(const bnb_classifier* h);
  * the summed milliseconds and the launch count; returns the number of categories (11). */
 BNB_API int bnb_profile_begin(bnb_classifier* h);
 BNB_API int bnb_profile_end(bnb_classifier* h, float* ms, int64_t* launches, int cap);
+/* Per-launch device times (ms) and categories of the region closed by the last bnb_profile_end, in issue order;
+ * returns the number of entries written (<= cap). */
+BNB_API int bnb_profile_launches(bnb_classifier* h, float* ms, int32_t* cat, int cap);
 /* JSON description of the layer plan extracted from a .tflite (no GPU needed). Returns bytes
  * written (excluding NUL) or a negative status; `cap` too small -> BNB_ERR_INVALID_ARGUMENT. */
 BNB_API int bnb_describe_model(const void* tflite, size_t tflite_len, char* json, size_t cap);
