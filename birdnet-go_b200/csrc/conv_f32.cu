@@ -219,7 +219,7 @@ pw_conv_kernel(const PwArgs a) {
 // comes for free: partial[b][part][c] (deterministic, no atomics), reduced by se_mlp_kernel.
 constexpr int kDwMaxThreads = 256;
 
-__global__ void __launch_bounds__(kDwMaxThreads)
+__global__ void __launch_bounds__(kDwMaxThreads, 4)
 dw_conv_kernel(const DwArgs a) {
   __shared__ float4 s_red[kDwMaxThreads];
   const int c4_per_cta = a.c4_per_cta, lanes = blockDim.x / c4_per_cta;    // pixel lanes per CTA
@@ -351,7 +351,7 @@ int dw_parts(int B, int Ho, int Wo, int C) {
   const int c4_per_cta = c4n / groups;
   const int lanes = kDwMaxThreads / c4_per_cta > 0 ? kDwMaxThreads / c4_per_cta : 1;
   const int npix = Ho * Wo;
-  int parts = (4 * kNumSMs + B * groups - 1) / (B * groups);
+  int parts = (8 * kNumSMs + B * groups - 1) / (B * groups);
   const int max_parts = (npix + 8 * lanes - 1) / (8 * lanes);
   if (parts > max_parts) parts = max_parts;
   if (parts < 1) parts = 1;

@@ -33,8 +33,9 @@ namespace {
 
 constexpr int kBM = 128;            // rows per tile = TMEM lanes = UMMA M
 constexpr int kBK = 64;             // K per stage: 64 fp16 = one 128-byte swizzle row
-constexpr int kThreads = 320;
-constexpr int kEpiWarps = 4, kMmaWarp = 4, kLoadWarp = 5, kProdWarp0 = 6, kProdThreads = 128;
+constexpr int kThreads = 576;         // 18 warps: 8 epilogue, 1 MMA issuer, 1 loader, 8 converters
+constexpr int kEpiWarps = 8, kMmaWarp = 8, kLoadWarp = 9, kProdWarp0 = 10, kProdThreads = 256;
+constexpr int kRowsPerPass = kProdThreads / 8, kPasses = 128 / kRowsPerPass;   // converter: 32 rows per pass, 4 passes
 constexpr int kAccCols = 256;       // TMEM columns per accumulator buffer
 constexpr uint32_t kSpinLimit = 1u << 28;
 
@@ -107,6 +108,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -159,8 +170,8 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
 
   if (warp >= kProdWarp0) {
     // ============================== A converters (4 warps) ====================================
-    const int pt = threadIdx.x - kProdWarp0 * 32;           // 0..127
-    const int c = pt & 7, r0 = pt >> 3;                     // this thread: 16-byte chunk c of rows r0 + 16*q
+    const int pt = threadIdx.x - kProdWarp0 * 32;           // 0..255
+    const int c = pt & 7, r0 = pt >> 3;                     // this thread: 16-byte chunk c of rows r0 + 32*q
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / a.n_tiles) * kBM;
@@ -169,13 +180,13 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
         uint8_t* buf = base_ptr + (size_t)s * stage_bytes;
         const int k = ks * kBK + c * 8;
         const bool k_live = k < a.k_pad;                     // chunk read by some MMA of this stage
-        float v[8][8];
+        float v[kPasses][8];
         mbar_wait(raw_bar(s), ph);
         if (k_live) {
           float g[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int r = r0 + 16 * q, m = m0 + r;
+          for (int q = 0; q < kPasses; ++q) {
+            const int r = r0 + kRowsPerPass * q, m = m0 + r;
             if (m < a.M && k < a.K) {
               const float4 x0 = *reinterpret_cast<const float4*>(buf + r * pitch + c * 32);
               float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -190,8 +201,8 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
           if (a.gate) {
             int last_chunk = -1;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int m = m0 + r0 + 16 * q;
+            for (int q = 0; q < kPasses; ++q) {
+              const int m = m0 + r0 + kRowsPerPass * q;
               if (m < a.M && k < a.K) {
                 const int chunk = m / a.rows_per_chunk;
                 if (chunk != last_chunk) {
@@ -214,8 +225,8 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
           uint8_t* hi = buf;
           uint8_t* lo = buf + a_bytes;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int r = r0 + 16 * q;
+          for (int q = 0; q < kPasses; ++q) {
+            const int r = r0 + kRowsPerPass * q;
             uint32_t ph_[4], pl_[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -289,46 +300,65 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
       }
     }
   } else {
-    // ============================== epilogue (warps 0-3) =======================================
+    // ============================== epilogue (warps 0-7) =======================================
+    // warp w owns TMEM lanes 32*(w%4).. (rows) and one half of the tile's columns; 32 columns per tcgen05.ld,
+    // bias staged once per tile in a warp-private shared-memory strip (broadcast LDS), 128 B contiguous stores per row.
+    const int quarter = warp & 3, half = warp >> 2;
+    float* s_bias = reinterpret_cast<float*>(base_ptr + (size_t)a.stages * stage_bytes + ((8u * (3 * a.stages + 4) + 16 + 15) & ~15u)) + warp * 128;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
       const int n0 = nt * a.bn;
       const int bn = min(a.bn, a.n_pad - n0);
+      const int c_split = min(bn, ((bn / 2 + 31) / 32) * 32);
+      const int c_begin = half ? c_split : 0, c_end = half ? bn : c_split;
       const int buf = tcount & 1;
+      // bias strip for this warp's columns (issued before the accumulator wait so its latency is hidden)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cc = c_begin + lane + 32 * j;
+        if (cc < c_end) s_bias[lane + 32 * j] = __ldg(a.bias + n0 + cc);     // bias is padded to n_pad + 16 at upload
+      }
+      __syncwarp();
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
       tc_fence_after();
-      const int m = mt * kBM + warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * kAccCols;
+      const int m = mt * kBM + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kAccCols;
       float* crow = a.C + (size_t)m * a.N;
       const float* rrow = a.residual ? a.residual + (size_t)m * a.N : nullptr;
-      for (int c0 = 0; c0 < bn; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        uint32_t r[32];
+        const bool wide = (c_end - c0) >= 32;
+        if (wide) tmem_ld32(taddr + (uint32_t)c0, r); else tmem_ld16(taddr + (uint32_t)c0, r);
+        const int ncols = wide ? 32 : 16;
+        const int n = n0 + c0;
+        float4 res[8];
+        const bool full = (m < a.M) && (n + ncols <= a.N) && a.c_vec4;
+        if (rrow && full) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) if (4 * j4 < ncols) res[j4] = __ldg(reinterpret_cast<const float4*>(rrow + n) + j4);
+        }
         tmem_ld_wait();
         if (m < a.M) {
-          const int n = n0 + c0;
-          if (n + 16 <= a.N) {
+          if (full) {
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias + n) + j4);
-              float4 o;
-              o.x = act_apply(__uint_as_float(r[4 * j4 + 0]) + bz.x, a.act);
-              o.y = act_apply(__uint_as_float(r[4 * j4 + 1]) + bz.y, a.act);
-              o.z = act_apply(__uint_as_float(r[4 * j4 + 2]) + bz.z, a.act);
-              o.w = act_apply(__uint_as_float(r[4 * j4 + 3]) + bz.w, a.act);
-              if (rrow) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + n) + j4);
-                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if (4 * j4 < ncols) {
+                const float4 bz = *reinterpret_cast<const float4*>(s_bias + (c0 - c_begin) + 4 * j4);
+                float4 o;
+                o.x = act_apply(__uint_as_float(r[4 * j4 + 0]) + bz.x, a.act);
+                o.y = act_apply(__uint_as_float(r[4 * j4 + 1]) + bz.y, a.act);
+                o.z = act_apply(__uint_as_float(r[4 * j4 + 2]) + bz.z, a.act);
+                o.w = act_apply(__uint_as_float(r[4 * j4 + 3]) + bz.w, a.act);
+                if (rrow) { o.x += res[j4].x; o.y += res[j4].y; o.z += res[j4].z; o.w += res[j4].w; }
+                *(reinterpret_cast<float4*>(crow + n) + j4) = o;
               }
-              if (a.c_vec4) *(reinterpret_cast<float4*>(crow + n) + j4) = o;
-              else { crow[n + 4 * j4] = o.x; crow[n + 4 * j4 + 1] = o.y; crow[n + 4 * j4 + 2] = o.z; crow[n + 4 * j4 + 3] = o.w; }
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (n + j < a.N) {
-                float o = act_apply(__uint_as_float(r[j]) + __ldg(a.bias + n + j), a.act);
+            for (int j = 0; j < 32; ++j) {
+              if (j < ncols && n + j < a.N) {
+                float o = act_apply(__uint_as_float(r[j]) + s_bias[(c0 - c_begin) + j], a.act);
                 if (rrow) o += __ldg(rrow + n + j);
                 crow[n + j] = o;
               }
@@ -336,6 +366,7 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
           }
         }
       }
+      __syncwarp();                      // the bias strip is rewritten at the next tile
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
     }
@@ -393,7 +424,7 @@ static void choose_tiling(const PwTcLayer& L, int M, int* bn_out, int* stages_ou
   if (L.k_stages >= 3) while (bn > 128) { ++n_tiles; bn = bn_of(n_tiles); }            // deeper ring for long K
   while (m_tiles * ((L.n_pad + bn - 1) / bn) < kNumSMs && bn > 64) { ++n_tiles; bn = bn_of(n_tiles); }
   const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
-  int stages = (int)((220 * 1024) / stage);
+  int stages = (int)((216 * 1024) / stage);
   if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
   *bn_out = bn; *stages_out = stages;
@@ -439,7 +470,7 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   int bn = 0, stages = 0;
   choose_tiling(L, p.M, &bn, &stages);
   const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
-  const size_t smem_bytes = (size_t)stages * stage + 1024 /*alignment*/ + 8 * (3 * stages + 4) + 16;
+  const size_t smem_bytes = (size_t)stages * stage + 1024 /*alignment*/ + ((8 * (3 * stages + 4) + 16 + 15) & ~15) + kEpiWarps * 128 * sizeof(float);
   if (smem_bytes > 227 * 1024) throw std::runtime_error("pw_tc: shared memory budget exceeded");
   if (smem_bytes > max_set) {
     BNB_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
