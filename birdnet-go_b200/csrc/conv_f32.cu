@@ -214,45 +214,65 @@ pw_conv_kernel(const PwArgs a) {
 // 3x3 depthwise conv + bias + SiLU, NHWC, zero padding 1 on each side (stride 1 SAME, or the
 // reference's explicit PAD(1,1) + VALID stride 2).  One thread = 4 channels of one output pixel.
 // =================================================================================================
-// Grid (parts, B, channel groups).  A thread owns 4 channels (its 9 taps + bias live in registers) and walks
-// over the output pixels of its part; the SiLU outputs are also summed per channel so the squeeze-excite mean
-// comes for free: partial[b][part][c] (deterministic, no atomics), reduced by se_mlp_kernel.
+// Grid (Ho, B, channel groups): one CTA = one output row of one chunk.  A thread owns 4 channels (its 9 taps +
+// bias live in registers) and walks along a segment of the row with a sliding 3x3 register window, so each new
+// output costs 3 (stride 1) or 6 (stride 2) 16-byte loads instead of 9, all issued before the previous output's
+// math.  The SiLU outputs are also summed per channel: partial[b][ho][c] is the squeeze-excite row sum
+// (deterministic, no atomics), reduced by se_gate_kernel.
 constexpr int kDwMaxThreads = 256;
 
-__global__ void __launch_bounds__(kDwMaxThreads, 4)
+template <int STRIDE>
+__global__ void __launch_bounds__(kDwMaxThreads)
 dw_conv_kernel(const DwArgs a) {
   __shared__ float4 s_red[kDwMaxThreads];
-  const int c4_per_cta = a.c4_per_cta, lanes = blockDim.x / c4_per_cta;    // pixel lanes per CTA
+  const int c4_per_cta = a.c4_per_cta, lanes = blockDim.x / c4_per_cta;    // row segments per CTA
   const int cl = threadIdx.x % c4_per_cta, pl = threadIdx.x / c4_per_cta;
-  const int c4 = blockIdx.z * c4_per_cta + cl, b = blockIdx.y, part = blockIdx.x;
+  const int c4 = blockIdx.z * c4_per_cta + cl, b = blockIdx.y, ho = blockIdx.x;
   const int c4n = a.C / 4;
-  const int npix = a.Ho * a.Wo, per = (npix + gridDim.x - 1) / gridDim.x;
-  const int p_begin = part * per, p_end = min(npix, p_begin + per);
+  const int seg = (a.Wo + lanes - 1) / lanes;
+  const int w0 = pl * seg, w1 = min(a.Wo, w0 + seg);
   float4 w[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const float4*>(a.w + t * a.C) + c4);
   const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias) + c4);
-  const float4* inb = reinterpret_cast<const float4*>(a.in + (size_t)b * a.H * a.W * a.C) + c4;
-  float4* outb = reinterpret_cast<float4*>(a.out + (size_t)b * npix * a.C) + c4;
-  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = p_begin + pl; p < p_end; p += lanes) {
-    const int ho = p / a.Wo, wo = p - ho * a.Wo;
-    float4 acc = bz;
+  const float4* rowp[3];
+  bool rv[3];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int hi = ho * STRIDE - 1 + kh;
+    rv[kh] = hi >= 0 && hi < a.H;                                          // uniform across the CTA
+    rowp[kh] = reinterpret_cast<const float4*>(a.in + ((size_t)b * a.H + (rv[kh] ? hi : 0)) * a.W * a.C) + c4;
+  }
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto ld = [&](int kh, int wi) { return (rv[kh] && wi >= 0 && wi < a.W) ? __ldg(rowp[kh] + (size_t)wi * c4n) : zero; };
+  float4* outp = reinterpret_cast<float4*>(a.out + ((size_t)b * a.Ho + ho) * a.Wo * a.C) + c4;
+  float4 sum = zero;
+  float4 x[3][3];
+  if (w0 < w1) {
+    if (STRIDE == 1) {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) { x[kh][1] = ld(kh, w0 - 1); x[kh][2] = ld(kh, w0); }
+    } else {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) x[kh][2] = ld(kh, 2 * w0 - 1);
+    }
+  }
+  for (int wo = w0; wo < w1; ++wo) {
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      const int hi = ho * a.stride - 1 + kh;
-      if (hi < 0 || hi >= a.H) continue;
+      if (STRIDE == 1) { x[kh][0] = x[kh][1]; x[kh][1] = x[kh][2]; x[kh][2] = ld(kh, wo + 1); }
+      else { x[kh][0] = x[kh][2]; x[kh][1] = ld(kh, 2 * wo); x[kh][2] = ld(kh, 2 * wo + 1); }
+    }
+    float4 acc = bz;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int wi = wo * a.stride - 1 + kw;
-        if (wi < 0 || wi >= a.W) continue;
-        const float4 x = __ldg(inb + (size_t)(hi * a.W + wi) * c4n);
-        const float4 ww = w[kh * 3 + kw];
-        acc.x = fmaf(x.x, ww.x, acc.x); acc.y = fmaf(x.y, ww.y, acc.y); acc.z = fmaf(x.z, ww.z, acc.z); acc.w = fmaf(x.w, ww.w, acc.w);
+        const float4 v = x[kh][kw], ww = w[kh * 3 + kw];
+        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y); acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
       }
-    }
     acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w);
-    outb[(size_t)p * c4n] = acc;
+    outp[(size_t)wo * c4n] = acc;
     sum.x += acc.x; sum.y += acc.y; sum.z += acc.z; sum.w += acc.w;
   }
   if (a.partial != nullptr) {
@@ -260,7 +280,7 @@ dw_conv_kernel(const DwArgs a) {
     __syncthreads();
     if (pl == 0) {
       for (int l = 1; l < lanes; ++l) { const float4 o = s_red[l * c4_per_cta + cl]; sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w; }
-      reinterpret_cast<float4*>(a.partial + ((size_t)b * gridDim.x + part) * a.C)[c4] = sum;
+      reinterpret_cast<float4*>(a.partial + ((size_t)b * a.Ho + ho) * a.C)[c4] = sum;
     }
   }
 }
@@ -344,19 +364,7 @@ void launch_pw_conv(const PwArgs& a, cudaStream_t s, LaunchCounter& lc) {
   BNB_LAUNCH_CHECK(lc);
 }
 
-int dw_parts(int B, int Ho, int Wo, int C) {
-  // enough CTAs to fill the machine (~4 per SM), at least ~8 pixels per pixel-lane
-  const int c4n = C / 4;
-  const int groups = (c4n + kDwMaxThreads - 1) / kDwMaxThreads;
-  const int c4_per_cta = c4n / groups;
-  const int lanes = kDwMaxThreads / c4_per_cta > 0 ? kDwMaxThreads / c4_per_cta : 1;
-  const int npix = Ho * Wo;
-  int parts = (8 * kNumSMs + B * groups - 1) / (B * groups);
-  const int max_parts = (npix + 8 * lanes - 1) / (8 * lanes);
-  if (parts > max_parts) parts = max_parts;
-  if (parts < 1) parts = 1;
-  return parts;
-}
+int dw_parts(int B, int Ho, int Wo, int C) { (void)B; (void)Wo; (void)C; return Ho; }   // one partial sum per output row
 
 void launch_dw_conv(const DwArgs& a0, cudaStream_t s, LaunchCounter& lc) {
   DwArgs a = a0;
@@ -364,10 +372,12 @@ void launch_dw_conv(const DwArgs& a0, cudaStream_t s, LaunchCounter& lc) {
   const int groups = (c4n + kDwMaxThreads - 1) / kDwMaxThreads;
   if (c4n % groups) throw std::runtime_error("dw_conv: channel count not divisible into CTA groups");
   a.c4_per_cta = c4n / groups;
-  const int lanes = kDwMaxThreads / a.c4_per_cta > 0 ? kDwMaxThreads / a.c4_per_cta : 1;
-  const int parts = a.parts > 0 ? a.parts : dw_parts(a.B, a.Ho, a.Wo, a.C);
-  dim3 grid(parts, a.B, groups);
-  dw_conv_kernel<<<grid, lanes * a.c4_per_cta, 0, s>>>(a);
+  int lanes = kDwMaxThreads / a.c4_per_cta > 0 ? kDwMaxThreads / a.c4_per_cta : 1;
+  if (lanes > a.Wo) lanes = a.Wo;
+  dim3 grid(a.Ho, a.B, groups);
+  if (a.stride == 1) dw_conv_kernel<1><<<grid, lanes * a.c4_per_cta, 0, s>>>(a);
+  else if (a.stride == 2) dw_conv_kernel<2><<<grid, lanes * a.c4_per_cta, 0, s>>>(a);
+  else throw std::runtime_error("dw_conv: unsupported stride");
   BNB_LAUNCH_CHECK(lc);
 }
 

@@ -60,6 +60,8 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
     throw unsupported_model("stem geometry differs from BirdNET v2.4 (4x8/s2, 2->24, 1x1 48->24)");
   if (P.post.out_h != 1) throw unsupported_model("post conv must reduce the mel axis to 1");
   for (const BlockPlan& b : P.blocks)
+    if (b.has_se && b.out_h > kMaxDwParts) throw unsupported_model("squeeze-excite block taller than the row-sum buffer");
+  for (const BlockPlan& b : P.blocks)
     if (b.cin % 4 || b.cexp % 4 || b.cout % 4 || (b.has_se && (b.cexp > 1536 || b.cse > 64))) throw unsupported_model("block channel counts");
   n_species_ = P.n_species(); n_samples_ = F.n_samples; emb_dim_ = P.emb_dim();
 
