@@ -180,7 +180,7 @@ void Engine::upload_weights(const NetPlan& P) {
   const bool tc = (precision_ == BNB_PRECISION_F16X3);
   auto upconv = [&](const ConvW& c, size_t n, bool gemm = false) {
     DevConv d; d.w = up(c.w, n);
-    std::vector<float> z((size_t)c.cout + 16, 0.f);      // +16: the tensor-core epilogue reads bias in float4s up to n_pad
+    std::vector<float> z((size_t)c.cout + 64, 0.f);      // +64: the tensor-core epilogue stages bias strips a little past n_pad
     if (c.b) memcpy(z.data(), c.b, (size_t)c.cout * sizeof(float));
     d.b = up(z.data(), z.size());
     if (gemm && tc) {                                    // fp16 hi/lo split + swizzled smem image for pw_tc.cu

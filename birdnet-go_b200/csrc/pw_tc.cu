@@ -20,6 +20,9 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -120,6 +123,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+#define BNB_TRACE(ev, iter) do { if (a.trace && blockIdx.x == 0 && (iter) < 64) a.trace[(ev) * 64 + (iter)] = clock64(); } while (0)
+
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
   if (act == ACT_RELU) return fmaxf(v, 0.f);
@@ -131,7 +136,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // read into registers by the 4 producer warps, and is then overwritten IN PLACE by the fp16 hi (16 KB) and lo (16 KB)
 // 128B-swizzled K-major tiles the MMA consumes.
 __global__ void __launch_bounds__(kThreads, 1)
-pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
+pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap c_map) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -141,13 +146,13 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
   const uint32_t a_bytes = kBM * 128u;                     // one fp16 [128][64] slab (16 KB); raw fp32 uses 2 of them
   const uint32_t b_bytes = (uint32_t)a.bn * 128u;          // one fp16 [bn][64] slab
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  const uint32_t bars = base + (uint32_t)a.stages * stage_bytes;   // rawfull[S], full[S], empty[S], tfull[2], tempty[2], tmem ptr
+  const uint32_t bars = base + (uint32_t)a.stages * stage_bytes + 8u * 4096u;   // [8 x 4 KB epilogue staging] rawfull[S], full[S], empty[S], tfull[2], tempty[2], tmem ptr
   auto raw_bar = [&](int s) { return bars + 8u * s; };
   auto full_bar = [&](int s) { return bars + 8u * (a.stages + s); };
   auto empty_bar = [&](int s) { return bars + 8u * (2 * a.stages + s); };
   auto tfull_bar = [&](int b) { return bars + 8u * (3 * a.stages + b); };
   auto tempty_bar = [&](int b) { return bars + 8u * (3 * a.stages + 2 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (size_t)a.stages * stage_bytes + 8u * (3 * a.stages + 4));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (size_t)a.stages * stage_bytes + 8u * 4096u + 8u * (3 * a.stages + 4));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(raw_bar(s), 1); mbar_init(full_bar(s), kProdThreads + 1); mbar_init(empty_bar(s), 1); }
@@ -181,9 +186,24 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
         const int k = ks * kBK + c * 8;
         const bool k_live = k < a.k_pad;                     // chunk read by some MMA of this stage
         float v[kPasses][8];
+        // SE gate of each row's chunk: independent of the A tile, so the loads are issued BEFORE the wait on the
+        // TMA data and their L2 latency hides behind it (they were the converter's critical path).
+        float4 g0[kPasses], g1[kPasses];
+        if (a.gate && k_live) {
+#pragma unroll
+          for (int q = 0; q < kPasses; ++q) {
+            const int m = m0 + r0 + kRowsPerPass * q;
+            g0[q] = make_float4(1.f, 1.f, 1.f, 1.f); g1[q] = g0[q];
+            if (m < a.M && k < a.K) {
+              const float* gp = a.gate + (size_t)(m / a.rows_per_chunk) * a.K + k;
+              g0[q] = __ldg(reinterpret_cast<const float4*>(gp));
+              if (k + 4 < a.K) g1[q] = __ldg(reinterpret_cast<const float4*>(gp + 4));
+            }
+          }
+        }
         mbar_wait(raw_bar(s), ph);
+        if (pt == 0) BNB_TRACE(1, it);
         if (k_live) {
-          float g[8];
 #pragma unroll
           for (int q = 0; q < kPasses; ++q) {
             const int r = r0 + kRowsPerPass * q, m = m0 + r;
@@ -199,23 +219,10 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
             }
           }
           if (a.gate) {
-            int last_chunk = -1;
 #pragma unroll
             for (int q = 0; q < kPasses; ++q) {
-              const int m = m0 + r0 + kRowsPerPass * q;
-              if (m < a.M && k < a.K) {
-                const int chunk = m / a.rows_per_chunk;
-                if (chunk != last_chunk) {
-                  const float* gp = a.gate + (size_t)chunk * a.K + k;
-                  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
-                  float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (k + 4 < a.K) g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
-                  g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
-                  last_chunk = chunk;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[q][i] *= g[i];
-              }
+              v[q][0] *= g0[q].x; v[q][1] *= g0[q].y; v[q][2] *= g0[q].z; v[q][3] *= g0[q].w;
+              v[q][4] *= g1[q].x; v[q][5] *= g1[q].y; v[q][6] *= g1[q].z; v[q][7] *= g1[q].w;
             }
           }
         }
@@ -242,6 +249,7 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
         }
         fence_proxy_async();
         mbar_arrive(full_bar(s));
+        if (pt == 0) BNB_TRACE(2, it);
       }
     }
   } else if (warp == kLoadWarp) {
@@ -256,6 +264,7 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t dst = base + (uint32_t)s * stage_bytes;
         if (lane == 0) {
+          BNB_TRACE(0, it);
           // A: ONE 2-D TMA request per stage (box = box_k x 128 rows of fp32; out-of-range rows / columns arrive as zeros)
           mbar_arrive_expect_tx(raw_bar(s), (uint32_t)a.box_k * 4u * kBM);
           tma_load_2d(dst, &a_map, ks * kBK, m0, raw_bar(s));
@@ -278,11 +287,13 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
         const uint32_t idesc = make_idesc((uint32_t)bn);
         const int buf = tcount & 1;
         mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);
+        BNB_TRACE(7, tcount);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccCols;
         for (int ks = 0; ks < k_stages; ++ks, ++it) {
           const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
           mbar_wait(full_bar(s), ph);
+          BNB_TRACE(3, it);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + a_bytes);
@@ -295,16 +306,23 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
             umma(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1);
           }
           umma_commit(empty_bar(s));                        // smem stage reusable once these MMAs retire
+          BNB_TRACE(4, it);
         }
         umma_commit(tfull_bar(buf));                        // accumulator complete
       }
     }
   } else {
     // ============================== epilogue (warps 0-7) =======================================
-    // warp w owns TMEM lanes 32*(w%4).. (rows) and one half of the tile's columns; 32 columns per tcgen05.ld,
-    // bias staged once per tile in a warp-private shared-memory strip (broadcast LDS), 128 B contiguous stores per row.
+    // warp w owns TMEM lanes 32*(w%4).. (rows) and one half of the tile's columns, 32 columns per tcgen05.ld.
+    // A thread holds one ROW of the chunk, so direct stores would scatter 16-byte pieces over 32 different rows
+    // (measured: 7.5-19 k cycles per tile).  Instead the 32x32 sub-tile is written to a warp-private, 128B-swizzled
+    // shared-memory buffer (conflict-free 16 B stores) and leaves through ONE 2-D TMA tensor store, which also clips
+    // rows >= M and columns >= N.  Layers whose row pitch is not 16-byte aligned (the 6522-wide head) keep direct stores.
     const int quarter = warp & 3, half = warp >> 2;
-    float* s_bias = reinterpret_cast<float*>(base_ptr + (size_t)a.stages * stage_bytes + ((8u * (3 * a.stages + 4) + 16 + 15) & ~15u)) + warp * 128;
+    uint8_t* extra = base_ptr + (size_t)a.stages * stage_bytes;
+    float* s_bias = reinterpret_cast<float*>(extra + 8 * 4096 + ((8u * (3 * a.stages + 4) + 16 + 15) & ~15u)) + warp * 128;
+    uint8_t* s_out = extra + warp * 4096;                  // 32 rows x 128 B, 1024-aligned
+    const uint32_t s_out_u32 = smem_u32(s_out);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
@@ -317,51 +335,56 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int cc = c_begin + lane + 32 * j;
-        if (cc < c_end) s_bias[lane + 32 * j] = __ldg(a.bias + n0 + cc);     // bias is padded to n_pad + 16 at upload
+        s_bias[lane + 32 * j] = (cc < c_end + 16 && n0 + cc < a.n_pad + 16) ? __ldg(a.bias + n0 + cc) : 0.f;   // bias is padded to n_pad + 16
       }
       __syncwarp();
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
+      if (threadIdx.x == 0) BNB_TRACE(5, tcount);
       tc_fence_after();
-      const int m = mt * kBM + quarter * 32 + lane;
+      const int m_w = mt * kBM + quarter * 32;             // first row of this warp
+      const int m = m_w + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kAccCols;
       float* crow = a.C + (size_t)m * a.N;
       const float* rrow = a.residual ? a.residual + (size_t)m * a.N : nullptr;
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t r[32];
-        const bool wide = (c_end - c0) >= 32;
-        if (wide) tmem_ld32(taddr + (uint32_t)c0, r); else tmem_ld16(taddr + (uint32_t)c0, r);
-        const int ncols = wide ? 32 : 16;
+        tmem_ld32(taddr + (uint32_t)c0, r);               // columns beyond bn are never stored (clipped / masked)
         const int n = n0 + c0;
         float4 res[8];
-        const bool full = (m < a.M) && (n + ncols <= a.N) && a.c_vec4;
-        if (rrow && full) {
+        if (rrow) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) if (4 * j4 < ncols) res[j4] = __ldg(reinterpret_cast<const float4*>(rrow + n) + j4);
+          for (int j4 = 0; j4 < 8; ++j4)
+            res[j4] = (m < a.M && n + 4 * j4 + 4 <= a.N) ? __ldg(reinterpret_cast<const float4*>(rrow + n) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (a.c_vec4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous TMA store has read the buffer (lane 0 owns the groups)
+        __syncwarp();
         tmem_ld_wait();
-        if (m < a.M) {
-          if (full) {
+        if (a.c_vec4) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              if (4 * j4 < ncols) {
-                const float4 bz = *reinterpret_cast<const float4*>(s_bias + (c0 - c_begin) + 4 * j4);
-                float4 o;
-                o.x = act_apply(__uint_as_float(r[4 * j4 + 0]) + bz.x, a.act);
-                o.y = act_apply(__uint_as_float(r[4 * j4 + 1]) + bz.y, a.act);
-                o.z = act_apply(__uint_as_float(r[4 * j4 + 2]) + bz.z, a.act);
-                o.w = act_apply(__uint_as_float(r[4 * j4 + 3]) + bz.w, a.act);
-                if (rrow) { o.x += res[j4].x; o.y += res[j4].y; o.z += res[j4].z; o.w += res[j4].w; }
-                *(reinterpret_cast<float4*>(crow + n) + j4) = o;
-              }
-            }
-          } else {
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bz = *reinterpret_cast<const float4*>(s_bias + (c0 - c_begin) + 4 * j4);
+            float4 o;
+            o.x = act_apply(__uint_as_float(r[4 * j4 + 0]) + bz.x, a.act);
+            o.y = act_apply(__uint_as_float(r[4 * j4 + 1]) + bz.y, a.act);
+            o.z = act_apply(__uint_as_float(r[4 * j4 + 2]) + bz.z, a.act);
+            o.w = act_apply(__uint_as_float(r[4 * j4 + 3]) + bz.w, a.act);
+            if (rrow) { o.x += res[j4].x; o.y += res[j4].y; o.z += res[j4].z; o.w += res[j4].w; }
+            *reinterpret_cast<float4*>(s_out + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(reinterpret_cast<uint64_t>(&c_map)), "r"(n), "r"(m_w), "r"(s_out_u32) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else if (m < a.M) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < ncols && n + j < a.N) {
-                float o = act_apply(__uint_as_float(r[j]) + s_bias[(c0 - c_begin) + j], a.act);
-                if (rrow) o += __ldg(rrow + n + j);
-                crow[n + j] = o;
-              }
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < bn && n + j < a.N) {
+              float o = act_apply(__uint_as_float(r[j]) + s_bias[(c0 - c_begin) + j], a.act);
+              if (rrow) o += __ldg(rrow + n + j);
+              crow[n + j] = o;
             }
           }
         }
@@ -369,7 +392,9 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
       __syncwarp();                      // the bias strip is rewritten at the next tile
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
+      if (threadIdx.x == 0) BNB_TRACE(6, tcount);
     }
+    if (a.c_vec4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores complete before exit
   }
 
   tc_fence_before();
@@ -419,12 +444,12 @@ PwTcLayer pw_tc_prepare(const float* w, int N, int K, std::vector<uint8_t>* imag
 static void choose_tiling(const PwTcLayer& L, int M, int* bn_out, int* stages_out) {
   const int m_tiles = (M + kBM - 1) / kBM;
   int n_tiles = (L.n_pad + 255) / 256;
-  auto bn_of = [&](int nt) { return ((L.n_pad + nt - 1) / nt + 15) / 16 * 16; };
+  auto bn_of = [&](int nt) { return nt == 1 ? L.n_pad : ((L.n_pad + nt - 1) / nt + 31) / 32 * 32; };   // 32-column TMA store boxes must not spill into the next n-tile
   int bn = bn_of(n_tiles);
   if (L.k_stages >= 3) while (bn > 128) { ++n_tiles; bn = bn_of(n_tiles); }            // deeper ring for long K
   while (m_tiles * ((L.n_pad + bn - 1) / bn) < kNumSMs && bn > 64) { ++n_tiles; bn = bn_of(n_tiles); }
   const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
-  int stages = (int)((216 * 1024) / stage);
+  int stages = (int)((184 * 1024) / stage);
   if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
   *bn_out = bn; *stages_out = stages;
@@ -432,13 +457,13 @@ static void choose_tiling(const PwTcLayer& L, int M, int* bn_out, int* stages_ou
 
 // 2-D tensor map over the fp32 activation matrix A[M][K] (K contiguous): box = box_k x 128 rows, no swizzle.
 // cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda).
-static CUtensorMap encode_a_map(const float* A, int M, int K, int box_k) {
+static CUtensorMap encode_map(const float* A, int M, int K, int box_k, int box_rows, bool swizzle128) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn fn = nullptr;
   static std::mutex mu;
-  static std::map<std::tuple<const float*, int, int>, CUtensorMap> cache;
+  static std::map<std::tuple<const float*, int, int, int>, CUtensorMap> cache;
   std::lock_guard<std::mutex> lk(mu);
   if (!fn) {
     void* p = nullptr;
@@ -447,16 +472,16 @@ static CUtensorMap encode_a_map(const float* A, int M, int K, int box_k) {
     if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("pw_tc: cuTensorMapEncodeTiled not available");
     fn = reinterpret_cast<EncodeFn>(p);
   }
-  auto key = std::make_tuple(A, M, K);
+  auto key = std::make_tuple(A, M, K, box_rows * 2 + (swizzle128 ? 1 : 0));
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   CUtensorMap m;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
   const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)kBM};
+  const cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("pw_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   if (cache.size() > 4096) cache.clear();
@@ -470,7 +495,7 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   int bn = 0, stages = 0;
   choose_tiling(L, p.M, &bn, &stages);
   const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
-  const size_t smem_bytes = (size_t)stages * stage + 1024 /*alignment*/ + ((8 * (3 * stages + 4) + 16 + 15) & ~15) + kEpiWarps * 128 * sizeof(float);
+  const size_t smem_bytes = (size_t)stages * stage + 1024 /*alignment*/ + kEpiWarps * 4096 + ((8 * (3 * stages + 4) + 16 + 15) & ~15) + kEpiWarps * 128 * sizeof(float);
   if (smem_bytes > 227 * 1024) throw std::runtime_error("pw_tc: shared memory budget exceeded");
   if (smem_bytes > max_set) {
     BNB_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -485,8 +510,28 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int tiles = m_tiles * a.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  const CUtensorMap amap = encode_a_map(p.A, p.M, p.K, a.box_k);
-  pw_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(a, amap);
+  const CUtensorMap amap = encode_map(p.A, p.M, p.K, a.box_k, kBM, false);
+  // output map: 32 x 32 fp32 boxes, 128B swizzle (the epilogue's staging layout); only when rows are 16-byte aligned
+  const CUtensorMap cmap = a.c_vec4 ? encode_map(p.C, p.M, p.N, p.N < 32 ? p.N : 32, 32, true) : amap;
+  // debug timeline: BNB_PWTC_TRACE=<file> BNB_PWTC_TRACE_IDX=<n-th pw_tc launch of the process>
+  static long long launch_idx = 0;
+  static const char* trace_path = getenv("BNB_PWTC_TRACE");
+  static const long long trace_idx = getenv("BNB_PWTC_TRACE_IDX") ? atoll(getenv("BNB_PWTC_TRACE_IDX")) : 0;
+  long long* trace = nullptr;
+  if (trace_path && launch_idx == trace_idx) { BNB_CUDA(cudaMallocManaged(&trace, 8 * 64 * sizeof(long long))); memset(trace, 0, 8 * 64 * sizeof(long long)); a.trace = trace; }
+  ++launch_idx;
+  pw_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(a, amap, cmap);
+  if (trace) {
+    BNB_CUDA(cudaStreamSynchronize(s));
+    FILE* f = fopen(trace_path, "w");
+    if (f) {
+      fprintf(f, "# M=%d N=%d K=%d bn=%d stages=%d grid=%d tiles=%d\n# iter loader_issue conv_raw_ready conv_done mma_full_ready mma_committed epi_acc_ready epi_done mma_tmem_free\n", p.M, p.N, p.K, bn, stages, grid, tiles);
+      const long long t0 = trace[0];
+      for (int i = 0; i < 64; ++i) { fprintf(f, "%d", i); for (int e = 0; e < 8; ++e) fprintf(f, " %lld", trace[e * 64 + i] ? trace[e * 64 + i] - t0 : -1); fprintf(f, "\n"); }
+      fclose(f);
+    }
+    cudaFree(trace);
+  }
   BNB_LAUNCH_CHECK(lc);
 }
 

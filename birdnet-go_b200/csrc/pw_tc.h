@@ -17,6 +17,7 @@ struct PwTcArgs {
   const float* A; const uint8_t* Wimg; const float* bias; float* C; const float* residual; const float* gate;
   int M, N, K, rows_per_chunk, act;
   int n_pad, k_pad, n_tiles, bn, stages, c_vec4, box_k;
+  long long* trace;   // debug: per-role clock64 timestamps of CTA 0 (BNB_PWTC_TRACE), else null
 };
 
 // Split W[N][K] (fp32, K-major = the OHWI / [O,I] layout of the .tflite) into fp16 hi/lo and lay both out as
