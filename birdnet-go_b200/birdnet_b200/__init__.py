@@ -69,6 +69,7 @@ SYMBOLS = {
     "bnb_profile_begin": (C.c_int, [C.c_void_p]),
     "bnb_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bnb_profile_launches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "bnb_debug_pw_tiling": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "bnb_describe_model": (C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "bnb_debug_read_tensor": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "bnb_debug_keep_intermediates": (C.c_int, [C.c_void_p, C.c_int]),
@@ -99,6 +100,14 @@ def _check(rc):
         msg = last_error()
         raise (B200Unavailable if rc == ERR_NO_DEVICE else B200Error)(rc, msg)
     return rc
+
+
+def pw_tiling(M, N, K):
+    """(bn, stages, smem_bytes) the tcgen05 GEMM launcher picks for an [M,K] x [N,K]^T layer."""
+    lib = load_library()
+    bn, st, sm = C.c_int(), C.c_int(), C.c_int64()
+    _check(lib.bnb_debug_pw_tiling(M, N, K, C.byref(bn), C.byref(st), C.byref(sm)))
+    return bn.value, st.value, sm.value
 
 
 def describe_model(model_bytes: bytes) -> str:

@@ -187,6 +187,15 @@ int bnb_profile_launches(bnb_classifier* h, float* ms, int32_t* cat, int cap) {
   return h->eng->profile_launches(ms, cat, cap);
 }
 
+int bnb_debug_pw_tiling(int M, int N, int K, int* bn, int* stages, int64_t* smem_bytes) {
+  if (!bn || !stages || !smem_bytes || M <= 0 || N <= 0 || K <= 0) return fail(BNB_ERR_INVALID_ARGUMENT, "bad tiling query");
+  PwTcLayer L; L.N = N; L.K = K; L.n_pad = (N + 15) / 16 * 16; L.k_pad = (K + 15) / 16 * 16; L.k_stages = (K + 63) / 64;
+  size_t sm = 0;
+  pw_tc_tiling(L, M, bn, stages, &sm);
+  *smem_bytes = (int64_t)sm;
+  return BNB_OK;
+}
+
 int bnb_describe_model(const void* tflite, size_t tflite_len, char* json, size_t cap) {
   if (!tflite || !json) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL pointer");
   std::string s;

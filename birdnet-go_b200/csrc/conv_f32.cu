@@ -222,18 +222,19 @@ pw_conv_kernel(const PwArgs a) {
 constexpr int kDwMaxThreads = 256;
 
 template <int STRIDE>
-__global__ void __launch_bounds__(kDwMaxThreads)
+__global__ void __launch_bounds__(kDwMaxThreads, 3)
 dw_conv_kernel(const DwArgs a) {
-  __shared__ float4 s_red[kDwMaxThreads];
+  __shared__ float4 s_w[9][kDwMaxThreads];      // taps of this CTA's channels; also reused for the row-sum reduction
   const int c4_per_cta = a.c4_per_cta, lanes = blockDim.x / c4_per_cta;    // row segments per CTA
   const int cl = threadIdx.x % c4_per_cta, pl = threadIdx.x / c4_per_cta;
   const int c4 = blockIdx.z * c4_per_cta + cl, b = blockIdx.y, ho = blockIdx.x;
   const int c4n = a.C / 4;
   const int seg = (a.Wo + lanes - 1) / lanes;
   const int w0 = pl * seg, w1 = min(a.Wo, w0 + seg);
-  float4 w[9];
+  if (pl == 0) {
 #pragma unroll
-  for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const float4*>(a.w + t * a.C) + c4);
+    for (int t = 0; t < 9; ++t) s_w[t][cl] = __ldg(reinterpret_cast<const float4*>(a.w + t * a.C) + c4);
+  }
   const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias) + c4);
   const float4* rowp[3];
   bool rv[3];
@@ -247,35 +248,37 @@ dw_conv_kernel(const DwArgs a) {
   auto ld = [&](int kh, int wi) { return (rv[kh] && wi >= 0 && wi < a.W) ? __ldg(rowp[kh] + (size_t)wi * c4n) : zero; };
   float4* outp = reinterpret_cast<float4*>(a.out + ((size_t)b * a.Ho + ho) * a.Wo * a.C) + c4;
   float4 sum = zero;
-  float4 x[3][3];
+  // sliding window x0|x1|x2 per input row + the NEXT output's new columns prefetched one iteration ahead
+  float4 x0[3], x1[3], x2[3], n1[3], n2[3];
   if (w0 < w1) {
-    if (STRIDE == 1) {
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) { x[kh][1] = ld(kh, w0 - 1); x[kh][2] = ld(kh, w0); }
-    } else {
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) x[kh][2] = ld(kh, 2 * w0 - 1);
+    for (int kh = 0; kh < 3; ++kh) {
+      if (STRIDE == 1) { x1[kh] = ld(kh, w0 - 1); x2[kh] = ld(kh, w0); n2[kh] = ld(kh, w0 + 1); n1[kh] = zero; }
+      else { x2[kh] = ld(kh, 2 * w0 - 1); n1[kh] = ld(kh, 2 * w0); n2[kh] = ld(kh, 2 * w0 + 1); x1[kh] = zero; }
     }
   }
+  __syncthreads();
   for (int wo = w0; wo < w1; ++wo) {
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      if (STRIDE == 1) { x[kh][0] = x[kh][1]; x[kh][1] = x[kh][2]; x[kh][2] = ld(kh, wo + 1); }
-      else { x[kh][0] = x[kh][2]; x[kh][1] = ld(kh, 2 * wo); x[kh][2] = ld(kh, 2 * wo + 1); }
+      if (STRIDE == 1) { x0[kh] = x1[kh]; x1[kh] = x2[kh]; x2[kh] = n2[kh]; if (wo + 1 < w1) n2[kh] = ld(kh, wo + 2); }
+      else { x0[kh] = x2[kh]; x1[kh] = n1[kh]; x2[kh] = n2[kh]; if (wo + 1 < w1) { n1[kh] = ld(kh, 2 * wo + 2); n2[kh] = ld(kh, 2 * wo + 3); } }
     }
     float4 acc = bz;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const float4 v = x[kh][kw], ww = w[kh * 3 + kw];
-        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y); acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
-      }
+    for (int kh = 0; kh < 3; ++kh) {
+      const float4 wa = s_w[kh * 3 + 0][cl], wb = s_w[kh * 3 + 1][cl], wc = s_w[kh * 3 + 2][cl];
+      acc.x = fmaf(x0[kh].x, wa.x, acc.x); acc.y = fmaf(x0[kh].y, wa.y, acc.y); acc.z = fmaf(x0[kh].z, wa.z, acc.z); acc.w = fmaf(x0[kh].w, wa.w, acc.w);
+      acc.x = fmaf(x1[kh].x, wb.x, acc.x); acc.y = fmaf(x1[kh].y, wb.y, acc.y); acc.z = fmaf(x1[kh].z, wb.z, acc.z); acc.w = fmaf(x1[kh].w, wb.w, acc.w);
+      acc.x = fmaf(x2[kh].x, wc.x, acc.x); acc.y = fmaf(x2[kh].y, wc.y, acc.y); acc.z = fmaf(x2[kh].z, wc.z, acc.z); acc.w = fmaf(x2[kh].w, wc.w, acc.w);
+    }
     acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w);
     outp[(size_t)wo * c4n] = acc;
     sum.x += acc.x; sum.y += acc.y; sum.z += acc.z; sum.w += acc.w;
   }
   if (a.partial != nullptr) {
+    __syncthreads();                      // everyone is done with the taps: reuse row 0 of s_w for the reduction
+    float4* s_red = &s_w[0][0];
     s_red[threadIdx.x] = sum;
     __syncthreads();
     if (pl == 0) {

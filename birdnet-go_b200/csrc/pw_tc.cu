@@ -440,19 +440,25 @@ PwTcLayer pw_tc_prepare(const float* w, int N, int K, std::vector<uint8_t>* imag
   return L;
 }
 
-// N tiling for a given M: fill the 148 SMs, keep >= 3 pipeline stages when K is long.
-static void choose_tiling(const PwTcLayer& L, int M, int* bn_out, int* stages_out) {
+// Shared-memory bytes of one launch configuration (must mirror the carve-up inside the kernel).
+static size_t smem_for(int bn, int stages) {
+  const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
+  return (size_t)stages * stage + 1024 /*alignment*/ + kEpiWarps * 4096 + ((8 * (3 * stages + 4) + 16 + 15) & ~15) + kEpiWarps * 128 * sizeof(float);
+}
+
+// N tiling for a given M: fill the 148 SMs, keep >= 3 pipeline stages when K is long, always fit >= 2 stages.
+void pw_tc_tiling(const PwTcLayer& L, int M, int* bn_out, int* stages_out, size_t* smem_out) {
   const int m_tiles = (M + kBM - 1) / kBM;
+  const size_t budget = 227 * 1024;
   int n_tiles = (L.n_pad + 255) / 256;
   auto bn_of = [&](int nt) { return nt == 1 ? L.n_pad : ((L.n_pad + nt - 1) / nt + 31) / 32 * 32; };   // 32-column TMA store boxes must not spill into the next n-tile
   int bn = bn_of(n_tiles);
+  while (smem_for(bn, 2) > budget) { ++n_tiles; bn = bn_of(n_tiles); }                   // two stages must fit
   if (L.k_stages >= 3) while (bn > 128) { ++n_tiles; bn = bn_of(n_tiles); }            // deeper ring for long K
   while (m_tiles * ((L.n_pad + bn - 1) / bn) < kNumSMs && bn > 64) { ++n_tiles; bn = bn_of(n_tiles); }
-  const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
-  int stages = (int)((184 * 1024) / stage);
-  if (stages > 6) stages = 6;
-  if (stages < 2) stages = 2;
-  *bn_out = bn; *stages_out = stages;
+  int stages = 6;
+  while (stages > 2 && smem_for(bn, stages) > budget) --stages;
+  *bn_out = bn; *stages_out = stages; *smem_out = smem_for(bn, stages);
 }
 
 // 2-D tensor map over the fp32 activation matrix A[M][K] (K contiguous): box = box_k x 128 rows, no swizzle.
@@ -493,9 +499,8 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   static size_t max_set = 0;
   if (p.a_mode != A_PLAIN || p.a_mul) throw std::runtime_error("pw_tc: A must be a plain [M][K] matrix (run the prep kernel first)");
   int bn = 0, stages = 0;
-  choose_tiling(L, p.M, &bn, &stages);
-  const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
-  const size_t smem_bytes = (size_t)stages * stage + 1024 /*alignment*/ + kEpiWarps * 4096 + ((8 * (3 * stages + 4) + 16 + 15) & ~15) + kEpiWarps * 128 * sizeof(float);
+  size_t smem_bytes = 0;
+  pw_tc_tiling(L, p.M, &bn, &stages, &smem_bytes);
   if (smem_bytes > 227 * 1024) throw std::runtime_error("pw_tc: shared memory budget exceeded");
   if (smem_bytes > max_set) {
     BNB_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));

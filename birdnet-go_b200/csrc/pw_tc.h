@@ -23,6 +23,8 @@ struct PwTcArgs {
 // Split W[N][K] (fp32, K-major = the OHWI / [O,I] layout of the .tflite) into fp16 hi/lo and lay both out as
 // the 128B-swizzled K-major shared-memory image of every (n-tile, k-stage); returns the tiling.
 PwTcLayer pw_tc_prepare(const float* w, int N, int K, std::vector<uint8_t>* image);
+// tiling decision for a layer at a given M (exposed for the CPU tests)
+void pw_tc_tiling(const PwTcLayer& L, int M, int* bn, int* stages, size_t* smem_bytes);
 void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, cudaStream_t s, LaunchCounter& lc);
 
 }  // namespace bnb

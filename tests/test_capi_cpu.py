@@ -83,3 +83,22 @@ def test_create_fails_closed_without_gpu(lib_path):
     assert lib.bnb_num_species(None) == bb.ERR_INVALID_ARGUMENT
     lib.bnb_classifier_destroy(None)                   # Close() on nil is a no-op
     assert "NULL" in bb.last_error() or bb.last_error()
+
+
+def test_every_gemm_layer_fits_the_tensor_core_kernel(lib_path):
+    """Host-side tiling of the tcgen05 GEMM for every pointwise / post / head layer at micro-batch, full-batch and
+    batch-1 row counts: >= 2 pipeline stages, N tile <= 256 TMEM columns, <= 227 KB shared memory, 32-column store
+    boxes never straddle two N tiles."""
+    d = json.loads(bb.describe_model(open(bb.DEFAULT_MODEL, "rb").read()))
+    shapes = []
+    for b in d["blocks"]:
+        hin, win, cin = b["in"]; ho, wo, co = b["out"]
+        shapes += [(hin * win, b["cexp"], cin), (ho * wo, co, b["cexp"])]
+    shapes += [(6, 1024, 1728), (1, 6522, 1024)]
+    for rows, N, K in shapes:
+        for chunks in (1, 16, 32, 64, 256, 1024):
+            bn, stages, smem = bb.pw_tiling(rows * chunks, N, K)
+            n_pad = (N + 15) // 16 * 16
+            assert 16 <= bn <= 256 and bn % 16 == 0 and stages >= 2 and smem <= 227 * 1024, (rows * chunks, N, K, bn, stages, smem)
+            if bn < n_pad:
+                assert bn % 32 == 0, (N, bn)
