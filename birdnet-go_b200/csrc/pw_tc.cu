@@ -136,7 +136,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // read into registers by the 4 producer warps, and is then overwritten IN PLACE by the fp16 hi (16 KB) and lo (16 KB)
 // 128B-swizzled K-major tiles the MMA consumes.
 __global__ void __launch_bounds__(kThreads, 1)
-pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap c_map) {
+pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -315,14 +315,15 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map, const 
     // ============================== epilogue (warps 0-7) =======================================
     // warp w owns TMEM lanes 32*(w%4).. (rows) and one half of the tile's columns, 32 columns per tcgen05.ld.
     // A thread holds one ROW of the chunk, so direct stores would scatter 16-byte pieces over 32 different rows
-    // (measured: 7.5-19 k cycles per tile).  Instead the 32x32 sub-tile is written to a warp-private, 128B-swizzled
-    // shared-memory buffer (conflict-free 16 B stores) and leaves through ONE 2-D TMA tensor store, which also clips
-    // rows >= M and columns >= N.  Layers whose row pitch is not 16-byte aligned (the 6522-wide head) keep direct stores.
+    // (measured: 7.5-19 k cycles per tile).  Instead the 32x32 sub-tile goes through a warp-private, XOR-swizzled
+    // shared-memory buffer (conflict-free 16 B stores) and is read back 4 rows x 128 B per instruction, so every
+    // global store instruction writes four full 128-byte row segments (a TMA tensor store of the same box was tried
+    // and is request-bound: 32 row requests per 4 KB).  The residual is added with the same coalesced pattern.
+    // Layers whose row pitch is not 16-byte aligned (the 6522-wide head) keep direct stores.
     const int quarter = warp & 3, half = warp >> 2;
     uint8_t* extra = base_ptr + (size_t)a.stages * stage_bytes;
     float* s_bias = reinterpret_cast<float*>(extra + 8 * 4096 + ((8u * (3 * a.stages + 4) + 16 + 15) & ~15u)) + warp * 128;
     uint8_t* s_out = extra + warp * 4096;                  // 32 rows x 128 B, 1024-aligned
-    const uint32_t s_out_u32 = smem_u32(s_out);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
@@ -350,16 +351,10 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map, const 
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);               // columns beyond bn are never stored (clipped / masked)
         const int n = n0 + c0;
-        float4 res[8];
-        if (rrow) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            res[j4] = (m < a.M && n + 4 * j4 + 4 <= a.N) ? __ldg(reinterpret_cast<const float4*>(rrow + n) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (a.c_vec4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous TMA store has read the buffer (lane 0 owns the groups)
-        __syncwarp();
+        __syncwarp();                                      // previous chunk's read-back of s_out is complete
         tmem_ld_wait();
         if (a.c_vec4) {
+          // (1) row-per-lane -> swizzled staging, (2) read back 4 rows x 128 B per instruction, (3) coalesced global store
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bz = *reinterpret_cast<const float4*>(s_bias + (c0 - c_begin) + 4 * j4);
@@ -368,15 +363,22 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map, const 
             o.y = act_apply(__uint_as_float(r[4 * j4 + 1]) + bz.y, a.act);
             o.z = act_apply(__uint_as_float(r[4 * j4 + 2]) + bz.z, a.act);
             o.w = act_apply(__uint_as_float(r[4 * j4 + 3]) + bz.w, a.act);
-            if (rrow) { o.x += res[j4].x; o.y += res[j4].y; o.z += res[j4].z; o.w += res[j4].w; }
             *reinterpret_cast<float4*>(s_out + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o;
           }
-          fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                         ::"l"(reinterpret_cast<uint64_t>(&c_map)), "r"(n), "r"(m_w), "r"(s_out_u32) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          const int chunk = lane & 7, ncol = n + 4 * chunk;
+          const bool col_ok = (c0 + 4 * chunk < bn) && (ncol + 4 <= a.N);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = 4 * j + (lane >> 3), mrow = m_w + row;
+            if (col_ok && mrow < a.M) {
+              float4 o = *reinterpret_cast<const float4*>(s_out + row * 128 + ((chunk ^ (row & 7)) << 4));
+              if (a.residual) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)mrow * a.N + ncol));
+                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+              }
+              *reinterpret_cast<float4*>(a.C + (size_t)mrow * a.N + ncol) = o;
+            }
           }
         } else if (m < a.M) {
 #pragma unroll
@@ -394,7 +396,6 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map, const 
       mbar_arrive(tempty_bar(buf));
       if (threadIdx.x == 0) BNB_TRACE(6, tcount);
     }
-    if (a.c_vec4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores complete before exit
   }
 
   tc_fence_before();
@@ -516,8 +517,6 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   const int tiles = m_tiles * a.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   const CUtensorMap amap = encode_map(p.A, p.M, p.K, a.box_k, kBM, false);
-  // output map: 32 x 32 fp32 boxes, 128B swizzle (the epilogue's staging layout); only when rows are 16-byte aligned
-  const CUtensorMap cmap = a.c_vec4 ? encode_map(p.C, p.M, p.N, p.N < 32 ? p.N : 32, 32, true) : amap;
   // debug timeline: BNB_PWTC_TRACE=<file> BNB_PWTC_TRACE_IDX=<n-th pw_tc launch of the process>
   static long long launch_idx = 0;
   static const char* trace_path = getenv("BNB_PWTC_TRACE");
@@ -525,7 +524,7 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   long long* trace = nullptr;
   if (trace_path && launch_idx == trace_idx) { BNB_CUDA(cudaMallocManaged(&trace, 8 * 64 * sizeof(long long))); memset(trace, 0, 8 * 64 * sizeof(long long)); a.trace = trace; }
   ++launch_idx;
-  pw_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(a, amap, cmap);
+  pw_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(a, amap);
   if (trace) {
     BNB_CUDA(cudaStreamSynchronize(s));
     FILE* f = fopen(trace_path, "w");

@@ -1,7 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -8
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
 echo "== launch times micro 64"; timeout 300 python tools/launch_times.py --micro-batch 64 --lanes 1 > gpurun_out/launch_times_m64.txt 2>&1; head -36 gpurun_out/launch_times_m64.txt; tail -42 gpurun_out/launch_times_m64.txt
-for cfg in "32 2" "64 1" "64 2"; do set -- $cfg; echo "== bench f16x3 micro $1 lanes $2"; timeout 300 python bench.py --steps 10 --warmup 3 --micro-batch $1 --lanes $2 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['e2e']['value']), {k:round(v,3) for k,v in d['kernel_ms_per_step'].items()})"; done
-echo "== ncu pw_tc E1"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:pw_tc -c 2 -f -o gpurun_out/prof_pw python tools/launch_times.py --batch 64 --micro-batch 64 > gpurun_out/ncu_pw.log 2>&1; tail -2 gpurun_out/ncu_pw.log
-echo "== ncu dw"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:dw_conv -c 2 -f -o gpurun_out/prof_dw python tools/launch_times.py --batch 64 --micro-batch 64 > gpurun_out/ncu_dw.log 2>&1; tail -2 gpurun_out/ncu_dw.log
+for cfg in "32 1" "32 2" "64 1" "64 2"; do set -- $cfg; echo "== bench f16x3 micro $1 lanes $2"; timeout 300 python bench.py --steps 10 --warmup 3 --micro-batch $1 --lanes $2 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['e2e']['value']), {k:round(v,3) for k,v in d['kernel_ms_per_step'].items()})"; done
