@@ -349,20 +349,25 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
       const float* rrow = a.residual ? a.residual + (size_t)m * a.N : nullptr;
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);               // columns beyond bn are never stored (clipped / masked)
+        if (!(a.dbg & 4)) tmem_ld32(taddr + (uint32_t)c0, r);               // columns beyond bn are never stored (clipped / masked)
+        else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
         const int n = n0 + c0;
         __syncwarp();                                      // previous chunk's read-back of s_out is complete
-        tmem_ld_wait();
+        if (!(a.dbg & 4)) tmem_ld_wait();
+        const int act = (a.dbg & 1) ? ACT_NONE : a.act;
         if (a.c_vec4) {
           // (1) row-per-lane -> swizzled staging, (2) read back 4 rows x 128 B per instruction, (3) coalesced global store
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bz = *reinterpret_cast<const float4*>(s_bias + (c0 - c_begin) + 4 * j4);
             float4 o;
-            o.x = act_apply(__uint_as_float(r[4 * j4 + 0]) + bz.x, a.act);
-            o.y = act_apply(__uint_as_float(r[4 * j4 + 1]) + bz.y, a.act);
-            o.z = act_apply(__uint_as_float(r[4 * j4 + 2]) + bz.z, a.act);
-            o.w = act_apply(__uint_as_float(r[4 * j4 + 3]) + bz.w, a.act);
+            o.x = act_apply(__uint_as_float(r[4 * j4 + 0]) + bz.x, act);
+            o.y = act_apply(__uint_as_float(r[4 * j4 + 1]) + bz.y, act);
+            o.z = act_apply(__uint_as_float(r[4 * j4 + 2]) + bz.z, act);
+            o.w = act_apply(__uint_as_float(r[4 * j4 + 3]) + bz.w, act);
             *reinterpret_cast<float4*>(s_out + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o;
           }
           __syncwarp();
@@ -371,7 +376,7 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int row = 4 * j + (lane >> 3), mrow = m_w + row;
-            if (col_ok && mrow < a.M) {
+            if (col_ok && mrow < a.M && !(a.dbg & 2)) {
               float4 o = *reinterpret_cast<const float4*>(s_out + row * 128 + ((chunk ^ (row & 7)) << 4));
               if (a.residual) {
                 const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)mrow * a.N + ncol));
@@ -518,6 +523,8 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   const CUtensorMap amap = encode_map(p.A, p.M, p.K, a.box_k, kBM, false);
   // debug timeline: BNB_PWTC_TRACE=<file> BNB_PWTC_TRACE_IDX=<n-th pw_tc launch of the process>
+  static const int dbg_flags = getenv("BNB_PWTC_DBG") ? atoi(getenv("BNB_PWTC_DBG")) : 0;
+  a.dbg = dbg_flags;
   static long long launch_idx = 0;
   static const char* trace_path = getenv("BNB_PWTC_TRACE");
   static const long long trace_idx = getenv("BNB_PWTC_TRACE_IDX") ? atoll(getenv("BNB_PWTC_TRACE_IDX")) : 0;

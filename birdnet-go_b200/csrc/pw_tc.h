@@ -17,6 +17,7 @@ struct PwTcArgs {
   const float* A; const uint8_t* Wimg; const float* bias; float* C; const float* residual; const float* gate;
   int M, N, K, rows_per_chunk, act;
   int n_pad, k_pad, n_tiles, bn, stages, c_vec4, box_k;
+  int dbg;            // debug knobs (BNB_PWTC_DBG): 1 = no activation, 2 = no global store, 4 = no TMEM load, 8 = no staging
   long long* trace;   // debug: per-role clock64 timestamps of CTA 0 (BNB_PWTC_TRACE), else null
 };
 
