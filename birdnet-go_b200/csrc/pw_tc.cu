@@ -125,6 +125,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 #define BNB_TRACE(ev, iter) do { if (a.trace && blockIdx.x == 0 && (iter) < 64) a.trace[(ev) * 64 + (iter)] = clock64(); } while (0)
 
+// SiLU of two values with ONE reciprocal: 1/a = b * rcp(a*b).  x is clamped at -80 so that a, b = 1 + exp(-x) stay
+// finite (a*b may overflow to +inf -> rcp = 0 -> both results -0, the correct limit).  MUFU-bound epilogue: 1.5 instead of 2 per value.
+__device__ __forceinline__ void silu2(float& x, float& y) {
+  float ex, ey, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * fmaxf(x, -80.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(-1.4426950408889634f * fmaxf(y, -80.f)));
+  const float a = 1.0f + ex, b = 1.0f + ey;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a * b));
+  x = x * (r * b); y = y * (r * a);
+}
+
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
   if (act == ACT_RELU) return fmaxf(v, 0.f);
@@ -145,18 +156,22 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
 
   const uint32_t a_bytes = kBM * 128u;                     // one fp16 [128][64] slab (16 KB); raw fp32 uses 2 of them
   const uint32_t b_bytes = (uint32_t)a.bn * 128u;          // one fp16 [bn][64] slab
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  const uint32_t bars = base + (uint32_t)a.stages * stage_bytes + 8u * 4096u;   // [8 x 4 KB epilogue staging] rawfull[S], full[S], empty[S], tfull[2], tempty[2], tmem ptr
+  const uint32_t stage_bytes = 2 * a_bytes + (a.b_res ? 0u : 2 * b_bytes);
+  const uint32_t bres_bytes = a.b_res ? 2 * b_bytes : 0u;          // resident weight tile (hi | lo) after the stage ring
+  const uint32_t bres = base + (uint32_t)a.stages * stage_bytes;
+  const uint32_t bars = bres + bres_bytes + 8u * 4096u;   // [8 x 4 KB epilogue staging] rawfull[S], full[S], empty[S], tfull[2], tempty[2], tmem ptr
   auto raw_bar = [&](int s) { return bars + 8u * s; };
   auto full_bar = [&](int s) { return bars + 8u * (a.stages + s); };
   auto empty_bar = [&](int s) { return bars + 8u * (2 * a.stages + s); };
   auto tfull_bar = [&](int b) { return bars + 8u * (3 * a.stages + b); };
   auto tempty_bar = [&](int b) { return bars + 8u * (3 * a.stages + 2 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (size_t)a.stages * stage_bytes + 8u * 4096u + 8u * (3 * a.stages + 4));
+  const uint32_t bres_bar = bars + 8u * (3 * a.stages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (size_t)a.stages * stage_bytes + bres_bytes + 8u * 4096u + 8u * (3 * a.stages + 5));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(raw_bar(s), 1); mbar_init(full_bar(s), kProdThreads + 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps * 32); }
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -168,8 +183,10 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // N-stationary CTAs: CTA b keeps n-tile (b % n_tiles) for its whole life (bias strip and, for one-stage layers, the
+  // weight tile are loaded once) and walks over m-tiles b / n_tiles, + gridDim.x / n_tiles, ...  (gridDim.x % n_tiles == 0)
   const int m_tiles = (a.M + kBM - 1) / kBM;
-  const int total_tiles = m_tiles * a.n_tiles;
+  const int nt_fix = blockIdx.x % a.n_tiles, mt_first = blockIdx.x / a.n_tiles, mt_step = gridDim.x / a.n_tiles;
   const int k_stages = (a.K + kBK - 1) / kBK;
   const int pitch = a.box_k * 4;                               // bytes per raw fp32 row in the landing buffer
 
@@ -178,8 +195,8 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
     const int pt = threadIdx.x - kProdWarp0 * 32;           // 0..255
     const int c = pt & 7, r0 = pt >> 3;                     // this thread: 16-byte chunk c of rows r0 + 32*q
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / a.n_tiles) * kBM;
+    for (int mt = mt_first; mt < m_tiles; mt += mt_step) {
+      const int m0 = mt * kBM;
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
         const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
         uint8_t* buf = base_ptr + (size_t)s * stage_bytes;
@@ -253,12 +270,18 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
       }
     }
   } else if (warp == kLoadWarp) {
-    // ============================== loader warp: async bulk copies of A rows (fp32) and B slabs ==
+    // ============================== loader warp: async bulk copies of A tiles (fp32, TMA) and B slabs ==
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % a.n_tiles, m0 = (tile / a.n_tiles) * kBM;
-      const int n0 = nt * a.bn;
-      const uint32_t bn_bytes = (uint32_t)min(a.bn, a.n_pad - n0) * 128u;
+    const int n0 = nt_fix * a.bn;
+    const uint32_t bn_bytes = (uint32_t)min(a.bn, a.n_pad - n0) * 128u;
+    if (a.b_res && lane == 0) {                             // one-stage layer: this CTA's weight tile is loaded once
+      const uint8_t* wsrc = a.Wimg + (size_t)n0 * 128;
+      mbar_arrive_expect_tx(bres_bar, 2 * bn_bytes);
+      bulk_g2s(bres, wsrc, bn_bytes, bres_bar);
+      bulk_g2s(bres + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, bres_bar);
+    }
+    for (int mt = mt_first; mt < m_tiles; mt += mt_step) {
+      const int m0 = mt * kBM;
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
         const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
@@ -268,10 +291,13 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
           // A: ONE 2-D TMA request per stage (box = box_k x 128 rows of fp32; out-of-range rows / columns arrive as zeros)
           mbar_arrive_expect_tx(raw_bar(s), (uint32_t)a.box_k * 4u * kBM);
           tma_load_2d(dst, &a_map, ks * kBK, m0, raw_bar(s));
-          mbar_arrive_expect_tx(full_bar(s), 2 * bn_bytes);
-          const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
-          bulk_g2s(dst + 2 * a_bytes, wsrc, bn_bytes, full_bar(s));
-          bulk_g2s(dst + 2 * a_bytes + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, full_bar(s));
+          if (a.b_res) mbar_arrive(full_bar(s));
+          else {
+            mbar_arrive_expect_tx(full_bar(s), 2 * bn_bytes);
+            const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
+            bulk_g2s(dst + 2 * a_bytes, wsrc, bn_bytes, full_bar(s));
+            bulk_g2s(dst + 2 * a_bytes + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, full_bar(s));
+          }
         }
         __syncwarp();
       }
@@ -280,8 +306,9 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
     // ============================== MMA issuer ================================================
     if (lane == 0) {
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        const int nt = tile % a.n_tiles;
+      if (a.b_res) mbar_wait(bres_bar, 0);
+      for (int mt = mt_first; mt < m_tiles; mt += mt_step, ++tcount) {
+        const int nt = nt_fix;
         const int n0 = nt * a.bn;
         const int bn = min(a.bn, a.n_pad - n0);
         const uint32_t idesc = make_idesc((uint32_t)bn);
@@ -297,7 +324,8 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + a_bytes);
-          const uint64_t d_bhi = make_desc(sa + 2 * a_bytes), d_blo = make_desc(sa + 2 * a_bytes + b_bytes);
+          const uint32_t sb = a.b_res ? bres : sa + 2 * a_bytes;
+          const uint64_t d_bhi = make_desc(sb), d_blo = make_desc(sb + b_bytes);
           const int kk_n = min(kBK, a.k_pad - ks * kBK) / 16;
           for (int kk = 0; kk < kk_n; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);        // +32 bytes (>>4) inside the swizzle row
@@ -321,24 +349,23 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
     // and is request-bound: 32 row requests per 4 KB).  The residual is added with the same coalesced pattern.
     // Layers whose row pitch is not 16-byte aligned (the 6522-wide head) keep direct stores.
     const int quarter = warp & 3, half = warp >> 2;
-    uint8_t* extra = base_ptr + (size_t)a.stages * stage_bytes;
-    float* s_bias = reinterpret_cast<float*>(extra + 8 * 4096 + ((8u * (3 * a.stages + 4) + 16 + 15) & ~15u)) + warp * 128;
+    uint8_t* extra = base_ptr + (size_t)a.stages * stage_bytes + bres_bytes;
+    float* s_bias = reinterpret_cast<float*>(extra + 8 * 4096 + ((8u * (3 * a.stages + 5) + 16 + 15) & ~15u)) + warp * 128;
     uint8_t* s_out = extra + warp * 4096;                  // 32 rows x 128 B, 1024-aligned
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int mt = tile / a.n_tiles, nt = tile % a.n_tiles;
-      const int n0 = nt * a.bn;
-      const int bn = min(a.bn, a.n_pad - n0);
-      const int c_split = min(bn, ((bn / 2 + 31) / 32) * 32);
-      const int c_begin = half ? c_split : 0, c_end = half ? bn : c_split;
-      const int buf = tcount & 1;
-      // bias strip for this warp's columns (issued before the accumulator wait so its latency is hidden)
+    // this CTA's n-tile never changes: column split and bias strip are set up once
+    const int n0 = nt_fix * a.bn;
+    const int bn = min(a.bn, a.n_pad - n0);
+    const int c_split = min(bn, ((bn / 2 + 31) / 32) * 32);
+    const int c_begin = half ? c_split : 0, c_end = half ? bn : c_split;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cc = c_begin + lane + 32 * j;
-        s_bias[lane + 32 * j] = (cc < c_end + 16 && n0 + cc < a.n_pad + 16) ? __ldg(a.bias + n0 + cc) : 0.f;   // bias is padded to n_pad + 16
-      }
-      __syncwarp();
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c_begin + lane + 32 * j;
+      s_bias[lane + 32 * j] = (cc < c_end + 16 && n0 + cc < a.n_pad + 16) ? __ldg(a.bias + n0 + cc) : 0.f;   // bias is padded past n_pad at upload
+    }
+    __syncwarp();
+    uint32_t tcount = 0;
+    for (int mt = mt_first; mt < m_tiles; mt += mt_step, ++tcount) {
+      const int buf = tcount & 1;
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
       if (threadIdx.x == 0) BNB_TRACE(5, tcount);
       tc_fence_after();
@@ -364,10 +391,10 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bz = *reinterpret_cast<const float4*>(s_bias + (c0 - c_begin) + 4 * j4);
             float4 o;
-            o.x = act_apply(__uint_as_float(r[4 * j4 + 0]) + bz.x, act);
-            o.y = act_apply(__uint_as_float(r[4 * j4 + 1]) + bz.y, act);
-            o.z = act_apply(__uint_as_float(r[4 * j4 + 2]) + bz.z, act);
-            o.w = act_apply(__uint_as_float(r[4 * j4 + 3]) + bz.w, act);
+            o.x = __uint_as_float(r[4 * j4 + 0]) + bz.x; o.y = __uint_as_float(r[4 * j4 + 1]) + bz.y;
+            o.z = __uint_as_float(r[4 * j4 + 2]) + bz.z; o.w = __uint_as_float(r[4 * j4 + 3]) + bz.w;
+            if (act == ACT_SILU) { silu2(o.x, o.y); silu2(o.z, o.w); }
+            else if (act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4*>(s_out + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o;
           }
           __syncwarp();
@@ -396,7 +423,6 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
           }
         }
       }
-      __syncwarp();                      // the bias strip is rewritten at the next tile
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
       if (threadIdx.x == 0) BNB_TRACE(6, tcount);
@@ -447,24 +473,27 @@ PwTcLayer pw_tc_prepare(const float* w, int N, int K, std::vector<uint8_t>* imag
 }
 
 // Shared-memory bytes of one launch configuration (must mirror the carve-up inside the kernel).
-static size_t smem_for(int bn, int stages) {
-  const size_t stage = 2 * (size_t)kBM * 128 + 2 * (size_t)bn * 128;
-  return (size_t)stages * stage + 1024 /*alignment*/ + kEpiWarps * 4096 + ((8 * (3 * stages + 4) + 16 + 15) & ~15) + kEpiWarps * 128 * sizeof(float);
+static size_t smem_for(int bn, int stages, bool b_res) {
+  const size_t stage = 2 * (size_t)kBM * 128 + (b_res ? 0 : 2 * (size_t)bn * 128);
+  return (size_t)stages * stage + (b_res ? 2 * (size_t)bn * 128 : 0) + 1024 /*alignment*/ + kEpiWarps * 4096 +
+         ((8 * (3 * stages + 5) + 16 + 15) & ~15) + kEpiWarps * 128 * sizeof(float);
 }
 
 // N tiling for a given M: fill the 148 SMs, keep >= 3 pipeline stages when K is long, always fit >= 2 stages.
-void pw_tc_tiling(const PwTcLayer& L, int M, int* bn_out, int* stages_out, size_t* smem_out) {
+void pw_tc_tiling(const PwTcLayer& L, int M, int* bn_out, int* stages_out, size_t* smem_out, int* b_res_out) {
   const int m_tiles = (M + kBM - 1) / kBM;
   const size_t budget = 227 * 1024;
+  const bool b_res = L.k_stages == 1;                                                    // weight tile resident per CTA
   int n_tiles = (L.n_pad + 255) / 256;
-  auto bn_of = [&](int nt) { return nt == 1 ? L.n_pad : ((L.n_pad + nt - 1) / nt + 31) / 32 * 32; };   // 32-column TMA store boxes must not spill into the next n-tile
+  auto bn_of = [&](int nt) { return nt == 1 ? L.n_pad : ((L.n_pad + nt - 1) / nt + 31) / 32 * 32; };   // 32-column store chunks must not spill into the next n-tile
   int bn = bn_of(n_tiles);
-  while (smem_for(bn, 2) > budget) { ++n_tiles; bn = bn_of(n_tiles); }                   // two stages must fit
+  while (smem_for(bn, 2, b_res) > budget) { ++n_tiles; bn = bn_of(n_tiles); }            // two stages must fit
   if (L.k_stages >= 3) while (bn > 128) { ++n_tiles; bn = bn_of(n_tiles); }            // deeper ring for long K
   while (m_tiles * ((L.n_pad + bn - 1) / bn) < kNumSMs && bn > 64) { ++n_tiles; bn = bn_of(n_tiles); }
   int stages = 6;
-  while (stages > 2 && smem_for(bn, stages) > budget) --stages;
-  *bn_out = bn; *stages_out = stages; *smem_out = smem_for(bn, stages);
+  while (stages > 2 && smem_for(bn, stages, b_res) > budget) --stages;
+  *bn_out = bn; *stages_out = stages; *smem_out = smem_for(bn, stages, b_res);
+  if (b_res_out) *b_res_out = b_res ? 1 : 0;
 }
 
 // 2-D tensor map over the fp32 activation matrix A[M][K] (K contiguous): box = box_k x 128 rows, no swizzle.
@@ -506,7 +535,8 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   if (p.a_mode != A_PLAIN || p.a_mul) throw std::runtime_error("pw_tc: A must be a plain [M][K] matrix (run the prep kernel first)");
   int bn = 0, stages = 0;
   size_t smem_bytes = 0;
-  pw_tc_tiling(L, p.M, &bn, &stages, &smem_bytes);
+  int b_res = 0;
+  pw_tc_tiling(L, p.M, &bn, &stages, &smem_bytes, &b_res);
   if (smem_bytes > 227 * 1024) throw std::runtime_error("pw_tc: shared memory budget exceeded");
   if (smem_bytes > max_set) {
     BNB_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -516,11 +546,12 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   a.A = p.A; a.Wimg = d_image; a.bias = p.bias; a.C = p.C; a.residual = p.residual; a.gate = p.gate;
   a.M = p.M; a.N = p.N; a.K = p.K; a.rows_per_chunk = p.rows_per_chunk; a.act = p.act;
   a.box_k = p.K < kBK ? p.K : kBK;
+  a.b_res = b_res;
   a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.bn = bn; a.n_tiles = (L.n_pad + bn - 1) / bn; a.stages = stages;
   a.c_vec4 = (p.N % 4 == 0) ? 1 : 0;
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int tiles = m_tiles * a.n_tiles;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  const int grid = tiles < kNumSMs ? tiles : (kNumSMs / a.n_tiles) * a.n_tiles;   // multiple of n_tiles (N-stationary CTAs)
   const CUtensorMap amap = encode_map(p.A, p.M, p.K, a.box_k, kBM, false);
   // debug timeline: BNB_PWTC_TRACE=<file> BNB_PWTC_TRACE_IDX=<n-th pw_tc launch of the process>
   static const int dbg_flags = getenv("BNB_PWTC_DBG") ? atoi(getenv("BNB_PWTC_DBG")) : 0;
