@@ -289,36 +289,61 @@ dw_conv_kernel(const DwArgs a) {
 }
 
 // =================================================================================================
-// Squeeze-excite gate: gate[b][c] = sigmoid(W2 * silu(W1 * mean_hw(x[b]) + b1) + b2).  One CTA per chunk.
+// Squeeze-excite gate: gate[b][c] = sigmoid(W2 * silu(W1 * mean_hw(x[b]) + b1) + b2).
+// One CTA = kSeChunks chunks so every weight row fetched from L2 is used for several chunks; 32 warps split the
+// hidden units (float4 weight loads, warp-shuffle reductions); the channel means come from the per-row sums the
+// depthwise kernel left behind.
 // =================================================================================================
-constexpr int kSeThreads = 256;
-constexpr int kSeMaxC = 1536, kSeMaxS = 64;
+constexpr int kSeThreads = 1024;
+constexpr int kSeMaxC = 1536, kSeMaxS = 64, kSeChunks = 2;
 
 __global__ void __launch_bounds__(kSeThreads)
 se_gate_kernel(const SeArgs a) {
-  __shared__ float s_mean[kSeMaxC];
-  __shared__ float s_hidden[kSeMaxS];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  // channel means from the per-part sums the depthwise kernel left behind
-  for (int c = tid; c < a.C; c += kSeThreads) {
+  __shared__ __align__(16) float s_mean[kSeChunks][kSeMaxC];
+  __shared__ float s_hidden[kSeChunks][kSeMaxS];
+  const int b0 = blockIdx.x * kSeChunks, tid = threadIdx.x;
+  const int nb = min(kSeChunks, a.B - b0);
+  const float inv = 1.0f / (float)a.HW;
+  for (int i = tid; i < kSeChunks * a.C; i += kSeThreads) {
+    const int g = i / a.C, c = i - g * a.C;
     float s = 0.f;
-    for (int p = 0; p < a.parts; ++p) s += __ldg(a.partial + ((size_t)b * a.parts + p) * a.C + c);
-    s_mean[c] = s / (float)a.HW;
+    if (g < nb) for (int p = 0; p < a.parts; ++p) s += __ldg(a.partial + ((size_t)(b0 + g) * a.parts + p) * a.C + c);
+    s_mean[g][c] = s * inv;
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   for (int j = warp; j < a.Cse; j += kSeThreads / 32) {
-    const float* w = a.w1 + (size_t)j * a.C;
-    float s = 0.f;
-    for (int c = lane; c < a.C; c += 32) s = fmaf(s_mean[c], __ldg(w + c), s);
-    s = warp_sum(s);
-    if (lane == 0) s_hidden[j] = silu_f(s + __ldg(a.b1 + j));
+    const float4* w = reinterpret_cast<const float4*>(a.w1 + (size_t)j * a.C);
+    float acc[kSeChunks];
+#pragma unroll
+    for (int g = 0; g < kSeChunks; ++g) acc[g] = 0.f;
+    for (int c4 = lane; c4 < a.C / 4; c4 += 32) {
+      const float4 wv = __ldg(w + c4);
+#pragma unroll
+      for (int g = 0; g < kSeChunks; ++g) {
+        const float4 m = *reinterpret_cast<const float4*>(&s_mean[g][4 * c4]);
+        acc[g] = fmaf(m.x, wv.x, fmaf(m.y, wv.y, fmaf(m.z, wv.z, fmaf(m.w, wv.w, acc[g]))));
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kSeChunks; ++g) {
+      const float v = warp_sum(acc[g]);
+      if (lane == 0) s_hidden[g][j] = silu_f(v + __ldg(a.b1 + j));
+    }
   }
   __syncthreads();
   for (int c = tid; c < a.C; c += kSeThreads) {
-    float s = __ldg(a.b2 + c);
-    for (int j = 0; j < a.Cse; ++j) s = fmaf(s_hidden[j], __ldg(a.w2t + (size_t)j * a.C + c), s);   // w2t: [Cse][C] (transposed at load)
-    a.gate[(size_t)b * a.C + c] = sigmoid_f(s);
+    float acc[kSeChunks];
+    const float bz = __ldg(a.b2 + c);
+#pragma unroll
+    for (int g = 0; g < kSeChunks; ++g) acc[g] = bz;
+    for (int j = 0; j < a.Cse; ++j) {
+      const float wv = __ldg(a.w2t + (size_t)j * a.C + c);      // w2t: [Cse][C] (transposed at load) -> coalesced
+#pragma unroll
+      for (int g = 0; g < kSeChunks; ++g) acc[g] = fmaf(s_hidden[g][j], wv, acc[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < kSeChunks; ++g) if (g < nb) a.gate[(size_t)(b0 + g) * a.C + c] = sigmoid_f(acc[g]);
   }
 }
 
@@ -386,7 +411,7 @@ void launch_dw_conv(const DwArgs& a0, cudaStream_t s, LaunchCounter& lc) {
 
 void launch_se_gate(const SeArgs& a, cudaStream_t s, LaunchCounter& lc) {
   if (a.C > kSeMaxC || a.Cse > kSeMaxS) throw std::runtime_error("se_gate: channel count exceeds kernel limits");
-  se_gate_kernel<<<a.B, kSeThreads, 0, s>>>(a);
+  se_gate_kernel<<<(a.B + kSeChunks - 1) / kSeChunks, kSeThreads, 0, s>>>(a);
   BNB_LAUNCH_CHECK(lc);
 }
 

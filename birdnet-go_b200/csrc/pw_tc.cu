@@ -254,10 +254,15 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
             uint32_t ph_[4], pl_[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const __half h0 = __float2half_rn(v[q][2 * i]), h1 = __float2half_rn(v[q][2 * i + 1]);
-              const __half l0 = __float2half_rn(v[q][2 * i] - __half2float(h0)), l1 = __float2half_rn(v[q][2 * i + 1] - __half2float(h1));
-              ph_[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-              pl_[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              // Veltkamp split in fp32 (x = hi + lo exactly, hi has 11 significant bits = an exact fp16), then ONE packed
+              // cvt.rn.f16x2.f32 per pair: the scalar F2F conversions run at 16/clk/SM and were the converter's bottleneck.
+              const float x0 = v[q][2 * i], x1 = v[q][2 * i + 1];
+              const float t0 = __fmul_rn(x0, 8193.0f), t1 = __fmul_rn(x1, 8193.0f);
+              const float h0 = __fsub_rn(t0, __fsub_rn(t0, x0)), h1 = __fsub_rn(t1, __fsub_rn(t1, x1));
+              const float l0 = __fsub_rn(x0, h0), l1 = __fsub_rn(x1, h1);
+              const __half2 hh = __floats2half2_rn(h0, h1), ll = __floats2half2_rn(l0, l1);
+              ph_[i] = *reinterpret_cast<const uint32_t*>(&hh);
+              pl_[i] = *reinterpret_cast<const uint32_t*>(&ll);
             }
             const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
             *reinterpret_cast<uint4*>(hi + off) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
