@@ -213,8 +213,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--micro-batch", type=int, default=0)
-    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--micro-batch", type=int, default=64)
+    ap.add_argument("--lanes", type=int, default=2)
     ap.add_argument("--precision", default="default", choices=["default", "f32", "f16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
