@@ -6,6 +6,7 @@
 #include <new>
 
 #include "engine.h"
+#include "mbconv_tc.h"
 
 using namespace bnb;
 
@@ -193,6 +194,15 @@ int bnb_debug_pw_tiling(int M, int N, int K, int* bn, int* stages, int64_t* smem
   size_t sm = 0;
   pw_tc_tiling(L, M, bn, stages, &sm);
   *smem_bytes = (int64_t)sm;
+  return BNB_OK;
+}
+
+int bnb_debug_mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin, int* out10, int64_t* smem_bytes) {
+  if (!out10 || !smem_bytes) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL out");
+  const MbGeom g = mbconv_geometry(H, W, Ho, Wo, stride, Cin);
+  const int v[10] = {g.th, g.tw, g.ph, g.pw, g.tiles_h, g.tiles_w, g.k_stages, g.box_c, g.a_slots, g.b_slots};
+  for (int i = 0; i < 10; ++i) out10[i] = v[i];
+  *smem_bytes = (int64_t)g.smem_bytes;
   return BNB_OK;
 }
 

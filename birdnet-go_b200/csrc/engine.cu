@@ -7,6 +7,7 @@
 // Host-buffer calls overlap the H2D copy of micro-batch i+1 (copy stream) with the compute of
 // micro-batch i (compute stream).
 #include "engine.h"
+#include "mbconv_tc.h"
 
 #include <math.h>
 #include <string.h>
@@ -44,6 +45,8 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
   max_batch_ = opts.max_batch > 0 ? opts.max_batch : 256;
   micro_ = opts.micro_batch > 0 ? opts.micro_batch : 32;
   n_lanes_ = opts.reserved[0] > 0 ? std::min<int>(opts.reserved[0], kMaxLanes) : 2;
+  fused_ = !(getenv("BNB_FUSED") && atoi(getenv("BNB_FUSED")) == 0);
+  fused_force_ = getenv("BNB_FUSED") && atoi(getenv("BNB_FUSED")) == 2;   // also in keep-intermediates mode (debug)
   if (micro_ > max_batch_) micro_ = max_batch_;
   precision_ = opts.precision == BNB_PRECISION_DEFAULT ? BNB_PRECISION_F16X3 : opts.precision;
   precision_name_ = precision_ == BNB_PRECISION_F16X3 ? "FP16x3(tcgen05)+FP32" : "FP32";
@@ -60,7 +63,10 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
     throw unsupported_model("stem geometry differs from BirdNET v2.4 (4x8/s2, 2->24, 1x1 48->24)");
   if (P.post.out_h != 1) throw unsupported_model("post conv must reduce the mel axis to 1");
   for (const BlockPlan& b : P.blocks)
-    if (b.has_se && b.out_h > kMaxDwParts) throw unsupported_model("squeeze-excite block taller than the row-sum buffer");
+    if (b.has_se) {
+      const MbGeom mg = mbconv_geometry(b.in_h, b.in_w, b.out_h, b.out_w, b.stride, b.cin);
+      if (b.out_h > kMaxDwParts || mg.tiles_h * mg.tiles_w > kMaxDwParts) throw unsupported_model("squeeze-excite block needs more partial-sum slots than the buffer holds");
+    }
   for (const BlockPlan& b : P.blocks)
     if (b.cin % 4 || b.cexp % 4 || b.cout % 4 || (b.has_se && (b.cexp > 1536 || b.cse > 64))) throw unsupported_model("block channel counts");
   n_species_ = P.n_species(); n_samples_ = F.n_samples; emb_dim_ = P.emb_dim();
@@ -236,7 +242,7 @@ void Engine::alloc_workspace() {
     }
     w.x0 = dmalloc(cap_n * cx); w.x1 = dmalloc(cap_n * cx);
     w.e = dmalloc(cap_n * ce); w.d = dmalloc(cap_n * cd); w.g = dmalloc(cap_n * cg);
-    w.sep = dmalloc(cap_n * kMaxDwParts * cg);
+    w.sep = dmalloc(cap_n * kMaxDwParts * cg);   // SE partial sums: <= kMaxDwParts parts per chunk (rows, or fused-kernel tiles)
   };
   for (int l = 0; l < n_lanes_; ++l) {
     alloc_work(lanes_[l].w, mb, 0, split_, (size_t)stem_.out_h * (stem_.out_w / 2) * 24);
@@ -279,24 +285,37 @@ float* Engine::run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream
     const DevBlock& b = blocks_[bi];
     const BlockPlan& g = b.g;
     const int hw_in = g.in_h * g.in_w, hw_out = g.out_h * g.out_w;
-    float* e = scratch(g.exp_tensor, w.e, (size_t)hw_in * g.cexp, n);
-    PwArgs ex{};
-    ex.A = cur; ex.W = b.expand.w; ex.bias = b.expand.b; ex.C = e; ex.M = n * hw_in; ex.N = g.cexp; ex.K = g.cin;
-    ex.rows_per_chunk = hw_in; ex.act = ACT_SILU; ex.a_mode = A_PLAIN;
-    pw(ex, b.expand, C_PW_EXPAND, s);
-    record(g.exp_tensor, e, (size_t)hw_in * g.cexp, n);
     float* d = scratch(g.dw_tensor, w.d, (size_t)hw_out * g.cexp, n);
-    DwArgs dw{};
-    dw.in = e; dw.w = b.dw.w; dw.bias = b.dw.b; dw.out = d; dw.B = n; dw.H = g.in_h; dw.W = g.in_w; dw.C = g.cexp;
-    dw.stride = g.stride; dw.Ho = g.out_h; dw.Wo = g.out_w;
-    dw.parts = std::min(kMaxDwParts, dw_parts(n, g.out_h, g.out_w, g.cexp));
-    dw.partial = g.has_se ? w.sep : nullptr;
-    { ProfScope ps(this, C_DW, s); launch_dw_conv(dw, s, lc_); }
+    int se_parts = 0;
+    if (fused_ && b.expand.tc_img && (!keep_ || fused_force_)) {
+      // expand + SiLU + depthwise + SiLU + SE sums in one tcgen05 kernel: the expanded tensor is never materialised
+      const MbGeom mg = mbconv_geometry(g.in_h, g.in_w, g.out_h, g.out_w, g.stride, g.cin);
+      se_parts = mg.tiles_h * mg.tiles_w;
+      MbLaunch ml{};
+      ml.x = cur; ml.Wimg = b.expand.tc_img; ml.bias_e = b.expand.b; ml.w_dw = b.dw.w; ml.bias_dw = b.dw.b; ml.D = d;
+      ml.partial = g.has_se ? w.sep : nullptr;
+      ml.B = n; ml.H = g.in_h; ml.W = g.in_w; ml.Cin = g.cin; ml.C = g.cexp; ml.Ho = g.out_h; ml.Wo = g.out_w; ml.stride = g.stride;
+      { ProfScope ps(this, C_PW_EXPAND, s); launch_mbconv_tc(ml, s, lc_); }
+    } else {
+      float* e = scratch(g.exp_tensor, w.e, (size_t)hw_in * g.cexp, n);
+      PwArgs ex{};
+      ex.A = cur; ex.W = b.expand.w; ex.bias = b.expand.b; ex.C = e; ex.M = n * hw_in; ex.N = g.cexp; ex.K = g.cin;
+      ex.rows_per_chunk = hw_in; ex.act = ACT_SILU; ex.a_mode = A_PLAIN;
+      pw(ex, b.expand, C_PW_EXPAND, s);
+      record(g.exp_tensor, e, (size_t)hw_in * g.cexp, n);
+      DwArgs dw{};
+      dw.in = e; dw.w = b.dw.w; dw.bias = b.dw.b; dw.out = d; dw.B = n; dw.H = g.in_h; dw.W = g.in_w; dw.C = g.cexp;
+      dw.stride = g.stride; dw.Ho = g.out_h; dw.Wo = g.out_w;
+      dw.parts = std::min(kMaxDwParts, dw_parts(n, g.out_h, g.out_w, g.cexp));
+      dw.partial = g.has_se ? w.sep : nullptr;
+      se_parts = dw.parts;
+      { ProfScope ps(this, C_DW, s); launch_dw_conv(dw, s, lc_); }
+    }
     record(g.dw_tensor, d, (size_t)hw_out * g.cexp, n);
     float* gate = nullptr;
     if (g.has_se) {
       gate = scratch(g.gate_tensor, w.g, (size_t)g.cexp, n);
-      SeArgs se{w.sep, b.se1.w, b.se1.b, b.se2.w, b.se2.b, gate, n, hw_out, g.cexp, g.cse, dw.parts};
+      SeArgs se{w.sep, b.se1.w, b.se1.b, b.se2.w, b.se2.b, gate, n, hw_out, g.cexp, g.cse, se_parts};
       { ProfScope ps(this, C_SE, s); launch_se_gate(se, s, lc_); }
       record(g.gate_tensor, gate, (size_t)g.cexp, n);
     }

@@ -91,6 +91,8 @@ class Engine {
   LaunchCounter lc_;
   float last_ms_ = 0.f;
   bool keep_ = false;
+  bool fused_force_ = false;
+  bool fused_ = true;      // fused expand+depthwise tcgen05 kernel (BNB_FUSED=0 falls back to the two-kernel chain)
 
   // weights
   std::vector<void*> allocs_;                 // every cudaMalloc owned by the handle

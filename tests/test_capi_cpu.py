@@ -102,3 +102,19 @@ def test_every_gemm_layer_fits_the_tensor_core_kernel(lib_path):
             assert 16 <= bn <= 256 and bn % 16 == 0 and stages >= 2 and smem <= 227 * 1024, (rows * chunks, N, K, bn, stages, smem)
             if bn < n_pad:
                 assert bn % 32 == 0, (N, bn)
+
+
+def test_fused_block_geometry_covers_every_block(lib_path):
+    """Fused expand+depthwise kernel: for each of the 16 blocks the output tiles cover the image exactly once, the halo
+    patch fits the 128 GEMM rows, shared memory fits, and SE blocks need <= 32 partial-sum slots per chunk."""
+    d = json.loads(bb.describe_model(open(bb.DEFAULT_MODEL, "rb").read()))
+    for b in d["blocks"]:
+        hin, win, cin = b["in"]; ho, wo, _ = b["out"]
+        g = bb.mbconv_geometry(hin, win, ho, wo, b["stride"], cin)
+        assert g["ph"] == (g["th"] - 1) * b["stride"] + 3 and g["pw"] == (g["tw"] - 1) * b["stride"] + 3
+        assert g["ph"] * g["pw"] <= 128 and g["smem_bytes"] <= 227 * 1024
+        assert g["tiles_h"] * g["th"] >= ho and (g["tiles_h"] - 1) * g["th"] < ho
+        assert g["tiles_w"] * g["tw"] >= wo and (g["tiles_w"] - 1) * g["tw"] < wo
+        assert g["k_stages"] == (cin + 63) // 64 and g["a_slots"] >= g["k_stages"]
+        if b["se"]:
+            assert g["tiles_h"] * g["tiles_w"] <= 32
