@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include <map>
+#include <vector>
 #include <mutex>
 #include <tuple>
 
@@ -41,6 +42,8 @@ constexpr int kSliceCols = 32;      // expanded channels per slice
 constexpr int kABytes = 32768;      // one A stage: raw fp32 [128][64] -> in place hi | lo fp16 tiles (16 KB each)
 constexpr int kBStage = 8192;       // one (slice, k-stage) weight slab: hi 32 x 128 B | lo 32 x 128 B
 constexpr int kSBytes = 16384;      // expanded tile of one group: [128 pos][32 ch] fp32, 16-byte chunks XOR-swizzled
+
+#define MB_TRACE(ev, iter) do { if (a.trace && blockIdx.x == 0 && (iter) < 64) a.trace[(ev) * 64 + (iter)] = clock64(); } while (0)
 
 __device__ __forceinline__ float silu1(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
@@ -162,6 +165,7 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
           const int s = ib % a.b_slots; const uint32_t ph = (ib / a.b_slots) & 1;
           const int rows = min(kSliceCols, a.n_pad - j * kSliceCols);
           mbar_wait(b_empty(s), ph ^ 1);
+          MB_TRACE(0, ib);
           mbar_arrive_expect_tx(b_full(s), (uint32_t)(a.k_stages * 2 * rows * 128));
           for (int ks = 0; ks < a.k_stages; ++ks) {
             const uint8_t* src = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)j * kSliceCols * 128;
@@ -175,38 +179,52 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ================================================================
     if (lane == 0) {
+      // A slice's MMAs all accumulate into one 32-column TMEM tile, so back-to-back they are bound by the MMA
+      // pipeline latency (measured ~170 cycles each).  Up to four slices (the four accumulators: 2 groups x 2 buffers)
+      // are therefore issued interleaved, k-step by k-step.
       uint32_t ia = 0, ib = 0, sg[2] = {0, 0};
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         for (int ks = 0; ks < a.k_stages; ++ks) {                 // the whole converted patch must be in place
           const uint32_t i = ia + ks;
           mbar_wait(a_full(i % a.a_slots), (i / a.a_slots) & 1);
         }
-        tc_fence_after();
-        for (int j = 0; j < n_slices; ++j, ++ib) {
-          const int g = j & 1, buf = sg[g] & 1;
-          const int sb = ib % a.b_slots;
-          const int ncols = min(kSliceCols, a.n_pad - j * kSliceCols);
-          const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | (8u << 24);    // f32 accum, f16 x f16, M = 128
-          mbar_wait(t_empty(g, buf), ((sg[g] >> 1) & 1) ^ 1);
-          mbar_wait(b_full(sb), (ib / a.b_slots) & 1);
+        for (int j0 = 0; j0 < n_slices; j0 += 4) {
+          const int nb = min(4, n_slices - j0);
+          uint32_t d_tmem[4], idesc[4], bslot[4];
+          int gg[4], bufs[4];
+          for (int u = 0; u < nb; ++u) {
+            const int j = j0 + u, g = j & 1;
+            const uint32_t seq = sg[g] + (uint32_t)(u >> 1);        // u = g, g + 2 are this group's 1st / 2nd slice of the batch
+            const int buf = seq & 1;
+            const int ncols = min(kSliceCols, a.n_pad - j * kSliceCols);
+            gg[u] = g; bufs[u] = buf; bslot[u] = (ib + u) % a.b_slots;
+            idesc[u] = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | (8u << 24);    // f32 accum, f16 x f16, M = 128
+            d_tmem[u] = tmem_base + (uint32_t)(g * 2 + buf) * kSliceCols;
+            mbar_wait(t_empty(g, buf), ((seq >> 1) & 1) ^ 1);
+            if (u == 0) MB_TRACE(1, ib);
+            mbar_wait(b_full(bslot[u]), ((ib + u) / a.b_slots) & 1);
+          }
+          MB_TRACE(2, ib);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(g * 2 + buf) * kSliceCols;
           for (int ks = 0; ks < a.k_stages; ++ks) {
             const uint32_t sa = a_ring + (uint32_t)((ia + ks) % a.a_slots) * kABytes;
-            const uint32_t sbk = b_ring + (uint32_t)sb * b_slot_bytes + (uint32_t)ks * kBStage;
             const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + 16384);
-            const uint64_t d_bhi = make_desc(sbk), d_blo = make_desc(sbk + 4096);
             const int kk_n = min(64, a.k_pad - ks * 64) / 16;
             for (int kk = 0; kk < kk_n; ++kk) {
               const uint64_t adv = (uint64_t)(kk * 2);
-              umma(d_tmem, d_ahi + adv, d_bhi + adv, idesc, (ks | kk) != 0);
-              umma(d_tmem, d_alo + adv, d_bhi + adv, idesc, 1);
-              umma(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1);
+              for (int u = 0; u < nb; ++u) {
+                const uint32_t sbk = b_ring + bslot[u] * b_slot_bytes + (uint32_t)ks * kBStage;
+                const uint64_t d_bhi = make_desc(sbk), d_blo = make_desc(sbk + 4096);
+                umma(d_tmem[u], d_ahi + adv, d_bhi + adv, idesc[u], (ks | kk) != 0);
+                umma(d_tmem[u], d_alo + adv, d_bhi + adv, idesc[u], 1);
+                umma(d_tmem[u], d_ahi + adv, d_blo + adv, idesc[u], 1);
+              }
             }
           }
-          umma_commit(b_empty(sb));
-          umma_commit(t_full(g, buf));
-          ++sg[g];
+          for (int u = 0; u < nb; ++u) { umma_commit(b_empty(bslot[u])); umma_commit(t_full(gg[u], bufs[u])); }
+          MB_TRACE(3, ib);
+          for (int u = 0; u < nb; ++u) ++sg[gg[u]];
+          ib += nb;
         }
         for (int ks = 0; ks < a.k_stages; ++ks) umma_commit(a_empty((ia + ks) % a.a_slots));   // patch consumed by every slice
         ia += a.k_stages;
@@ -230,13 +248,15 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
       for (int j = g; j < n_slices; j += 2, ++sgl) {
         const int buf = sgl & 1;
         const int ch0 = j * kSliceCols;
-        // depthwise taps + biases of this slice (issued before the accumulator wait: latency hidden)
+        // depthwise taps + both biases of this slice (issued before the accumulator wait: latency hidden)
         const bool ch_ok = ch0 + lane < a.C;
         float wd[9], bd = 0.f;
 #pragma unroll
         for (int t = 0; t < 9; ++t) wd[t] = ch_ok ? __ldg(a.w_dw + (size_t)t * a.C + ch0 + lane) : 0.f;
         if (ch_ok) bd = __ldg(a.bias_dw + ch0 + lane);
+        const float bev = __ldg(a.bias_e + ch0 + lane);                   // lane i holds the expand bias of column i (padded at upload)
         mbar_wait(t_full(g, buf), (sgl >> 1) & 1);
+        if (threadIdx.x == 0) MB_TRACE(4, sgl);
         tc_fence_after();
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 + buf) * kSliceCols, r);
@@ -245,32 +265,55 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
         mbar_arrive(t_empty(g, buf));                                     // accumulator is in registers: free it early
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 be = __ldg(reinterpret_cast<const float4*>(a.bias_e + ch0) + i4);   // padded past n_pad at upload
           float4 o;
-          o.x = __uint_as_float(r[4 * i4 + 0]) + be.x; o.y = __uint_as_float(r[4 * i4 + 1]) + be.y;
-          o.z = __uint_as_float(r[4 * i4 + 2]) + be.z; o.w = __uint_as_float(r[4 * i4 + 3]) + be.w;
+          o.x = __uint_as_float(r[4 * i4 + 0]) + __shfl_sync(0xffffffffu, bev, 4 * i4 + 0);
+          o.y = __uint_as_float(r[4 * i4 + 1]) + __shfl_sync(0xffffffffu, bev, 4 * i4 + 1);
+          o.z = __uint_as_float(r[4 * i4 + 2]) + __shfl_sync(0xffffffffu, bev, 4 * i4 + 2);
+          o.w = __uint_as_float(r[4 * i4 + 3]) + __shfl_sync(0xffffffffu, bev, 4 * i4 + 3);
           silu2(o.x, o.y); silu2(o.z, o.w);
           if (!inside) o = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(S + row * 128 + ((i4 ^ (row & 7)) << 4)) = o;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");       // expanded tile of this group complete
-        // ---- depthwise 3x3 from shared memory: lane = channel, this warp takes output pixels q, q+4, ...
+        if (threadIdx.x == 0) MB_TRACE(5, sgl);
+        // ---- depthwise 3x3 from shared memory: lane = channel; the tile's output rows are cut into segments that the
+        // four warps take round-robin; a warp walks along its segment with a sliding 3x3 register window, so a new
+        // output costs 3 (stride 1) or 6 (stride 2) conflict-free LDS instead of 9.
         float lsum = 0.f;
-        for (int p = q; p < n_out; p += 4) {
-          const int oh = p / a.tw, ow = p - oh * a.tw;
-          const int ho = ho0 + oh, wo = wo0 + ow;
-          if (ho < a.Ho && wo < a.Wo) {
+        const int lsw = lane >> 2, lo4 = (lane & 3) * 4;
+        auto ldS = [&](int prow_, int pcol_) {
+          const int pos = prow_ * a.pw + pcol_;
+          return *reinterpret_cast<const float*>(S + pos * 128 + ((lsw ^ (pos & 7)) << 4) + lo4);
+        };
+        const int nseg = a.th >= 4 ? 1 : (a.th >= 2 ? 2 : 4);
+        const int segw = (a.tw + nseg - 1) / nseg;
+        for (int sidx = q; sidx < a.th * nseg; sidx += 4) {
+          const int oh = sidx / nseg, ws = (sidx - oh * nseg) * segw, we = min(a.tw, ws + segw);
+          const int ho = ho0 + oh;
+          if (ho >= a.Ho || ws >= we) continue;
+          const int pr = oh * a.stride;
+          float x0[3], x1[3], x2[3];
+          if (a.stride == 1) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) { x1[kh] = ldS(pr + kh, ws); x2[kh] = ldS(pr + kh, ws + 1); x0[kh] = 0.f; }
+          } else {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) { x2[kh] = ldS(pr + kh, 2 * ws); x0[kh] = 0.f; x1[kh] = 0.f; }
+          }
+          float* drow = a.D + (((size_t)b * a.Ho + ho) * a.Wo + wo0) * a.C + ch0 + lane;
+          for (int ow = ws; ow < we; ++ow) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              if (a.stride == 1) { x0[kh] = x1[kh]; x1[kh] = x2[kh]; x2[kh] = ldS(pr + kh, ow + 2); }
+              else { x0[kh] = x2[kh]; x1[kh] = ldS(pr + kh, 2 * ow + 1); x2[kh] = ldS(pr + kh, 2 * ow + 2); }
+            }
             float acc = bd;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                const int pos = (oh * a.stride + kh) * a.pw + ow * a.stride + kw;
-                const float e = *reinterpret_cast<const float*>(S + pos * 128 + ((((lane >> 2) ^ (pos & 7))) << 4) + (lane & 3) * 4);
-                acc = fmaf(e, wd[kh * 3 + kw], acc);
-              }
+            for (int kh = 0; kh < 3; ++kh) {
+              acc = fmaf(x0[kh], wd[kh * 3 + 0], acc); acc = fmaf(x1[kh], wd[kh * 3 + 1], acc); acc = fmaf(x2[kh], wd[kh * 3 + 2], acc);
+            }
             acc = silu1(acc);
-            if (ch_ok) { a.D[(((size_t)b * a.Ho + ho) * a.Wo + wo) * a.C + ch0 + lane] = acc; lsum += acc; }
+            if (ch_ok && wo0 + ow < a.Wo) { drow[(size_t)ow * a.C] = acc; lsum += acc; }
           }
         }
         if (a.partial != nullptr) {
@@ -279,7 +322,9 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
           if (q == 0 && ch_ok)
             a.partial[((size_t)b * tiles_per_chunk + tt) * a.C + ch0 + lane] = (red[lane] + red[32 + lane]) + (red[64 + lane] + red[96 + lane]);
         }
+        if (threadIdx.x == 0) MB_TRACE(6, sgl);
         asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");       // tile S and `red` may be overwritten now
+        if (threadIdx.x == 0) MB_TRACE(7, sgl);
       }
     }
   }
@@ -314,8 +359,8 @@ MbGeom mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin) {
   g.k_stages = (Cin + 63) / 64;
   g.box_c = Cin < 64 ? Cin : 64;
   // shared-memory plan: double-buffer the patch when it is one or two k-stages, 3-4 weight slice slots
-  g.a_slots = g.k_stages <= 2 ? 2 * g.k_stages : g.k_stages;
-  g.b_slots = g.k_stages == 1 ? 4 : 3;
+  g.a_slots = g.k_stages == 1 ? 2 : 3;    // ring of patch stages (a tile uses k_stages of them)
+  g.b_slots = 4;                          // the MMA issuer interleaves four slices
   g.smem_bytes = (size_t)g.a_slots * kABytes + (size_t)g.b_slots * g.k_stages * kBStage + 2 * kSBytes + 1024 +
                  8 * (3 * (size_t)g.a_slots + 2 * (size_t)g.b_slots + 8) + 64 + 16 + 1024 /*alignment*/;
   (void)H; (void)W;
@@ -372,7 +417,27 @@ void launch_mbconv_tc(const MbLaunch& L, cudaStream_t s, LaunchCounter& lc) {
   const CUtensorMap xmap = encode_x_map(L.x, L.B, L.H, L.W, L.Cin, g.box_c, g.pw, g.ph);
   const long long tiles = (long long)L.B * g.tiles_h * g.tiles_w;
   const int grid = tiles < kNumSMs ? (int)tiles : kNumSMs;
+  static long long launch_idx = 0;
+  static const char* trace_path = getenv("BNB_MB_TRACE");
+  static const long long trace_idx = getenv("BNB_MB_TRACE_IDX") ? atoll(getenv("BNB_MB_TRACE_IDX")) : 0;
+  long long* trace = nullptr;
+  if (trace_path && launch_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 8 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 8 * 64 * sizeof(long long), s)); a.trace = trace; }
+  ++launch_idx;
   mbconv_tc_kernel<<<grid, kThreads, g.smem_bytes, s>>>(a, xmap);
+  if (trace) {
+    std::vector<long long> h(8 * 64);
+    BNB_CUDA(cudaStreamSynchronize(s));
+    BNB_CUDA(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "w");
+    if (f) {
+      fprintf(f, "# B=%d H=%d W=%d Cin=%d C=%d stride=%d tile=%dx%d patch=%dx%d tiles/chunk=%d grid=%d k_stages=%d\n# slice bload_issue mma_tmem_free mma_b_ready mma_committed epi_acc_ready epi_E_done epi_dw_done epi_slice_end\n",
+              L.B, L.H, L.W, L.Cin, L.C, L.stride, g.th, g.tw, g.ph, g.pw, g.tiles_h * g.tiles_w, grid, g.k_stages);
+      long long t0 = h[0];
+      for (int i = 0; i < 64; ++i) { fprintf(f, "%d", i); for (int e = 0; e < 8; ++e) fprintf(f, " %lld", h[e * 64 + i] ? h[e * 64 + i] - t0 : -1); fprintf(f, "\n"); }
+      fclose(f);
+    }
+    cudaFree(trace);
+  }
   BNB_LAUNCH_CHECK(lc);
 }
 

@@ -20,6 +20,7 @@ struct MbArgs {
   int B, H, W, Cin, C, Ho, Wo, stride;
   int th, tw, ph, pw, tiles_h, tiles_w;
   int n_pad, k_pad, k_stages, box_c, a_slots, b_slots;
+  long long* trace;   // debug timeline of CTA 0 (BNB_MB_TRACE), else null
 };
 
 struct MbLaunch {
