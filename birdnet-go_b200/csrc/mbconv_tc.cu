@@ -41,7 +41,8 @@ constexpr int kRowsPerPass = kConvThreads / 8, kPasses = 128 / kRowsPerPass;
 constexpr int kSliceCols = 32;      // expanded channels per slice
 constexpr int kABytes = 32768;      // one A stage: raw fp32 [128][64] -> in place hi | lo fp16 tiles (16 KB each)
 constexpr int kBStage = 8192;       // one (slice, k-stage) weight slab: hi 32 x 128 B | lo 32 x 128 B
-constexpr int kSBytes = 16384;      // expanded tile of one group: [128 pos][32 ch] fp32, 16-byte chunks XOR-swizzled
+constexpr int kSPitch = 33;         // floats per position row: bank = (pos + channel) mod 32 for writers (lane = pos) and readers (lane = channel)
+constexpr int kSBytes = 128 * kSPitch * 4 + 512;   // expanded tile of one group: [128 pos][33] fp32, rounded to 1 KB (17408 B)
 
 #define MB_TRACE(ev, iter) do { if (a.trace && blockIdx.x == 0 && (iter) < 64) a.trace[(ev) * 64 + (iter)] = clock64(); } while (0)
 
@@ -106,7 +107,7 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
         const int k = ks * 64 + c * 8;
         const bool k_live = k < a.k_pad;
         float v[kPasses][8];
-        mbar_wait(a_raw(s), ph);
+        mbar_wait_relaxed(a_raw(s), ph);
         if (k_live) {
 #pragma unroll
           for (int q = 0; q < kPasses; ++q) {
@@ -150,7 +151,7 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
         const int hi0 = ty * a.th * a.stride - 1, wi0 = tx * a.tw * a.stride - 1;
         for (int ks = 0; ks < a.k_stages; ++ks, ++ia) {
           const int s = ia % a.a_slots; const uint32_t ph = (ia / a.a_slots) & 1;
-          mbar_wait(a_empty(s), ph ^ 1);
+          mbar_wait_relaxed(a_empty(s), ph ^ 1);
           mbar_arrive_expect_tx(a_raw(s), (uint32_t)(a.box_c * 4 * P));
           tma_load_4d(a_ring + (uint32_t)s * kABytes, &x_map, ks * 64, wi0, hi0, b, a_raw(s));
         }
@@ -164,7 +165,7 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
         for (int j = 0; j < n_slices; ++j, ++ib) {
           const int s = ib % a.b_slots; const uint32_t ph = (ib / a.b_slots) & 1;
           const int rows = min(kSliceCols, a.n_pad - j * kSliceCols);
-          mbar_wait(b_empty(s), ph ^ 1);
+          mbar_wait_relaxed(b_empty(s), ph ^ 1);
           MB_TRACE(0, ib);
           mbar_arrive_expect_tx(b_full(s), (uint32_t)(a.k_stages * 2 * rows * 128));
           for (int ks = 0; ks < a.k_stages; ++ks) {
@@ -188,13 +189,15 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
           const uint32_t i = ia + ks;
           mbar_wait(a_full(i % a.a_slots), (i / a.a_slots) & 1);
         }
-        for (int j0 = 0; j0 < n_slices; j0 += 4) {
-          const int nb = min(4, n_slices - j0);
+        const int batch = min(4, a.b_slots);
+        for (int j0 = 0; j0 < n_slices; j0 += batch) {
+          const int nb = min(batch, n_slices - j0);
+          uint32_t cnt[2] = {0, 0};
           uint32_t d_tmem[4], idesc[4], bslot[4];
           int gg[4], bufs[4];
           for (int u = 0; u < nb; ++u) {
             const int j = j0 + u, g = j & 1;
-            const uint32_t seq = sg[g] + (uint32_t)(u >> 1);        // u = g, g + 2 are this group's 1st / 2nd slice of the batch
+            const uint32_t seq = sg[g] + cnt[g]++;                  // this group's 1st / 2nd slice of the batch
             const int buf = seq & 1;
             const int ncols = min(kSliceCols, a.n_pad - j * kSliceCols);
             gg[u] = g; bufs[u] = buf; bslot[u] = (ib + u) % a.b_slots;
@@ -272,7 +275,8 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
           o.w = __uint_as_float(r[4 * i4 + 3]) + __shfl_sync(0xffffffffu, bev, 4 * i4 + 3);
           silu2(o.x, o.y); silu2(o.z, o.w);
           if (!inside) o = make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(S + row * 128 + ((i4 ^ (row & 7)) << 4)) = o;
+          float* sp = reinterpret_cast<float*>(S) + row * kSPitch + 4 * i4;
+          sp[0] = o.x; sp[1] = o.y; sp[2] = o.z; sp[3] = o.w;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");       // expanded tile of this group complete
         if (threadIdx.x == 0) MB_TRACE(5, sgl);
@@ -280,11 +284,8 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
         // four warps take round-robin; a warp walks along its segment with a sliding 3x3 register window, so a new
         // output costs 3 (stride 1) or 6 (stride 2) conflict-free LDS instead of 9.
         float lsum = 0.f;
-        const int lsw = lane >> 2, lo4 = (lane & 3) * 4;
-        auto ldS = [&](int prow_, int pcol_) {
-          const int pos = prow_ * a.pw + pcol_;
-          return *reinterpret_cast<const float*>(S + pos * 128 + ((lsw ^ (pos & 7)) << 4) + lo4);
-        };
+        const float* Sl = reinterpret_cast<const float*>(S) + lane;
+        auto ldS = [&](int prow_, int pcol_) { return Sl[(prow_ * a.pw + pcol_) * kSPitch]; };
         const int nseg = a.th >= 4 ? 1 : (a.th >= 2 ? 2 : 4);
         const int segw = (a.tw + nseg - 1) / nseg;
         for (int sidx = q; sidx < a.th * nseg; sidx += 4) {
@@ -360,7 +361,7 @@ MbGeom mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin) {
   g.box_c = Cin < 64 ? Cin : 64;
   // shared-memory plan: double-buffer the patch when it is one or two k-stages, 3-4 weight slice slots
   g.a_slots = g.k_stages == 1 ? 2 : 3;    // ring of patch stages (a tile uses k_stages of them)
-  g.b_slots = 4;                          // the MMA issuer interleaves four slices
+  g.b_slots = g.k_stages <= 2 ? 4 : 3;    // the MMA issuer interleaves min(4, b_slots) slices
   g.smem_bytes = (size_t)g.a_slots * kABytes + (size_t)g.b_slots * g.k_stages * kBStage + 2 * kSBytes + 1024 +
                  8 * (3 * (size_t)g.a_slots + 2 * (size_t)g.b_slots + 8) + 64 + 16 + 1024 /*alignment*/;
   (void)H; (void)W;

@@ -126,7 +126,7 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
             }
           }
         }
-        mbar_wait(raw_bar(s), ph);
+        mbar_wait_relaxed(raw_bar(s), ph);
         if (pt == 0) BNB_TRACE(1, it);
         if (k_live) {
 #pragma unroll
@@ -197,7 +197,7 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
       const int m0 = mt * kBM;
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
         const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_wait_relaxed(empty_bar(s), ph ^ 1);
         const uint32_t dst = base + (uint32_t)s * stage_bytes;
         if (lane == 0) {
           BNB_TRACE(0, it);

@@ -35,6 +35,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > kSpinLimit) __trap();
   }
 }
+// Same, for roles that wait long and are not latency critical (producers waiting for a free slot, consumers waiting
+// for data far ahead): back off between polls so the spinning warp does not steal issue slots from the math warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) __nanosleep(100);
+    if (spin > (kSpinLimit >> 4)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
