@@ -287,7 +287,10 @@ float* Engine::run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream
     const int hw_in = g.in_h * g.in_w, hw_out = g.out_h * g.out_w;
     float* d = scratch(g.dw_tensor, w.d, (size_t)hw_out * g.cexp, n);
     int se_parts = 0;
-    if (fused_ && b.expand.tc_img && (!keep_ || fused_force_)) {
+    // fused front half: wins on the large-map blocks of the front phase (K <= 72, few slices); the small-map blocks of
+    // the back phase keep the two-kernel chain (their 32-column MMA slices would be pipeline-latency bound: 36 dependent
+    // MMAs per slice at K = 192)
+    if (fused_ && b.expand.tc_img && ((!keep_ && bi < split_) || fused_force_)) {
       // expand + SiLU + depthwise + SiLU + SE sums in one tcgen05 kernel: the expanded tensor is never materialised
       const MbGeom mg = mbconv_geometry(g.in_h, g.in_w, g.out_h, g.out_w, g.stride, g.cin);
       se_parts = mg.tiles_h * mg.tiles_w;

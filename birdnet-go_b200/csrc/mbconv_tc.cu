@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include <map>
+#include <type_traits>
 #include <vector>
 #include <mutex>
 #include <tuple>
@@ -281,42 +282,45 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
         asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");       // expanded tile of this group complete
         if (threadIdx.x == 0) MB_TRACE(5, sgl);
         // ---- depthwise 3x3 from shared memory: lane = channel; the tile's output rows are cut into segments that the
-        // four warps take round-robin; a warp walks along its segment with a sliding 3x3 register window, so a new
-        // output costs 3 (stride 1) or 6 (stride 2) conflict-free LDS instead of 9.
+        // four warps take round-robin; a warp produces FOUR adjacent outputs at a time from one 3 x (3s+3) register window
+        // (independent accumulator chains: the single-output version was latency-bound at ~260 cycles per pixel).
         float lsum = 0.f;
         const float* Sl = reinterpret_cast<const float*>(S) + lane;
-        auto ldS = [&](int prow_, int pcol_) { return Sl[(prow_ * a.pw + pcol_) * kSPitch]; };
         const int nseg = a.th >= 4 ? 1 : (a.th >= 2 ? 2 : 4);
         const int segw = (a.tw + nseg - 1) / nseg;
-        for (int sidx = q; sidx < a.th * nseg; sidx += 4) {
-          const int oh = sidx / nseg, ws = (sidx - oh * nseg) * segw, we = min(a.tw, ws + segw);
-          const int ho = ho0 + oh;
-          if (ho >= a.Ho || ws >= we) continue;
-          const int pr = oh * a.stride;
-          float x0[3], x1[3], x2[3];
-          if (a.stride == 1) {
+        auto dw_segments = [&](auto stride_tag) {
+          constexpr int ST = decltype(stride_tag)::value;
+          constexpr int NC = 3 * ST + 3;                                   // window columns for four outputs
+          for (int sidx = q; sidx < a.th * nseg; sidx += 4) {
+            const int oh = sidx / nseg, ws = (sidx - oh * nseg) * segw, we = min(a.tw, ws + segw);
+            const int ho = ho0 + oh;
+            if (ho >= a.Ho || ws >= we) continue;
+            float* drow = a.D + (((size_t)b * a.Ho + ho) * a.Wo + wo0) * a.C + ch0 + lane;
+            for (int ow0 = ws; ow0 < we; ow0 += 4) {
+              float xw[3][NC];
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) { x1[kh] = ldS(pr + kh, ws); x2[kh] = ldS(pr + kh, ws + 1); x0[kh] = 0.f; }
-          } else {
+              for (int kh = 0; kh < 3; ++kh) {
+                const float* rp = Sl + ((oh * ST + kh) * a.pw) * kSPitch;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) { x2[kh] = ldS(pr + kh, 2 * ws); x0[kh] = 0.f; x1[kh] = 0.f; }
-          }
-          float* drow = a.D + (((size_t)b * a.Ho + ho) * a.Wo + wo0) * a.C + ch0 + lane;
-          for (int ow = ws; ow < we; ++ow) {
+                for (int cc = 0; cc < NC; ++cc) xw[kh][cc] = rp[min(ow0 * ST + cc, a.pw - 1) * kSPitch];
+              }
+              float acc[4] = {bd, bd, bd, bd};
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              if (a.stride == 1) { x0[kh] = x1[kh]; x1[kh] = x2[kh]; x2[kh] = ldS(pr + kh, ow + 2); }
-              else { x0[kh] = x2[kh]; x1[kh] = ldS(pr + kh, 2 * ow + 1); x2[kh] = ldS(pr + kh, 2 * ow + 2); }
+              for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) acc[i] = fmaf(xw[kh][i * ST + kw], wd[kh * 3 + kw], acc[i]);
+              silu2(acc[0], acc[1]); silu2(acc[2], acc[3]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int ow = ow0 + i;
+                if (ch_ok && ow < we && wo0 + ow < a.Wo) { drow[(size_t)ow * a.C] = acc[i]; lsum += acc[i]; }
+              }
             }
-            float acc = bd;
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              acc = fmaf(x0[kh], wd[kh * 3 + 0], acc); acc = fmaf(x1[kh], wd[kh * 3 + 1], acc); acc = fmaf(x2[kh], wd[kh * 3 + 2], acc);
-            }
-            acc = silu1(acc);
-            if (ch_ok && wo0 + ow < a.Wo) { drow[(size_t)ow * a.C] = acc; lsum += acc; }
           }
-        }
+        };
+        if (a.stride == 1) dw_segments(std::integral_constant<int, 1>{}); else dw_segments(std::integral_constant<int, 2>{});
         if (a.partial != nullptr) {
           red[q * 32 + lane] = lsum;
           asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");

@@ -160,3 +160,44 @@ def test_full_size_property_linearity_of_batching(clf):
     assert np.array_equal(y[:8], y[24:])
     z = clf.predict_batch((x[:8] * np.float32(0.5)))
     assert np.abs(_sig(z) - _sig(y[:8])).max() <= SIG_TOL
+
+
+def test_bat_pipeline_backbone_embedding(clf):
+    """BASELINE config 4 (BattyBirdNET): 144000 raw samples captured at 256 kHz go through the SAME v2.4 backbone and the
+    [1024] embedding feeds a small custom head (bat_onnx.go:252, custom_classifier.go:147-173).  The regional head files are
+    downloaded at run time in the reference and are not available here, so: backbone-to-embedding parity on synthetic
+    20-80 kHz FM sweeps + noise, and a seeded synthetic dense+sigmoid head applied to both embeddings."""
+    fs = 256000.0
+    t = np.arange(144000) / fs
+    rng = np.random.default_rng(256)
+    x = np.zeros((6, 144000), np.float32)
+    for i in range(6):
+        f0, f1 = rng.uniform(60e3, 80e3), rng.uniform(20e3, 35e3)
+        dur = rng.uniform(0.004, 0.02)
+        sig = 0.02 * rng.standard_normal(144000)
+        for start in np.arange(0.02, 0.55, rng.uniform(0.06, 0.12)):
+            m = (t >= start) & (t < start + dur)
+            tt = t[m] - start
+            sig[m] += 0.4 * np.sin(2 * np.pi * (f0 * tt + 0.5 * (f1 - f0) / dur * tt * tt)) * np.hanning(m.sum())
+        x[i] = np.round(np.clip(sig, -1, 1) * 32767).astype(np.int16).astype(np.float32) / np.float32(32768)
+    logits, emb = clf.predict_batch(x, with_embeddings=True)
+    rl, remb = bo.Oracle(dtype=torch.float64).predict_batch(x, with_embeddings=True)
+    assert np.abs(emb - remb).max() <= 2e-3 * max(1.0, np.abs(remb).max())
+    assert np.abs(_sig(logits) - _sig(rl)).max() <= SIG_TOL
+    w = rng.standard_normal((1024, 12)).astype(np.float64) * 0.05     # synthetic 12-class regional head
+    head = lambda e: 1.0 / (1.0 + np.exp(-(e.astype(np.float64) @ w)))
+    assert np.abs(head(emb) - head(remb)).max() <= 1e-3
+
+
+def test_full_batch_256_invariants(lib_path):
+    """BASELINE config 2/3 sizes (batch 256, micro-batches, two phases): independence of chunks and of batch position."""
+    from bench import soundscape_batch
+    c = bb.B200Classifier(max_batch=256)
+    x = soundscape_batch(256)                                    # 79 distinct chunks tiled
+    y = c.predict_batch(x)
+    assert np.isfinite(y).all()
+    for k in range(79, 256):
+        assert np.array_equal(y[k], y[k % 79]), k                # same chunk in another micro-batch / phase slot: identical bits
+    idx, conf = c.analyze_batch(x, 1.5, 10)
+    assert np.array_equal(idx[:79], idx[79:158]) and (np.diff(conf, axis=1) <= 0).all()
+    c.close()
