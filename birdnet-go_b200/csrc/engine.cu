@@ -290,9 +290,10 @@ float* Engine::run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream
     // fused front half: wins on the large-map blocks of the front phase (K <= 72, few slices); the small-map blocks of
     // the back phase keep the two-kernel chain (their 32-column MMA slices would be pipeline-latency bound: 36 dependent
     // MMAs per slice at K = 192)
-    if (fused_ && b.expand.tc_img && ((!keep_ && bi < split_) || fused_force_)) {
+    const MbGeom mg = mbconv_geometry(g.in_h, g.in_w, g.out_h, g.out_w, g.stride, g.cin);
+    const bool fits = mg.th > 0 && mg.smem_bytes <= kMbSmemLimit;        // K > 128 does not fit the shared-memory plan
+    if (fused_ && fits && b.expand.tc_img && ((!keep_ && bi < split_) || fused_force_)) {
       // expand + SiLU + depthwise + SiLU + SE sums in one tcgen05 kernel: the expanded tensor is never materialised
-      const MbGeom mg = mbconv_geometry(g.in_h, g.in_w, g.out_h, g.out_w, g.stride, g.cin);
       se_parts = mg.tiles_h * mg.tiles_w;
       MbLaunch ml{};
       ml.x = cur; ml.Wimg = b.expand.tc_img; ml.bias_e = b.expand.b; ml.w_dw = b.dw.w; ml.bias_dw = b.dw.b; ml.D = d;

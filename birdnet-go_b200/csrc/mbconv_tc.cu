@@ -14,7 +14,7 @@
 //            coordinates arrive as zeros), converted once per tile to fp16 hi/lo 128B-swizzled K-major tiles.
 //   slices = the expanded channels in groups of 32: per slice one small MMA group (N = 32) into one of four
 //            32-column TMEM accumulators; B (pre-split weight image of pw_tc.cu) streams per slice via cp.async.bulk.
-//   epilogue groups (2 x 4 warps) alternate slices: TMEM -> +bias -> SiLU -> zero outside the image (padding is
+//   epilogue groups (3 x 4 warps) take slices round-robin: TMEM -> +bias -> SiLU -> zero outside the image (padding is
 //            zero in the EXPANDED domain) -> swizzled smem tile [128 pos][32 ch] -> group barrier -> depthwise with
 //            lane = channel (conflict-free LDS), coalesced 128 B stores of the output, SE row sums (deterministic).
 #include <stdio.h>
@@ -36,14 +36,20 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 608;       // 19 warps: 8 epilogue (2 groups), MMA, A loader, 8 converters, B loader
-constexpr int kMmaWarp = 8, kLoadAWarp = 9, kConvWarp0 = 10, kConvThreads = 256, kLoadBWarp = 18;
+constexpr int kGroups = 3;          // epilogue groups of 4 warps; slice j belongs to group j % kGroups (the CUDA-core work of the
+                                    // epilogue, not the MMA, bounds this kernel: 12 of the 19 warps do it)
+constexpr int kThreads = 608;       // 19 warps: 12 epilogue (3 groups), MMA, A loader, 4 converters, B loader
+constexpr int kMmaWarp = 12, kLoadAWarp = 13, kConvWarp0 = 14, kConvThreads = 128, kLoadBWarp = 18;
+constexpr int kTmemCols = 256;      // kGroups x 2 accumulators x 32 columns, rounded to a power of two
 constexpr int kRowsPerPass = kConvThreads / 8, kPasses = 128 / kRowsPerPass;
 constexpr int kSliceCols = 32;      // expanded channels per slice
 constexpr int kABytes = 32768;      // one A stage: raw fp32 [128][64] -> in place hi | lo fp16 tiles (16 KB each)
-constexpr int kBStage = 8192;       // one (slice, k-stage) weight slab: hi 32 x 128 B | lo 32 x 128 B
-constexpr int kSPitch = 33;         // floats per position row: bank = (pos + channel) mod 32 for writers (lane = pos) and readers (lane = channel)
-constexpr int kSBytes = 128 * kSPitch * 4 + 512;   // expanded tile of one group: [128 pos][33] fp32, rounded to 1 KB (17408 B)
+constexpr int kUnitCols = kGroups * kSliceCols;   // one MMA unit: a slice for every group (N = 96)
+constexpr int kBufCols = 128;       // TMEM columns per accumulator buffer (unit rounded up)
+constexpr int kBStage = 2 * kUnitCols * 128;     // one (unit, k-stage) weight slab: hi 96 x 128 B | lo 96 x 128 B (24 KB)
+constexpr int kSPitch = 36;         // floats per position row (144 B): 16 B-aligned rows for STS.128 by the writers (lane = pos, 8 lanes cover all banks);
+                                    // readers (lane = channel) hit consecutive banks
+constexpr int kSBytes = 128 * kSPitch * 4 + 1024;  // expanded tile of one group: [128 pos][36] fp32 + 1 KB slack that the depthwise window may over-read
 
 #define MB_TRACE(ev, iter) do { if (a.trace && blockIdx.x == 0 && (iter) < 64) a.trace[(ev) * 64 + (iter)] = clock64(); } while (0)
 
@@ -62,8 +68,8 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
   const uint32_t b_slot_bytes = (uint32_t)a.k_stages * kBStage;
   const uint32_t b_ring = a_ring + (uint32_t)a.a_slots * kABytes;             // b_slots x k_stages x 8 KB
   const uint32_t s_tiles = b_ring + (uint32_t)a.b_slots * b_slot_bytes;       // 2 x 16 KB
-  const uint32_t s_red = s_tiles + 2 * kSBytes;                               // 2 groups x 4 warps x 32 floats
-  const uint32_t bars = s_red + 1024;
+  const uint32_t s_red = s_tiles + kGroups * kSBytes;                         // kGroups x 4 warps x 32 floats
+  const uint32_t bars = s_red + 2048;
   auto a_raw = [&](int s) { return bars + 8u * s; };
   auto a_full = [&](int s) { return bars + 8u * (a.a_slots + s); };
   auto a_empty = [&](int s) { return bars + 8u * (2 * a.a_slots + s); };
@@ -71,18 +77,18 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
   auto b_full = [&](int s) { return bb + 8u * s; };
   auto b_empty = [&](int s) { return bb + 8u * (a.b_slots + s); };
   const uint32_t tb = bb + 8u * (2 * a.b_slots);
-  auto t_full = [&](int g, int buf) { return tb + 8u * (g * 2 + buf); };
-  auto t_empty = [&](int g, int buf) { return tb + 8u * (4 + g * 2 + buf); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (tb - base) + 64);
+  auto t_full = [&](int buf) { return tb + 8u * buf; };
+  auto t_empty = [&](int buf) { return tb + 8u * (2 + buf); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (tb - base) + 8 * 4 * kGroups);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.a_slots; ++s) { mbar_init(a_raw(s), 1); mbar_init(a_full(s), kConvThreads); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < a.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int g = 0; g < 2; ++g) for (int b = 0; b < 2; ++b) { mbar_init(t_full(g, b), 1); mbar_init(t_empty(g, b), 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), kGroups * 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -93,11 +99,12 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
   const int tiles_per_chunk = a.tiles_h * a.tiles_w;
   const int total_tiles = a.B * tiles_per_chunk;
   const int n_slices = (a.n_pad + kSliceCols - 1) / kSliceCols;
+  const int n_units = (n_slices + kGroups - 1) / kGroups;
   const int P = a.ph * a.pw;
   const int pitch = a.box_c * 4;
 
   if (warp >= kConvWarp0 && warp < kLoadBWarp) {
-    // ============================== A converters (8 warps): raw fp32 patch -> fp16 hi / lo tiles, in place ==
+    // ============================== A converters (4 warps): raw fp32 patch -> fp16 hi / lo tiles, in place ==
     const int pt = threadIdx.x - kConvWarp0 * 32;
     const int c = pt & 7, r0 = pt >> 3;
     uint32_t ia = 0;
@@ -159,21 +166,21 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
       }
     }
   } else if (warp == kLoadBWarp) {
-    // ============================== B loader: weight slabs of one 32-channel slice, all k-stages ============
+    // ============================== B loader: weight slabs of one unit (kGroups slices = 96 channels), all k-stages ==
     if (lane == 0) {
       uint32_t ib = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int j = 0; j < n_slices; ++j, ++ib) {
+        for (int u = 0; u < n_units; ++u, ++ib) {
           const int s = ib % a.b_slots; const uint32_t ph = (ib / a.b_slots) & 1;
-          const int rows = min(kSliceCols, a.n_pad - j * kSliceCols);
+          const int rows = min(kUnitCols, a.n_pad - u * kUnitCols);
           mbar_wait_relaxed(b_empty(s), ph ^ 1);
           MB_TRACE(0, ib);
           mbar_arrive_expect_tx(b_full(s), (uint32_t)(a.k_stages * 2 * rows * 128));
           for (int ks = 0; ks < a.k_stages; ++ks) {
-            const uint8_t* src = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)j * kSliceCols * 128;
+            const uint8_t* src = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)u * kUnitCols * 128;
             const uint32_t dst = b_ring + (uint32_t)s * b_slot_bytes + (uint32_t)ks * kBStage;
             bulk_g2s(dst, src, (uint32_t)rows * 128u, b_full(s));
-            bulk_g2s(dst + 4096, src + (size_t)a.n_pad * 128, (uint32_t)rows * 128u, b_full(s));
+            bulk_g2s(dst + kBStage / 2, src + (size_t)a.n_pad * 128, (uint32_t)rows * 128u, b_full(s));
           }
         }
       }
@@ -181,32 +188,29 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ================================================================
     if (lane == 0) {
-      // A slice's MMAs all accumulate into one 32-column TMEM tile, so back-to-back they are bound by the MMA
-      // pipeline latency (measured ~170 cycles each).  Up to four slices (the four accumulators: 2 groups x 2 buffers)
-      // are therefore issued interleaved, k-step by k-step.
-      uint32_t ia = 0, ib = 0, sg[2] = {0, 0};
+      // One MMA covers a unit = kGroups adjacent slices (N = 96): with N = 32 the instruction rate was bound by re-reading
+      // the A tile from shared memory for every slice (~93 cycles per MMA whatever N).  Two units (the two TMEM buffers) are
+      // issued interleaved k-step by k-step so that consecutive MMAs never accumulate into the same columns.
+      uint32_t ia = 0, ib = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         for (int ks = 0; ks < a.k_stages; ++ks) {                 // the whole converted patch must be in place
           const uint32_t i = ia + ks;
           mbar_wait(a_full(i % a.a_slots), (i / a.a_slots) & 1);
         }
-        const int batch = min(4, a.b_slots);
-        for (int j0 = 0; j0 < n_slices; j0 += batch) {
-          const int nb = min(batch, n_slices - j0);
-          uint32_t cnt[2] = {0, 0};
-          uint32_t d_tmem[4], idesc[4], bslot[4];
-          int gg[4], bufs[4];
-          for (int u = 0; u < nb; ++u) {
-            const int j = j0 + u, g = j & 1;
-            const uint32_t seq = sg[g] + cnt[g]++;                  // this group's 1st / 2nd slice of the batch
-            const int buf = seq & 1;
-            const int ncols = min(kSliceCols, a.n_pad - j * kSliceCols);
-            gg[u] = g; bufs[u] = buf; bslot[u] = (ib + u) % a.b_slots;
-            idesc[u] = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | (8u << 24);    // f32 accum, f16 x f16, M = 128
-            d_tmem[u] = tmem_base + (uint32_t)(g * 2 + buf) * kSliceCols;
-            mbar_wait(t_empty(g, buf), ((seq >> 1) & 1) ^ 1);
-            if (u == 0) MB_TRACE(1, ib);
-            mbar_wait(b_full(bslot[u]), ((ib + u) / a.b_slots) & 1);
+        const int batch = min(2, a.b_slots);
+        for (int u0 = 0; u0 < n_units; u0 += batch) {
+          const int nb = min(batch, n_units - u0);
+          uint32_t d_tmem[2], idesc[2], bslot[2];
+          int bufs[2];
+          for (int v = 0; v < nb; ++v) {
+            const uint32_t seq = ib + v;
+            const int ncols = min(kUnitCols, a.n_pad - (u0 + v) * kUnitCols);
+            bufs[v] = seq & 1; bslot[v] = seq % a.b_slots;
+            idesc[v] = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | (8u << 24);    // f32 accum, f16 x f16, M = 128
+            d_tmem[v] = tmem_base + (uint32_t)bufs[v] * kBufCols;
+            mbar_wait(t_empty(bufs[v]), ((seq >> 1) & 1) ^ 1);
+            if (v == 0) MB_TRACE(1, ib);
+            mbar_wait(b_full(bslot[v]), (seq / a.b_slots) & 1);
           }
           MB_TRACE(2, ib);
           tc_fence_after();
@@ -216,18 +220,17 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
             const int kk_n = min(64, a.k_pad - ks * 64) / 16;
             for (int kk = 0; kk < kk_n; ++kk) {
               const uint64_t adv = (uint64_t)(kk * 2);
-              for (int u = 0; u < nb; ++u) {
-                const uint32_t sbk = b_ring + bslot[u] * b_slot_bytes + (uint32_t)ks * kBStage;
-                const uint64_t d_bhi = make_desc(sbk), d_blo = make_desc(sbk + 4096);
-                umma(d_tmem[u], d_ahi + adv, d_bhi + adv, idesc[u], (ks | kk) != 0);
-                umma(d_tmem[u], d_alo + adv, d_bhi + adv, idesc[u], 1);
-                umma(d_tmem[u], d_ahi + adv, d_blo + adv, idesc[u], 1);
+              for (int v = 0; v < nb; ++v) {
+                const uint32_t sbk = b_ring + bslot[v] * b_slot_bytes + (uint32_t)ks * kBStage;
+                const uint64_t d_bhi = make_desc(sbk), d_blo = make_desc(sbk + kBStage / 2);
+                umma(d_tmem[v], d_ahi + adv, d_bhi + adv, idesc[v], (ks | kk) != 0);
+                umma(d_tmem[v], d_alo + adv, d_bhi + adv, idesc[v], 1);
+                umma(d_tmem[v], d_ahi + adv, d_blo + adv, idesc[v], 1);
               }
             }
           }
-          for (int u = 0; u < nb; ++u) { umma_commit(b_empty(bslot[u])); umma_commit(t_full(gg[u], bufs[u])); }
+          for (int v = 0; v < nb; ++v) { umma_commit(b_empty(bslot[v])); umma_commit(t_full(bufs[v])); }
           MB_TRACE(3, ib);
-          for (int u = 0; u < nb; ++u) ++sg[gg[u]];
           ib += nb;
         }
         for (int ks = 0; ks < a.k_stages; ++ks) umma_commit(a_empty((ia + ks) % a.a_slots));   // patch consumed by every slice
@@ -235,7 +238,7 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
       }
     }
   } else {
-    // ============================== epilogue groups (2 x 4 warps) ==============================================
+    // ============================== epilogue groups (3 x 4 warps) ==============================================
     const int g = warp >> 2, q = warp & 3;
     const int row = q * 32 + lane;                                        // patch position = TMEM lane of this thread
     const int prow = row / a.pw, pcol = row - prow * a.pw;
@@ -249,8 +252,14 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
       const int ho0 = ty * a.th, wo0 = tx * a.tw;
       const int hi = ho0 * a.stride - 1 + prow, wi = wo0 * a.stride - 1 + pcol;
       const bool inside = row < P && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;   // padding is ZERO in the expanded domain
-      for (int j = g; j < n_slices; j += 2, ++sgl) {
+      for (int u = 0; u < n_units; ++u, ++sgl) {
         const int buf = sgl & 1;
+        const int j = u * kGroups + g;
+        if (j >= n_slices) {                                               // ragged last unit: handshake only
+          mbar_wait(t_full(buf), (sgl >> 1) & 1);
+          mbar_arrive(t_empty(buf));
+          continue;
+        }
         const int ch0 = j * kSliceCols;
         // depthwise taps + both biases of this slice (issued before the accumulator wait: latency hidden)
         const bool ch_ok = ch0 + lane < a.C;
@@ -259,14 +268,14 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
         for (int t = 0; t < 9; ++t) wd[t] = ch_ok ? __ldg(a.w_dw + (size_t)t * a.C + ch0 + lane) : 0.f;
         if (ch_ok) bd = __ldg(a.bias_dw + ch0 + lane);
         const float bev = __ldg(a.bias_e + ch0 + lane);                   // lane i holds the expand bias of column i (padded at upload)
-        mbar_wait(t_full(g, buf), (sgl >> 1) & 1);
+        mbar_wait(t_full(buf), (sgl >> 1) & 1);
         if (threadIdx.x == 0) MB_TRACE(4, sgl);
         tc_fence_after();
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 + buf) * kSliceCols, r);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kBufCols + (uint32_t)g * kSliceCols, r);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(t_empty(g, buf));                                     // accumulator is in registers: free it early
+        mbar_arrive(t_empty(buf));                                        // accumulator is in registers: free it early
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           float4 o;
@@ -276,8 +285,7 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
           o.w = __uint_as_float(r[4 * i4 + 3]) + __shfl_sync(0xffffffffu, bev, 4 * i4 + 3);
           silu2(o.x, o.y); silu2(o.z, o.w);
           if (!inside) o = make_float4(0.f, 0.f, 0.f, 0.f);
-          float* sp = reinterpret_cast<float*>(S) + row * kSPitch + 4 * i4;
-          sp[0] = o.x; sp[1] = o.y; sp[2] = o.z; sp[3] = o.w;
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(S) + row * kSPitch + 4 * i4) = o;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");       // expanded tile of this group complete
         if (threadIdx.x == 0) MB_TRACE(5, sgl);
@@ -288,22 +296,23 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
         const float* Sl = reinterpret_cast<const float*>(S) + lane;
         const int nseg = a.th >= 4 ? 1 : (a.th >= 2 ? 2 : 4);
         const int segw = (a.tw + nseg - 1) / nseg;
+        const int wlim = min(a.tw, a.Wo - wo0);                            // output columns of this tile that exist
         auto dw_segments = [&](auto stride_tag) {
           constexpr int ST = decltype(stride_tag)::value;
           constexpr int NC = 3 * ST + 3;                                   // window columns for four outputs
+          const int rowp = a.pw * kSPitch;
           for (int sidx = q; sidx < a.th * nseg; sidx += 4) {
-            const int oh = sidx / nseg, ws = (sidx - oh * nseg) * segw, we = min(a.tw, ws + segw);
+            const int oh = sidx / nseg, ws = (sidx - oh * nseg) * segw, we = min(wlim, ws + segw);
             const int ho = ho0 + oh;
             if (ho >= a.Ho || ws >= we) continue;
-            float* drow = a.D + (((size_t)b * a.Ho + ho) * a.Wo + wo0) * a.C + ch0 + lane;
-            for (int ow0 = ws; ow0 < we; ow0 += 4) {
+            float* dp = a.D + (((size_t)b * a.Ho + ho) * a.Wo + wo0 + ws) * a.C + ch0 + lane;
+            const float* rp = Sl + (oh * ST * a.pw + ws * ST) * kSPitch;   // window origin; columns at immediate offsets
+            for (int nleft = we - ws; nleft > 0; nleft -= 4, rp += 4 * ST * kSPitch, dp += 4 * (size_t)a.C) {
               float xw[3][NC];
 #pragma unroll
-              for (int kh = 0; kh < 3; ++kh) {
-                const float* rp = Sl + ((oh * ST + kh) * a.pw) * kSPitch;
+              for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                for (int cc = 0; cc < NC; ++cc) xw[kh][cc] = rp[min(ow0 * ST + cc, a.pw - 1) * kSPitch];
-              }
+                for (int cc = 0; cc < NC; ++cc) xw[kh][cc] = rp[kh * rowp + cc * kSPitch];   // may over-read past the patch: unused
               float acc[4] = {bd, bd, bd, bd};
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh)
@@ -314,8 +323,9 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
               silu2(acc[0], acc[1]); silu2(acc[2], acc[3]);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const int ow = ow0 + i;
-                if (ch_ok && ow < we && wo0 + ow < a.Wo) { drow[(size_t)ow * a.C] = acc[i]; lsum += acc[i]; }
+                const bool ok = ch_ok && i < nleft;
+                if (ok) dp[i * (size_t)a.C] = acc[i];
+                lsum += ok ? acc[i] : 0.f;
               }
             }
           }
@@ -339,7 +349,7 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
   if (warp == kMmaWarp) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
   }
 }
 
@@ -363,11 +373,12 @@ MbGeom mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin) {
     }
   g.k_stages = (Cin + 63) / 64;
   g.box_c = Cin < 64 ? Cin : 64;
-  // shared-memory plan: double-buffer the patch when it is one or two k-stages, 3-4 weight slice slots
-  g.a_slots = g.k_stages == 1 ? 2 : 3;    // ring of patch stages (a tile uses k_stages of them)
-  g.b_slots = g.k_stages <= 2 ? 4 : 3;    // the MMA issuer interleaves min(4, b_slots) slices
-  g.smem_bytes = (size_t)g.a_slots * kABytes + (size_t)g.b_slots * g.k_stages * kBStage + 2 * kSBytes + 1024 +
-                 8 * (3 * (size_t)g.a_slots + 2 * (size_t)g.b_slots + 8) + 64 + 16 + 1024 /*alignment*/;
+  // shared-memory plan: the patch ring (a tile uses k_stages slots; two tiles in flight only when k_stages == 1) and the
+  // weight-unit ring (one slot = 96 channels x all k-stages; the MMA issuer interleaves min(2, b_slots) units)
+  g.a_slots = g.k_stages == 1 ? 2 : g.k_stages;
+  g.b_slots = g.k_stages <= 2 ? 2 : 1;
+  g.smem_bytes = (size_t)g.a_slots * kABytes + (size_t)g.b_slots * g.k_stages * kBStage + kGroups * kSBytes + 2048 +
+                 8 * (3 * (size_t)g.a_slots + 2 * (size_t)g.b_slots + 4 * kGroups) + 64 + 16 + 1024 /*alignment*/;
   (void)H; (void)W;
   return g;
 }
@@ -408,7 +419,7 @@ void launch_mbconv_tc(const MbLaunch& L, cudaStream_t s, LaunchCounter& lc) {
   static size_t max_set = 0;
   const MbGeom g = mbconv_geometry(L.H, L.W, L.Ho, L.Wo, L.stride, L.Cin);
   if (g.th == 0) throw std::runtime_error("mbconv_tc: no tile geometry fits 128 patch positions");
-  if (g.smem_bytes > 227 * 1024) throw std::runtime_error("mbconv_tc: shared memory budget exceeded");
+  if (g.smem_bytes > kMbSmemLimit) throw std::runtime_error("mbconv_tc: shared memory budget exceeded");
   if (g.smem_bytes > max_set) {
     BNB_CUDA(cudaFuncSetAttribute(mbconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     max_set = g.smem_bytes;

@@ -12,6 +12,7 @@ struct MbGeom {
   int k_stages, box_c, a_slots, b_slots;
   size_t smem_bytes;
 };
+constexpr size_t kMbSmemLimit = 227 * 1024;
 // tile geometry + shared-memory plan for one block (host logic, also used by the CPU tests)
 MbGeom mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin);
 

@@ -201,3 +201,20 @@ def test_full_batch_256_invariants(lib_path):
     idx, conf = c.analyze_batch(x, 1.5, 10)
     assert np.array_equal(idx[:79], idx[79:158]) and (np.diff(conf, axis=1) <= 0).all()
     c.close()
+
+
+def test_fused_and_unfused_chains_agree(lib_path, golden, audio, monkeypatch):
+    """The fused expand+depthwise kernel (default for the large-map blocks, forced for all blocks with BNB_FUSED=2)
+    and the two-kernel chain (BNB_FUSED=0) are two schedules of the same arithmetic: same oracle, same tolerance."""
+    chunks = bo.slice_chunks(audio["soundscape"], 72000)[:24]
+    ref = golden["soundscape_logits"][:24].astype(np.float64)
+    outs = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("BNB_FUSED", mode)
+        c = bb.B200Classifier(max_batch=24, micro_batch=8)
+        outs[mode] = c.predict_batch(chunks).copy()
+        c.close()
+        err = np.abs(_sig(outs[mode]) - _sig(ref)).max()
+        assert err <= 1e-3, (mode, err)
+        assert (outs[mode].argmax(1) == ref.argmax(1)).all()
+    assert np.abs(outs["0"] - outs["2"]).max() < 5e-3
