@@ -70,7 +70,7 @@ SYMBOLS = {
     "bnb_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bnb_profile_launches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bnb_debug_pw_tiling": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
-    "bnb_debug_mbconv_geometry": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "bnb_debug_mbconv_geometry": (C.c_int, [C.c_int] * 9 + [C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "bnb_describe_model": (C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "bnb_debug_read_tensor": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "bnb_debug_keep_intermediates": (C.c_int, [C.c_void_p, C.c_int]),
@@ -111,12 +111,12 @@ def pw_tiling(M, N, K):
     return bn.value, st.value, sm.value
 
 
-def mbconv_geometry(H, W, Ho, Wo, stride, Cin):
+def mbconv_geometry(H, W, Ho, Wo, stride, Cin, C_exp=0, B=0, max_tiles=0):
     """Tile geometry + smem bytes of the fused expand+depthwise kernel for one block."""
     lib = load_library()
     out = (C.c_int * 10)()
     sm = C.c_int64()
-    _check(lib.bnb_debug_mbconv_geometry(H, W, Ho, Wo, stride, Cin, out, C.byref(sm)))
+    _check(lib.bnb_debug_mbconv_geometry(H, W, Ho, Wo, stride, Cin, C_exp, B, max_tiles, out, C.byref(sm)))
     keys = ("th", "tw", "ph", "pw", "tiles_h", "tiles_w", "k_stages", "box_c", "a_slots", "b_slots")
     d = dict(zip(keys, list(out)))
     d["smem_bytes"] = sm.value

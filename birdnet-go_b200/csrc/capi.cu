@@ -197,9 +197,9 @@ int bnb_debug_pw_tiling(int M, int N, int K, int* bn, int* stages, int64_t* smem
   return BNB_OK;
 }
 
-int bnb_debug_mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin, int* out10, int64_t* smem_bytes) {
+int bnb_debug_mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin, int C, int B, int max_tiles, int* out10, int64_t* smem_bytes) {
   if (!out10 || !smem_bytes) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL out");
-  const MbGeom g = mbconv_geometry(H, W, Ho, Wo, stride, Cin);
+  const MbGeom g = mbconv_geometry(H, W, Ho, Wo, stride, Cin, C, B, max_tiles);
   const int v[10] = {g.th, g.tw, g.ph, g.pw, g.tiles_h, g.tiles_w, g.k_stages, g.box_c, g.a_slots, g.b_slots};
   for (int i = 0; i < 10; ++i) out10[i] = v[i];
   *smem_bytes = (int64_t)g.smem_bytes;

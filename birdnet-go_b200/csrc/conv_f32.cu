@@ -28,11 +28,14 @@ __global__ void __launch_bounds__(kStemThreads)
 stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restrict__ stem_out, float* __restrict__ out) {
   __shared__ __align__(16) float s_in[kStemKh][4][kStemQ][2];          // [row][col%4][col/4][ci]
   __shared__ __align__(16) float s_w[kStemKh * kStemKw * 2 * kStemCo];  // [kh][kw][ci][co]
-  __shared__ __align__(16) float s_wm[kStemCo * 2 * kStemCo];           // [co][48]
+  __shared__ __align__(16) float s_wm[kStemCo * 2 * kStemCo];           // [48][co] (transposed at load)
   __shared__ float s_b[kStemCo], s_bm[kStemCo];
   const int tid = threadIdx.x, h = blockIdx.x, b = blockIdx.y;
   for (int i = tid; i < kStemKh * kStemKw * 2 * kStemCo; i += kStemThreads) s_w[i] = __ldg(p.w_stem + i);
-  for (int i = tid; i < kStemCo * 2 * kStemCo; i += kStemThreads) s_wm[i] = __ldg(p.w_mix + i);
+  for (int i = tid; i < kStemCo * 2 * kStemCo; i += kStemThreads) {     // [co][48] -> [c][co]
+    const int co = i / (2 * kStemCo), c = i - co * 2 * kStemCo;
+    s_wm[c * kStemCo + co] = __ldg(p.w_mix + i);
+  }
   if (tid < kStemCo) { s_b[tid] = __ldg(p.b_stem + tid); s_bm[tid] = __ldg(p.b_mix + tid); }
   // stage input rows; padded column index pc = col + pad_l  (pc in [0, kStemCols))
   const float* inb = in + (size_t)b * p.in_h * p.in_w * 2;
@@ -45,9 +48,11 @@ stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restr
   }
   __syncthreads();
 
-  float acc0[kStemCo], acc1[kStemCo];
+  // accumulators as channel PAIRS: every FMA of this loop is a packed fma.rn.f32x2 (sm_100 FFMA2: x broadcast to both
+  // halves, two adjacent output channels' weights from one 64-bit register pair), halving the FMA-pipe instruction count
+  float2 acc0[kStemCo / 2], acc1[kStemCo / 2];
 #pragma unroll
-  for (int c = 0; c < kStemCo; ++c) { acc0[c] = s_b[c]; acc1[c] = s_b[c]; }
+  for (int c = 0; c < kStemCo / 2; ++c) { acc0[c] = make_float2(s_b[2 * c], s_b[2 * c + 1]); acc1[c] = acc0[c]; }
   // stem position w0 = 2*tid reads padded cols 4*tid + kw ; w1 = 2*tid+1 reads 4*tid + 2 + kw
 #pragma unroll
   for (int kh = 0; kh < kStemKh; ++kh) {
@@ -56,56 +61,57 @@ stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restr
       const int pc0 = kw, pc1 = kw + 2;   // + 4*tid
       const float2 x0 = *reinterpret_cast<const float2*>(&s_in[kh][pc0 & 3][tid + (pc0 >> 2)][0]);
       const float2 x1 = *reinterpret_cast<const float2*>(&s_in[kh][pc1 & 3][tid + (pc1 >> 2)][0]);
+      const float2 x0a = make_float2(x0.x, x0.x), x0b = make_float2(x0.y, x0.y);
+      const float2 x1a = make_float2(x1.x, x1.x), x1b = make_float2(x1.y, x1.y);
       const float* w = s_w + ((kh * kStemKw + kw) * 2) * kStemCo;
 #pragma unroll
       for (int c4 = 0; c4 < kStemCo / 4; ++c4) {
         const float4 wa = *reinterpret_cast<const float4*>(w + 4 * c4);
         const float4 wb = *reinterpret_cast<const float4*>(w + kStemCo + 4 * c4);
-        acc0[4 * c4 + 0] = fmaf(x0.x, wa.x, acc0[4 * c4 + 0]); acc0[4 * c4 + 1] = fmaf(x0.x, wa.y, acc0[4 * c4 + 1]);
-        acc0[4 * c4 + 2] = fmaf(x0.x, wa.z, acc0[4 * c4 + 2]); acc0[4 * c4 + 3] = fmaf(x0.x, wa.w, acc0[4 * c4 + 3]);
-        acc1[4 * c4 + 0] = fmaf(x1.x, wa.x, acc1[4 * c4 + 0]); acc1[4 * c4 + 1] = fmaf(x1.x, wa.y, acc1[4 * c4 + 1]);
-        acc1[4 * c4 + 2] = fmaf(x1.x, wa.z, acc1[4 * c4 + 2]); acc1[4 * c4 + 3] = fmaf(x1.x, wa.w, acc1[4 * c4 + 3]);
-        acc0[4 * c4 + 0] = fmaf(x0.y, wb.x, acc0[4 * c4 + 0]); acc0[4 * c4 + 1] = fmaf(x0.y, wb.y, acc0[4 * c4 + 1]);
-        acc0[4 * c4 + 2] = fmaf(x0.y, wb.z, acc0[4 * c4 + 2]); acc0[4 * c4 + 3] = fmaf(x0.y, wb.w, acc0[4 * c4 + 3]);
-        acc1[4 * c4 + 0] = fmaf(x1.y, wb.x, acc1[4 * c4 + 0]); acc1[4 * c4 + 1] = fmaf(x1.y, wb.y, acc1[4 * c4 + 1]);
-        acc1[4 * c4 + 2] = fmaf(x1.y, wb.z, acc1[4 * c4 + 2]); acc1[4 * c4 + 3] = fmaf(x1.y, wb.w, acc1[4 * c4 + 3]);
+        const float2 wa0 = make_float2(wa.x, wa.y), wa1 = make_float2(wa.z, wa.w);
+        const float2 wb0 = make_float2(wb.x, wb.y), wb1 = make_float2(wb.z, wb.w);
+        acc0[2 * c4] = __ffma2_rn(x0a, wa0, acc0[2 * c4]); acc0[2 * c4 + 1] = __ffma2_rn(x0a, wa1, acc0[2 * c4 + 1]);
+        acc1[2 * c4] = __ffma2_rn(x1a, wa0, acc1[2 * c4]); acc1[2 * c4 + 1] = __ffma2_rn(x1a, wa1, acc1[2 * c4 + 1]);
+        acc0[2 * c4] = __ffma2_rn(x0b, wb0, acc0[2 * c4]); acc0[2 * c4 + 1] = __ffma2_rn(x0b, wb1, acc0[2 * c4 + 1]);
+        acc1[2 * c4] = __ffma2_rn(x1b, wb0, acc1[2 * c4]); acc1[2 * c4 + 1] = __ffma2_rn(x1b, wb1, acc1[2 * c4 + 1]);
       }
     }
   }
   // ReLU, optional dump of the stem tensor, then pool
   float pool[2 * kStemCo];   // [max(24) | avg(24)]
 #pragma unroll
-  for (int c = 0; c < kStemCo; ++c) {
-    const float a = fmaxf(acc0[c], 0.f), d = fmaxf(acc1[c], 0.f);
-    acc0[c] = a; acc1[c] = d;
-    pool[c] = fmaxf(a, d);
-    pool[kStemCo + c] = (a + d) * 0.5f;
+  for (int c = 0; c < kStemCo / 2; ++c) {
+    acc0[c].x = fmaxf(acc0[c].x, 0.f); acc0[c].y = fmaxf(acc0[c].y, 0.f);
+    acc1[c].x = fmaxf(acc1[c].x, 0.f); acc1[c].y = fmaxf(acc1[c].y, 0.f);
+    pool[2 * c] = fmaxf(acc0[c].x, acc1[c].x); pool[2 * c + 1] = fmaxf(acc0[c].y, acc1[c].y);
+    pool[kStemCo + 2 * c] = (acc0[c].x + acc1[c].x) * 0.5f; pool[kStemCo + 2 * c + 1] = (acc0[c].y + acc1[c].y) * 0.5f;
   }
   if (stem_out != nullptr) {
     float* so = stem_out + (((size_t)b * p.out_h + h) * p.out_w + 2 * tid) * kStemCo;
 #pragma unroll
-    for (int c = 0; c < kStemCo; ++c) { so[c] = acc0[c]; so[kStemCo + c] = acc1[c]; }
+    for (int c = 0; c < kStemCo / 2; ++c) {
+      so[2 * c] = acc0[c].x; so[2 * c + 1] = acc0[c].y; so[kStemCo + 2 * c] = acc1[c].x; so[kStemCo + 2 * c + 1] = acc1[c].y;
+    }
   }
-  // 1x1 mix 48 -> 24
+  // 1x1 mix 48 -> 24 (weights staged transposed [c][co]: pooled value broadcast x two adjacent outputs per FFMA2)
+  float2 mix[kStemCo / 2];
+#pragma unroll
+  for (int c = 0; c < kStemCo / 2; ++c) mix[c] = make_float2(s_bm[2 * c], s_bm[2 * c + 1]);
+#pragma unroll
+  for (int c = 0; c < 2 * kStemCo; ++c) {
+    const float2 pb = make_float2(pool[c], pool[c]);
+    const float* w = s_wm + c * kStemCo;
+#pragma unroll
+    for (int q = 0; q < kStemCo / 4; ++q) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + 4 * q);
+      mix[2 * q] = __ffma2_rn(pb, make_float2(wv.x, wv.y), mix[2 * q]);
+      mix[2 * q + 1] = __ffma2_rn(pb, make_float2(wv.z, wv.w), mix[2 * q + 1]);
+    }
+  }
   float* o = out + (((size_t)b * p.out_h + h) * (p.out_w / 2) + tid) * kStemCo;
 #pragma unroll
-  for (int co4 = 0; co4 < kStemCo / 4; ++co4) {
-    float r[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int co = 4 * co4 + q;
-      float a = s_bm[co];
-      const float* w = s_wm + co * 2 * kStemCo;
-#pragma unroll
-      for (int c4 = 0; c4 < 2 * kStemCo / 4; ++c4) {
-        const float4 wv = *reinterpret_cast<const float4*>(w + 4 * c4);
-        a = fmaf(pool[4 * c4 + 0], wv.x, a); a = fmaf(pool[4 * c4 + 1], wv.y, a);
-        a = fmaf(pool[4 * c4 + 2], wv.z, a); a = fmaf(pool[4 * c4 + 3], wv.w, a);
-      }
-      r[q] = a;
-    }
-    *reinterpret_cast<float4*>(o + 4 * co4) = make_float4(r[0], r[1], r[2], r[3]);
-  }
+  for (int q = 0; q < kStemCo / 4; ++q)
+    *reinterpret_cast<float4*>(o + 4 * q) = make_float4(mix[2 * q].x, mix[2 * q].y, mix[2 * q + 1].x, mix[2 * q + 1].y);
 }
 
 // =================================================================================================
@@ -306,9 +312,19 @@ se_gate_kernel(const SeArgs a) {
   const float inv = 1.0f / (float)a.HW;
   for (int i = tid; i < kSeChunks * a.C; i += kSeThreads) {
     const int g = i / a.C, c = i - g * a.C;
-    float s = 0.f;
-    if (g < nb) for (int p = 0; p < a.parts; ++p) s += __ldg(a.partial + ((size_t)(b0 + g) * a.parts + p) * a.C + c);
-    s_mean[g][c] = s * inv;
+    // four independent partial accumulators: the loads of a round are in flight together (the serial version paid one L2
+    // round trip per part); the summation order is fixed by the code, hence independent of batch composition
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (g < nb) {
+      const float* pp = a.partial + (size_t)(b0 + g) * a.parts * a.C + c;
+      int p = 0;
+      for (; p + 4 <= a.parts; p += 4) {
+        s0 += __ldg(pp + (size_t)p * a.C); s1 += __ldg(pp + (size_t)(p + 1) * a.C);
+        s2 += __ldg(pp + (size_t)(p + 2) * a.C); s3 += __ldg(pp + (size_t)(p + 3) * a.C);
+      }
+      for (; p < a.parts; ++p) s0 += __ldg(pp + (size_t)p * a.C);
+    }
+    s_mean[g][c] = ((s0 + s1) + (s2 + s3)) * inv;
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
@@ -337,8 +353,16 @@ se_gate_kernel(const SeArgs a) {
     const float bz = __ldg(a.b2 + c);
 #pragma unroll
     for (int g = 0; g < kSeChunks; ++g) acc[g] = bz;
-    for (int j = 0; j < a.Cse; ++j) {
-      const float wv = __ldg(a.w2t + (size_t)j * a.C + c);      // w2t: [Cse][C] (transposed at load) -> coalesced
+    int j = 0;
+    for (; j + 4 <= a.Cse; j += 4) {                               // w2t: [Cse][C] (transposed at load) -> coalesced; 4 loads in flight
+      const float w0 = __ldg(a.w2t + (size_t)j * a.C + c), w1 = __ldg(a.w2t + (size_t)(j + 1) * a.C + c);
+      const float w2 = __ldg(a.w2t + (size_t)(j + 2) * a.C + c), w3 = __ldg(a.w2t + (size_t)(j + 3) * a.C + c);
+#pragma unroll
+      for (int g = 0; g < kSeChunks; ++g)
+        acc[g] = fmaf(s_hidden[g][j + 3], w3, fmaf(s_hidden[g][j + 2], w2, fmaf(s_hidden[g][j + 1], w1, fmaf(s_hidden[g][j], w0, acc[g]))));
+    }
+    for (; j < a.Cse; ++j) {
+      const float wv = __ldg(a.w2t + (size_t)j * a.C + c);
 #pragma unroll
       for (int g = 0; g < kSeChunks; ++g) acc[g] = fmaf(s_hidden[g][j], wv, acc[g]);
     }

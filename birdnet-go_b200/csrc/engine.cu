@@ -64,8 +64,8 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
   if (P.post.out_h != 1) throw unsupported_model("post conv must reduce the mel axis to 1");
   for (const BlockPlan& b : P.blocks)
     if (b.has_se) {
-      const MbGeom mg = mbconv_geometry(b.in_h, b.in_w, b.out_h, b.out_w, b.stride, b.cin);
-      if (b.out_h > kMaxDwParts || mg.tiles_h * mg.tiles_w > kMaxDwParts) throw unsupported_model("squeeze-excite block needs more partial-sum slots than the buffer holds");
+      const MbGeom mg = mbconv_geometry(b.in_h, b.in_w, b.out_h, b.out_w, b.stride, b.cin, b.cexp, 0, kMaxDwParts);
+      if (b.out_h > kMaxDwParts || mg.th == 0) throw unsupported_model("squeeze-excite block needs more partial-sum slots than the buffer holds");
     }
   for (const BlockPlan& b : P.blocks)
     if (b.cin % 4 || b.cexp % 4 || b.cout % 4 || (b.has_se && (b.cexp > 1536 || b.cse > 64))) throw unsupported_model("block channel counts");
@@ -287,18 +287,20 @@ float* Engine::run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream
     const int hw_in = g.in_h * g.in_w, hw_out = g.out_h * g.out_w;
     float* d = scratch(g.dw_tensor, w.d, (size_t)hw_out * g.cexp, n);
     int se_parts = 0;
-    // fused front half: wins on the large-map blocks of the front phase (K <= 72, few slices); the small-map blocks of
-    // the back phase keep the two-kernel chain (their 32-column MMA slices would be pipeline-latency bound: 36 dependent
-    // MMAs per slice at K = 192)
-    const MbGeom mg = mbconv_geometry(g.in_h, g.in_w, g.out_h, g.out_w, g.stride, g.cin);
+    // fused front half: wins on the large-map blocks of the front phase and on the stride-2 block of the back phase; the
+    // stride-1 small-map blocks of the back phase measure the same either way (run 26) and keep the two-kernel chain
+    const int mb_cap = g.has_se ? kMaxDwParts : 0;
+    // the tile search sees the NOMINAL launch size (micro-batch in the front phase, max batch in the back phase), never the
+    // actual one: the geometry fixes the order of the SE partial sums, and results must not depend on batch composition
+    const MbGeom mg = mbconv_geometry(g.in_h, g.in_w, g.out_h, g.out_w, g.stride, g.cin, g.cexp, bi < split_ ? micro_ : max_batch_, mb_cap);
     const bool fits = mg.th > 0 && mg.smem_bytes <= kMbSmemLimit;        // K > 128 does not fit the shared-memory plan
-    if (fused_ && fits && b.expand.tc_img && ((!keep_ && bi < split_) || fused_force_)) {
+    if (fused_ && fits && b.expand.tc_img && ((!keep_ && (bi < split_ || g.stride == 2)) || fused_force_)) {
       // expand + SiLU + depthwise + SiLU + SE sums in one tcgen05 kernel: the expanded tensor is never materialised
       se_parts = mg.tiles_h * mg.tiles_w;
       MbLaunch ml{};
       ml.x = cur; ml.Wimg = b.expand.tc_img; ml.bias_e = b.expand.b; ml.w_dw = b.dw.w; ml.bias_dw = b.dw.b; ml.D = d;
       ml.partial = g.has_se ? w.sep : nullptr;
-      ml.B = n; ml.H = g.in_h; ml.W = g.in_w; ml.Cin = g.cin; ml.C = g.cexp; ml.Ho = g.out_h; ml.Wo = g.out_w; ml.stride = g.stride;
+      ml.B = n; ml.H = g.in_h; ml.W = g.in_w; ml.Cin = g.cin; ml.C = g.cexp; ml.Ho = g.out_h; ml.Wo = g.out_w; ml.stride = g.stride; ml.max_tiles = mb_cap; ml.B_nominal = bi < split_ ? micro_ : max_batch_;
       { ProfScope ps(this, C_PW_EXPAND, s); launch_mbconv_tc(ml, s, lc_); }
     } else {
       float* e = scratch(g.exp_tensor, w.e, (size_t)hw_in * g.cexp, n);
@@ -429,7 +431,7 @@ void Engine::ensure_host_staging() {
   BNB_CUDA(cudaHostAlloc(&h_in_, h_in_bytes_, cudaHostAllocDefault));
   BNB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_out_), h_out_bytes_, cudaHostAllocDefault));
   const int n_micro = ceil_div(max_batch_, micro_);
-  ev_h2d_.resize(n_micro);
+  ev_h2d_.resize(n_micro + 4);      // + the ramp of small micro-batches at the head of a host call
   for (auto& e : ev_h2d_) BNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
@@ -461,9 +463,13 @@ void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, in
   BNB_CUDA(cudaEventRecord(ev_start_, compute_));
   for (int l = 0; l < lanes; ++l) BNB_CUDA(cudaStreamWaitEvent(lanes_[l].stream, ev_start_, 0));   // previous call's back phase is done (stream order)
   // H2D per micro-batch on the copy stream; compute waits per micro-batch
+  // The first micro-batch's copy cannot overlap any compute of this call, so the head of the batch ramps up:
+  // micro/4, micro/4, micro/2, then full micro-batches (chunks are independent: any split gives the same bits).
   int mi = 0;
-  for (int i = 0; i < B; i += micro_, ++mi) {
-    const int n = std::min(micro_, B - i);
+  for (int i = 0; i < B; ++mi) {
+    int n = micro_;
+    if (micro_ >= 16 && B > micro_) n = mi < 2 ? micro_ / 4 : (mi == 2 ? micro_ / 2 : micro_);
+    n = std::min(n, B - i);
     const char* src = static_cast<const char*>(pcm) + (size_t)i * cb;
     if (!src_pinned) {   // callee copies (process.go:280-291): stage through our pinned buffer
       memcpy(static_cast<char*>(h_in_) + (size_t)i * cb, src, (size_t)n * cb);
@@ -474,6 +480,7 @@ void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, in
     Lane& L = lanes_[mi % lanes];
     BNB_CUDA(cudaStreamWaitEvent(L.stream, ev_h2d_[mi], 0));
     run_front(static_cast<const char*>(d_in_) + (size_t)i * cb, fmt, n, ws_mid_ + (size_t)i * mid_sz_, L, L.stream);
+    i += n;
   }
   for (int l = 0; l < lanes; ++l) { BNB_CUDA(cudaEventRecord(lanes_[l].done, lanes_[l].stream)); BNB_CUDA(cudaStreamWaitEvent(compute_, lanes_[l].done, 0)); }
   run_back(ws_mid_, B, d_logits_, d_emb_, compute_);

@@ -67,9 +67,12 @@ struct DifStage {
     for (int i = 0; i < N; i += LEN) {
 #pragma unroll
       for (int j = 0; j < H; ++j) {
+        // complex add / subtract as ONE packed instruction each (sm_100 FADD2 / FFMA2 on the (re, im) register pair;
+        // fma(v, -1, u) rounds once, exactly like u - v)
         const float2 u = a[OFF + i + j], v = a[OFF + i + j + H];
-        a[OFF + i + j] = make_float2(u.x + v.x, u.y + v.y);
-        const float dx = u.x - v.x, dy = u.y - v.y;
+        a[OFF + i + j] = __fadd2_rn(u, v);
+        const float2 d = __ffma2_rn(v, make_float2(-1.f, -1.f), u);
+        const float dx = d.x, dy = d.y;
         const int tk = j * (32 / LEN);          // W_LEN^j = W_32^tk = (cos, -sin)
         if (tk == 0) a[OFF + i + j + H] = make_float2(dx, dy);
         else if (tk == 8) a[OFF + i + j + H] = make_float2(dy, -dx);

@@ -358,17 +358,29 @@ mbconv_tc_kernel(const MbArgs a, const __grid_constant__ CUtensorMap x_map) {
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-MbGeom mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin) {
+MbGeom mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin, int C, int B, int max_tiles) {
   MbGeom g{};
-  int best_tiles = 1 << 30, best_p = 0;
+  // Tile search.  The kernel is bound by the CUDA-core work of its epilogue warps, so candidates are ranked by a small
+  // cost model (cycles, calibrated on clock64 traces of the 12x32 and 24x64 blocks):
+  //   slice = E phase (all 128 TMEM lanes whatever the patch size) + depthwise blocks of 4 outputs on the busiest warp
+  //   tile  = units x slice + patch load/convert bubble;   launch = ceil(B x tiles / SMs) x tile
+  // With B = 0 / C = 0 (unknown) this degenerates to "fewest tiles, then smallest patch".
+  const int n_slices = C > 0 ? (C + kSliceCols - 1) / kSliceCols : kGroups;
+  const int units = (n_slices + kGroups - 1) / kGroups;
+  long long best_cost = -1; int best_tiles = 0;
   for (int th = 1; th <= Ho; ++th)
     for (int tw = 1; tw <= Wo; ++tw) {
       const int ph = (th - 1) * stride + 3, pw = (tw - 1) * stride + 3;
       if (ph * pw > 128 || pw > 256 || ph > 256) continue;
-      const int tiles = ((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
-      if (tiles < best_tiles || (tiles == best_tiles && ph * pw < best_p)) {
-        best_tiles = tiles; best_p = ph * pw;
-        g.th = th; g.tw = tw; g.ph = ph; g.pw = pw; g.tiles_h = (Ho + th - 1) / th; g.tiles_w = (Wo + tw - 1) / tw;
+      const int tiles_h = (Ho + th - 1) / th, tiles_w = (Wo + tw - 1) / tw, tiles = tiles_h * tiles_w;
+      if (max_tiles > 0 && tiles > max_tiles) continue;
+      const int nseg = th >= 4 ? 1 : (th >= 2 ? 2 : 4), segw = (tw + nseg - 1) / nseg;
+      const int blocks = ((th * nseg + 3) / 4) * ((segw + 3) / 4);
+      const long long rounds = B > 0 ? ((long long)B * tiles + kNumSMs - 1) / kNumSMs : tiles;
+      const long long cost = rounds * ((long long)units * (1950 + 700 * blocks) + 3000) * 1024 + ph * pw;
+      if (best_cost < 0 || cost < best_cost || (cost == best_cost && tiles < best_tiles)) {
+        best_cost = cost; best_tiles = tiles;
+        g.th = th; g.tw = tw; g.ph = ph; g.pw = pw; g.tiles_h = tiles_h; g.tiles_w = tiles_w;
       }
     }
   g.k_stages = (Cin + 63) / 64;
@@ -417,7 +429,7 @@ static CUtensorMap encode_x_map(const float* x, int B, int H, int W, int C, int 
 
 void launch_mbconv_tc(const MbLaunch& L, cudaStream_t s, LaunchCounter& lc) {
   static size_t max_set = 0;
-  const MbGeom g = mbconv_geometry(L.H, L.W, L.Ho, L.Wo, L.stride, L.Cin);
+  const MbGeom g = mbconv_geometry(L.H, L.W, L.Ho, L.Wo, L.stride, L.Cin, L.C, L.B_nominal, L.max_tiles);
   if (g.th == 0) throw std::runtime_error("mbconv_tc: no tile geometry fits 128 patch positions");
   if (g.smem_bytes > kMbSmemLimit) throw std::runtime_error("mbconv_tc: shared memory budget exceeded");
   if (g.smem_bytes > max_set) {

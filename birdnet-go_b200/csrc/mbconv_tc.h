@@ -14,7 +14,9 @@ struct MbGeom {
 };
 constexpr size_t kMbSmemLimit = 227 * 1024;
 // tile geometry + shared-memory plan for one block (host logic, also used by the CPU tests)
-MbGeom mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin);
+// C = expanded channels, B = chunks in the launch (both feed the cost model; 0 = unknown), max_tiles = cap on tiles per
+// chunk (SE partial-sum slots; 0 = none)
+MbGeom mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin, int C = 0, int B = 0, int max_tiles = 0);
 
 struct MbArgs {
   const uint8_t* Wimg; const float* bias_e; const float* w_dw; const float* bias_dw; float* D; float* partial;
@@ -33,6 +35,8 @@ struct MbLaunch {
   float* D;                // depthwise output [B][Ho][Wo][C]
   float* partial;          // [B][tiles_h*tiles_w][C] SE sums per tile, or null
   int B, H, W, Cin, C, Ho, Wo, stride;
+  int max_tiles;           // cap on tiles per chunk (size of the SE partial-sum buffer), 0 = none
+  int B_nominal;           // launch size the tile search is run for (fixed per classifier: keeps results batch-invariant)
 };
 void launch_mbconv_tc(const MbLaunch& L, cudaStream_t s, LaunchCounter& lc);
 

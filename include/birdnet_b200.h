@@ -151,7 +151,8 @@ BNB_API int bnb_profile_launches(bnb_classifier* h, float* ms, int32_t* cat, int
 BNB_API int bnb_debug_pw_tiling(int M, int N, int K, int* bn, int* stages, int64_t* smem_bytes);
 /* Tile geometry of the fused expand+depthwise kernel for one block: out10 = {th, tw, ph, pw, tiles_h, tiles_w,
  * k_stages, box_c, a_slots, b_slots} (host logic only). */
-BNB_API int bnb_debug_mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin, int* out10, int64_t* smem_bytes);
+BNB_API int bnb_debug_mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin, int C, int B, int max_tiles, int* out10,
+                                      int64_t* smem_bytes);
 /* JSON description of the layer plan extracted from a .tflite (no GPU needed). Returns bytes
  * written (excluding NUL) or a negative status; `cap` too small -> BNB_ERR_INVALID_ARGUMENT. */
 BNB_API int bnb_describe_model(const void* tflite, size_t tflite_len, char* json, size_t cap);

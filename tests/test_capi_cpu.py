@@ -110,15 +110,16 @@ def test_fused_block_geometry_covers_every_block(lib_path):
     d = json.loads(bb.describe_model(open(bb.DEFAULT_MODEL, "rb").read()))
     for b in d["blocks"]:
         hin, win, cin = b["in"]; ho, wo, _ = b["out"]
-        g = bb.mbconv_geometry(hin, win, ho, wo, b["stride"], cin)
-        assert g["ph"] == (g["th"] - 1) * b["stride"] + 3 and g["pw"] == (g["tw"] - 1) * b["stride"] + 3
-        assert g["ph"] * g["pw"] <= 128
-        # the shared-memory plan fits for every block the engine fuses by default (input map >= 256 pixels, K <= 128);
-        # blocks with K > 128 fall back to the two-kernel chain (engine.cu checks the same limit)
-        if hin * win >= 256 or cin <= 128:
-            assert g["smem_bytes"] <= 227 * 1024, (b, g)
-        assert g["tiles_h"] * g["th"] >= ho and (g["tiles_h"] - 1) * g["th"] < ho
-        assert g["tiles_w"] * g["tw"] >= wo and (g["tiles_w"] - 1) * g["tw"] < wo
-        assert g["k_stages"] == (cin + 63) // 64 and g["a_slots"] >= g["k_stages"]
-        if b["se"]:
-            assert g["tiles_h"] * g["tiles_w"] <= 32
+        for B in (0, 1, 64, 256):                                            # the tile search is cost-model driven: any batch size
+            g = bb.mbconv_geometry(hin, win, ho, wo, b["stride"], cin, b["cexp"], B, 32 if b["se"] else 0)
+            assert g["ph"] == (g["th"] - 1) * b["stride"] + 3 and g["pw"] == (g["tw"] - 1) * b["stride"] + 3
+            assert g["ph"] * g["pw"] <= 128
+            # the shared-memory plan fits for every block the engine fuses by default (input map >= 256 pixels, K <= 128);
+            # blocks with K > 128 fall back to the two-kernel chain (engine.cu checks the same limit)
+            if hin * win >= 256 or cin <= 128:
+                assert g["smem_bytes"] <= 227 * 1024, (b, g)
+            assert g["tiles_h"] * g["th"] >= ho and (g["tiles_h"] - 1) * g["th"] < ho
+            assert g["tiles_w"] * g["tw"] >= wo and (g["tiles_w"] - 1) * g["tw"] < wo
+            assert g["k_stages"] == (cin + 63) // 64 and g["a_slots"] >= g["k_stages"]
+            if b["se"]:
+                assert g["tiles_h"] * g["tiles_w"] <= 32
