@@ -288,6 +288,20 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
       float* crow = a.C + (size_t)m * a.N;
       const float* rrow = a.residual ? a.residual + (size_t)m * a.N : nullptr;
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        // residual rows of this 32-column chunk, in the coalesced pattern of the store loop below: issued before the
+        // TMEM load and the staging pass so the global-memory latency is off the store path (ncu: 16 % of this kernel's
+        // stall samples sat on these loads when they were issued next to the stores)
+        float4 rv[8];
+        if (a.residual != nullptr && a.c_vec4) {
+          const int chunk = lane & 7, ncol = n0 + c0 + 4 * chunk;
+          const bool col_ok = (c0 + 4 * chunk < bn) && (ncol + 4 <= a.N);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int mrow = m_w + 4 * j + (lane >> 3);
+            rv[j] = (col_ok && mrow < a.M) ? __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)mrow * a.N + ncol))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t r[32];
         if (!(a.dbg & 4)) tmem_ld32(taddr + (uint32_t)c0, r);               // columns beyond bn are never stored (clipped / masked)
         else {
@@ -318,10 +332,7 @@ pw_tc_kernel(const PwTcArgs a, const __grid_constant__ CUtensorMap a_map) {
             const int row = 4 * j + (lane >> 3), mrow = m_w + row;
             if (col_ok && mrow < a.M && !(a.dbg & 2)) {
               float4 o = *reinterpret_cast<const float4*>(s_out + row * 128 + ((chunk ^ (row & 7)) << 4));
-              if (a.residual) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)mrow * a.N + ncol));
-                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-              }
+              if (a.residual) { o.x += rv[j].x; o.y += rv[j].y; o.z += rv[j].z; o.w += rv[j].w; }
               *reinterpret_cast<float4*>(a.C + (size_t)mrow * a.N + ncol) = o;
             }
           }
