@@ -312,7 +312,7 @@ float* Engine::run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream
       DwArgs dw{};
       dw.in = e; dw.w = b.dw.w; dw.bias = b.dw.b; dw.out = d; dw.B = n; dw.H = g.in_h; dw.W = g.in_w; dw.C = g.cexp;
       dw.stride = g.stride; dw.Ho = g.out_h; dw.Wo = g.out_w;
-      dw.parts = std::min(kMaxDwParts, dw_parts(n, g.out_h, g.out_w, g.cexp));
+      dw.parts = std::min(kMaxDwParts, dw_parts(n, g.out_h, g.out_w, g.cexp, g.in_w, g.stride));
       dw.partial = g.has_se ? w.sep : nullptr;
       se_parts = dw.parts;
       { ProfScope ps(this, C_DW, s); launch_dw_conv(dw, s, lc_); }

@@ -79,7 +79,7 @@ struct DwArgs {
   int parts;        // pixel partitions per chunk (0 = let the launcher choose via dw_parts)
   int c4_per_cta;   // set by the launcher
 };
-int dw_parts(int B, int Ho, int Wo, int C);
+int dw_parts(int B, int Ho, int Wo, int C, int W, int stride);
 void launch_dw_conv(const DwArgs& a, cudaStream_t s, LaunchCounter& lc);
 
 struct SeArgs {
