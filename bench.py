@@ -381,6 +381,16 @@ def main():
             t = torch.tensor([e2e2_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e2_s = float(t.item())
         e2e2_value = world * B * 2 * n_each / e2e2_s
         clf2.close()
+    # BASELINE config 1 shape: one 3 s chunk through the drop-in bnb_predict (host float32 in, 6522 logits out), median of 30
+    # after 5 warm-ups like cmd/perch-benchmark/main.go:29-33
+    one = np.ascontiguousarray(host[0])
+    lat = []
+    for i in range(35):
+        t0 = time.perf_counter()
+        clf.predict(one)
+        if i >= 5:
+            lat.append(1e3 * (time.perf_counter() - t0))
+    lat_ms = float(np.median(lat))
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -414,6 +424,7 @@ def main():
                          "issued_tflops": 3 * tf, "note": "achieved = algorithmic 1x1-conv FLOPs / time of the tcgen05 kernels (mbconv_tc also does the depthwise conv in that time); every product is issued as 3 fp16 MMAs (hi*hi + lo*hi + hi*lo)",
                          "peak_source": which + " bf16 dense (sustained)", "share_of_step": pw_ms / total_ms if total_ms else None},
             "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items()},
+            "latency_batch1_ms": lat_ms,
             "kernel_ms_note": "per-category CUDA-event sums of one step run on a single lane (no inter-kernel overlap); sum > ms_per_step because the timed region overlaps two lanes",
             "flop_roofline_frac": (value / world) * FLOP_PER_CHUNK / (peak_tf * 1e12),
             "hbm_floor_frac": (value / world) * MIN_HBM_BYTES_PER_CHUNK / (float(peaks["hbm_gbs"]) * 1e9),

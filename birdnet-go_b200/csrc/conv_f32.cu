@@ -295,86 +295,6 @@ dw_conv_kernel(const DwArgs a) {
 }
 
 // =================================================================================================
-// Depthwise 3x3 for SMALL maps (back-phase blocks: 6x16 and 3x8 pixels per chunk).  The row-per-CTA kernel above lets three
-// CTAs read every input row (340 MB of L2 traffic for an 85 MB tensor on the 6x16 blocks).  Here a CTA owns (chunk,
-// channel group, ALL columns); thread (column, channel quad) walks DOWN the map with a 3x3 register window: each input
-// row is fetched from global memory exactly once (one float4 per thread per column it owns, prefetched one row ahead),
-// exchanged with the horizontal neighbours through a double-buffered shared-memory row, and every thread owns one output
-// column of its channels, so the squeeze-excite partial sum (one part per COLUMN) needs no reduction.
-// =================================================================================================
-constexpr int kDwColMaxW = 32, kDwColMaxC4 = 32, kDwColThreads = 256;
-
-template <int STRIDE>
-__global__ void __launch_bounds__(kDwColThreads, 3)
-dw_col_kernel(const DwArgs a) {
-  __shared__ float4 s_row[2][kDwColMaxW + 2][kDwColMaxC4];
-  __shared__ float4 s_w[9][kDwColMaxC4];
-  const int c4g = a.c4_per_cta, c4n = a.C / 4;
-  const int cl = threadIdx.x % c4g, wo = threadIdx.x / c4g;               // blockDim = Wo * c4g
-  const int b = blockIdx.x, c4 = blockIdx.y * c4g + cl;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (wo == 0) {
-#pragma unroll
-    for (int t = 0; t < 9; ++t) s_w[t][cl] = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)t * a.C) + c4);
-    s_row[0][0][cl] = zero; s_row[1][0][cl] = zero;                       // left halo column
-    s_row[0][a.W + 1][cl] = zero; s_row[1][a.W + 1][cl] = zero;           // right halo column
-  }
-  const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias) + c4);
-  const float4* in = reinterpret_cast<const float4*>(a.in) + (size_t)b * a.H * a.W * c4n + c4;
-  float4* outp = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.Ho * a.Wo + wo) * c4n + c4;
-  float4 pre[STRIDE];
-#pragma unroll
-  for (int j = 0; j < STRIDE; ++j) pre[j] = __ldg(in + (size_t)(wo * STRIDE + j) * c4n);          // row 0
-  float4 w0[3] = {zero, zero, zero}, w1[3] = {zero, zero, zero}, w2[3] = {zero, zero, zero};
-  float4 sum = zero;
-  int ho = 0;
-  for (int hi = 0; hi <= a.H; ++hi) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { w0[k] = w1[k]; w1[k] = w2[k]; }
-    if (hi < a.H) {
-      float4 (*row)[kDwColMaxC4] = s_row[hi & 1];
-#pragma unroll
-      for (int j = 0; j < STRIDE; ++j) row[wo * STRIDE + j + 1][cl] = pre[j];
-      if (hi + 1 < a.H) {
-#pragma unroll
-        for (int j = 0; j < STRIDE; ++j) pre[j] = __ldg(in + ((size_t)(hi + 1) * a.W + wo * STRIDE + j) * c4n);
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < 3; ++k) w2[k] = row[wo * STRIDE + k][cl];       // input columns wo*S-1 .. wo*S+1 (halo offset +1)
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) w2[k] = zero;                             // zero row below the image
-    }
-    if (ho < a.Ho && hi - 1 == ho * STRIDE) {                               // window rows hi-2..hi are centred on output row ho
-      float4 acc = bz;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const float4* x = kh == 0 ? w0 : (kh == 1 ? w1 : w2);
-        const float4 wa = s_w[kh * 3 + 0][cl], wb = s_w[kh * 3 + 1][cl], wc = s_w[kh * 3 + 2][cl];
-        acc.x = fmaf(x[0].x, wa.x, acc.x); acc.y = fmaf(x[0].y, wa.y, acc.y); acc.z = fmaf(x[0].z, wa.z, acc.z); acc.w = fmaf(x[0].w, wa.w, acc.w);
-        acc.x = fmaf(x[1].x, wb.x, acc.x); acc.y = fmaf(x[1].y, wb.y, acc.y); acc.z = fmaf(x[1].z, wb.z, acc.z); acc.w = fmaf(x[1].w, wb.w, acc.w);
-        acc.x = fmaf(x[2].x, wc.x, acc.x); acc.y = fmaf(x[2].y, wc.y, acc.y); acc.z = fmaf(x[2].z, wc.z, acc.z); acc.w = fmaf(x[2].w, wc.w, acc.w);
-      }
-      acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w);
-      outp[(size_t)ho * a.Wo * c4n] = acc;
-      sum.x += acc.x; sum.y += acc.y; sum.z += acc.z; sum.w += acc.w;
-      ++ho;
-    }
-  }
-  if (a.partial != nullptr) reinterpret_cast<float4*>(a.partial + ((size_t)b * a.Wo + wo) * a.C)[c4] = sum;
-}
-
-// column kernel applies when the whole width fits one CTA with a useful channel group
-static int dw_col_group(int Ho, int Wo, int W, int C, int stride) {
-  if (Ho > 8 || Wo > kDwColMaxW || W > kDwColMaxW || C % 4 || (stride != 1 && stride != 2) || W != Wo * stride) return 0;
-  const int c4n = C / 4;
-  int best = 0;
-  for (int d = 1; d <= kDwColMaxC4 && d * Wo <= kDwColThreads; ++d) if (c4n % d == 0) best = d;
-  return best >= 8 ? best : 0;
-}
-
-// =================================================================================================
 // Squeeze-excite gate: gate[b][c] = sigmoid(W2 * silu(W1 * mean_hw(x[b]) + b1) + b2).
 // One CTA = kSeChunks chunks so every weight row fetched from L2 is used for several chunks; 32 warps split the
 // hidden units (float4 weight loads, warp-shuffle reductions); the channel means come from the per-row sums the
@@ -496,20 +416,11 @@ void launch_pw_conv(const PwArgs& a, cudaStream_t s, LaunchCounter& lc) {
   BNB_LAUNCH_CHECK(lc);
 }
 
-// SE partial sums per chunk: one per output row, or one per output COLUMN where the small-map column kernel runs
-int dw_parts(int B, int Ho, int Wo, int C, int W, int stride) { (void)B; return dw_col_group(Ho, Wo, W, C, stride) ? Wo : Ho; }
+int dw_parts(int B, int Ho, int Wo, int C, int W, int stride) { (void)B; (void)Wo; (void)C; (void)W; (void)stride; return Ho; }   // one partial sum per output row
 
 void launch_dw_conv(const DwArgs& a0, cudaStream_t s, LaunchCounter& lc) {
   DwArgs a = a0;
   const int c4n = a.C / 4;
-  const int cg = dw_col_group(a.Ho, a.Wo, a.W, a.C, a.stride);
-  if (cg > 0 && (a.partial == nullptr || a.parts == a.Wo)) {
-    a.c4_per_cta = cg;
-    dim3 grid(a.B, c4n / cg);
-    if (a.stride == 1) dw_col_kernel<1><<<grid, a.Wo * cg, 0, s>>>(a); else dw_col_kernel<2><<<grid, a.Wo * cg, 0, s>>>(a);
-    BNB_LAUNCH_CHECK(lc);
-    return;
-  }
   const int groups = (c4n + kDwMaxThreads - 1) / kDwMaxThreads;
   if (c4n % groups) throw std::runtime_error("dw_conv: channel count not divisible into CTA groups");
   a.c4_per_cta = c4n / groups;

@@ -468,7 +468,11 @@ void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, in
   int mi = 0;
   for (int i = 0; i < B; ++mi) {
     int n = micro_;
-    if (micro_ >= 16 && B > micro_) n = mi < 2 ? micro_ / 4 : (mi == 2 ? micro_ / 2 : micro_);
+    static const int ramp = getenv("BNB_RAMP") ? atoi(getenv("BNB_RAMP")) : 1;     // 0 = none, 1 = /4 /4 /2, 2 = /2 (tuning knob)
+    if (micro_ >= 16 && B > micro_) {
+      if (ramp == 1) n = mi < 2 ? micro_ / 4 : (mi == 2 ? micro_ / 2 : micro_);
+      else if (ramp == 2) n = mi == 0 ? micro_ / 2 : micro_;
+    }
     n = std::min(n, B - i);
     const char* src = static_cast<const char*>(pcm) + (size_t)i * cb;
     if (!src_pinned) {   // callee copies (process.go:280-291): stage through our pinned buffer
