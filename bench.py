@@ -10,7 +10,13 @@ One "step" = one pass of the hot path over one batch of 3 s chunks:
           collective is the NCCL all-gather of the per-chunk top-10 (80 B/chunk), inside the timed region.
 `value`  : chunks/s with the PCM already resident in HBM (device pointers through the C ABI).
 `e2e`    : chunks/s through the host-buffer C-ABI call (bnb_analyze_batch): pinned host float32 PCM -> H2D ->
-           kernels -> sigmoid/top-10 -> D2H, every step.
+           kernels -> sigmoid/top-10 -> D2H, every step, one synchronous caller.  Extra keys beside it:
+           `value_int16_pcm` (same call, int16 PCM as the reference's queue holds it), `value_two_callers` (two host
+           threads with a handle each), and top-level `latency_batch1_ms` (bnb_predict on one chunk, median of 30).
+`roofline`: the tcgen05 kernels (fused expand+depthwise and the other 1x1 GEMMs): algorithmic FLOPs / their CUDA-event
+           time measured on ONE lane (no overlap) vs the measured bf16 dense peak; `traffic` from the committed ncu list.
+`cpu_baseline` (N = 1 only): the oracle port on the host cores, bounded sample.  `clocks`: nvidia-smi samples taken
+           during the timed regions.  `gpu_launches`: kernels launched by the library inside the timed region.
 """
 from __future__ import annotations
 
@@ -242,7 +248,14 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner to fd 1 when the communicator comes up (NCCL_DEBUG=VERSION on the boxes): keep
+        # stdout to the one JSON line by pointing fd 1 at stderr while the communicator is created
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            t = torch.zeros(1, device="cuda"); dist.all_reduce(t); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     prec = {"default": bb.PRECISION_DEFAULT, "f32": bb.PRECISION_F32, "f16x3": bb.PRECISION_F16X3}[a.precision]
     clf = bb.B200Classifier(device=local, max_batch=a.batch, micro_batch=a.micro_batch, precision=prec, lanes=a.lanes)
     B = a.batch
