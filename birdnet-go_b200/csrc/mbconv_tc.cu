@@ -5,18 +5,23 @@
 // Replaces the CONV_2D(1x1) -> LOGISTIC/MUL -> [PAD] -> DEPTHWISE_CONV_2D -> LOGISTIC/MUL -> MEAN op groups the
 // reference executes inside TFLite (/root/reference/internal/inference/tflite/classifier.go:107).
 // The expanded tensor (4-8x the block input, 9.4 MB per chunk over the network, the largest HBM/L2 consumer of
-// the unfused chain) is never written: it lives in TMEM, then in a 16 KB shared-memory tile, then dies.
+// the unfused chain) is never written: it lives in TMEM, then in an 18 KB shared-memory tile, then dies.
 //
 // Work decomposition
 //   tile   = one chunk x a TH x TW patch of depthwise OUTPUT pixels; its input patch with halo
 //            PH x PW = ((TH-1)s+3) x ((TW-1)s+3) <= 128 positions = the 128 rows (TMEM lanes) of the expand GEMM.
+//            TH x TW comes from a cost model of the epilogue (mbconv_geometry), evaluated for the classifier's nominal
+//            launch size so that results never depend on the batch composition.
 //   A      = block input [B][H][W][Cin] fp32, fetched by ONE 4-D TMA box per 64 input channels (out-of-image
-//            coordinates arrive as zeros), converted once per tile to fp16 hi/lo 128B-swizzled K-major tiles.
-//   slices = the expanded channels in groups of 32: per slice one small MMA group (N = 32) into one of four
-//            32-column TMEM accumulators; B (pre-split weight image of pw_tc.cu) streams per slice via cp.async.bulk.
-//   epilogue groups (3 x 4 warps) take slices round-robin: TMEM -> +bias -> SiLU -> zero outside the image (padding is
-//            zero in the EXPANDED domain) -> swizzled smem tile [128 pos][32 ch] -> group barrier -> depthwise with
-//            lane = channel (conflict-free LDS), coalesced 128 B stores of the output, SE row sums (deterministic).
+//            coordinates arrive as zeros), converted once per tile by 4 warps to fp16 hi/lo 128B-swizzled K-major tiles.
+//   units  = the expanded channels in groups of 96 = three 32-channel slices: ONE MMA group (N = 96) per unit into one
+//            of two 128-column TMEM buffers (N = 32 MMAs cost the same ~90 cycles each and starved the epilogue);
+//            B (the pre-split weight image of pw_tc.cu) streams per unit via cp.async.bulk, two units in flight.
+//   epilogue groups (3 x 4 warps): group g owns slice g of every unit: tcgen05.ld -> +bias -> SiLU -> zero outside the
+//            image (padding is zero in the EXPANDED domain) -> fp32 smem tile [128 pos][36] (STS.128) -> group barrier
+//            -> depthwise with lane = channel, four outputs per step from a 3 x (3s+3) register window read at immediate
+//            offsets, coalesced 128 B stores of the output, per-tile SE sums in a fixed order (deterministic).
+// How each of these choices was measured into place: profiles/README.md (optimisation log of this kernel).
 #include <stdio.h>
 #include <stdlib.h>
 
