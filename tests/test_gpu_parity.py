@@ -160,6 +160,14 @@ def test_full_size_property_linearity_of_batching(clf):
     assert np.array_equal(y[:8], y[24:])
     z = clf.predict_batch((x[:8] * np.float32(0.5)))
     assert np.abs(_sig(z) - _sig(y[:8])).max() <= SIG_TOL
+    # parity of the synthetic workload itself (broadband noise + a loud tone: the hardest case for the split GEMMs)
+    ref = bo.Oracle(dtype=torch.float64).predict_batch(x[:6])
+    ds = np.abs(_sig(y[:6]) - _sig(ref)).max()
+    print("synthetic chirp+noise: max|dsigmoid|=%.3e max|dlogit|=%.3e" % (ds, np.abs(y[:6] - ref).max()))
+    assert ds <= SIG_TOL
+    top2 = np.sort(ref, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-2                      # top-1 must agree wherever the oracle's margin is not a tie
+    assert (y[:6].argmax(1) == ref.argmax(1))[clear].all()
 
 
 def test_bat_pipeline_backbone_embedding(clf):
