@@ -150,7 +150,8 @@ BNB_API int bnb_profile_launches(bnb_classifier* h, float* ms, int32_t* cat, int
  * bytes (host logic only, no GPU needed; lets the CPU tests check every layer shape fits the 227 KB budget). */
 BNB_API int bnb_debug_pw_tiling(int M, int N, int K, int* bn, int* stages, int64_t* smem_bytes);
 /* Tile geometry of the fused expand+depthwise kernel for one block: out10 = {th, tw, ph, pw, tiles_h, tiles_w,
- * k_stages, box_c, a_slots, b_slots} (host logic only). */
+ * k_stages, box_c, a_slots, b_slots} (host logic only).  C = expanded channels and B = nominal launch size feed the tile
+ * cost model (0 = unknown: fewest tiles); max_tiles caps the tiles per chunk (SE partial-sum slots, 0 = no cap). */
 BNB_API int bnb_debug_mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin, int C, int B, int max_tiles, int* out10,
                                       int64_t* smem_bytes);
 /* JSON description of the layer plan extracted from a .tflite (no GPU needed). Returns bytes
