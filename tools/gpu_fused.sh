@@ -1,2 +1,4 @@
 #!/bin/bash
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-two-callers 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['e2e']['value']))"
