@@ -74,6 +74,11 @@ SYMBOLS = {
     "bnb_describe_model": (C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "bnb_debug_read_tensor": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "bnb_debug_keep_intermediates": (C.c_int, [C.c_void_p, C.c_int]),
+    "bnb_debug_tmem_probe": (C.c_int, [C.c_void_p]),
+    "bnb_debug_mbconv2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnb_debug_pw2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -262,6 +267,43 @@ class B200Classifier:
         buf = np.empty(max_elems, np.float32)
         n = _check(self._lib.bnb_debug_read_tensor(self._h, tensor, _ptr(buf), buf.size))
         return buf[:n].copy()
+
+
+# --- kernel-level test hooks (tests/test_gpu_kernels.py) ------------------------------------------------------------
+def debug_tmem_probe():
+    out = np.zeros(4, np.int32)
+    _check(load_library().bnb_debug_tmem_probe(_ptr(out)))
+    return out
+
+
+def debug_mbconv2(x, w_exp, b_exp, w_dw, b_dw, stride, flags=0):
+    """x [B,H,W,Cin], w_exp [C,Cin], w_dw [9,C] -> (d [B,Ho,Wo,C], se_sum [B,C], info dict) through mbconv2_kernel."""
+    x = np.ascontiguousarray(x, np.float32); w_exp = np.ascontiguousarray(w_exp, np.float32)
+    b_exp = np.ascontiguousarray(b_exp, np.float32); w_dw = np.ascontiguousarray(w_dw, np.float32); b_dw = np.ascontiguousarray(b_dw, np.float32)
+    B, H, W, Cin = x.shape
+    Cc = w_exp.shape[0]
+    Ho, Wo = (H, W) if stride == 1 else (H // 2, W // 2)
+    d = np.zeros((B, Ho, Wo, Cc), np.float32)
+    se = np.zeros((B, Cc), np.float32)
+    info = np.zeros(10, np.int32)
+    _check(load_library().bnb_debug_mbconv2(_ptr(x), B, H, W, Cin, _ptr(w_exp), _ptr(b_exp), _ptr(w_dw), _ptr(b_dw), Cc, stride, flags,
+                                            _ptr(d), _ptr(se), _ptr(info)))
+    keys = ("TH", "TW", "PH", "PW", "n_mma", "k_stages", "a_resident", "a_slots", "b_slots", "smem")
+    return d, se, dict(zip(keys, info.tolist()))
+
+
+def debug_pw2(A, Wt, bias, gate=None, rows_per_chunk=0, residual=None, act=0, planes_out=True):
+    """out [M,N] = act(A' W^T + bias) (+ residual) through pw2_kernel; A [M,K], Wt [N,K]."""
+    A = np.ascontiguousarray(A, np.float32); Wt = np.ascontiguousarray(Wt, np.float32); bias = np.ascontiguousarray(bias, np.float32)
+    M, K = A.shape
+    N = Wt.shape[0]
+    out = np.zeros((M, N), np.float32)
+    info = np.zeros(4, np.int32)
+    g = np.ascontiguousarray(gate, np.float32) if gate is not None else None
+    r = np.ascontiguousarray(residual, np.float32) if residual is not None else None
+    _check(load_library().bnb_debug_pw2(_ptr(A), M, K, _ptr(Wt), _ptr(bias), N, _ptr(g) if g is not None else None, rows_per_chunk,
+                                        _ptr(r) if r is not None else None, act, int(planes_out), _ptr(out), _ptr(info)))
+    return out, dict(zip(("bn", "stages", "b_res", "smem"), info.tolist()))
 
 
 class Result:

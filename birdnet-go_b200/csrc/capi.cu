@@ -55,6 +55,10 @@ int check_batch(const bnb_classifier* h, const void* pcm, int format, int B) {
 
 }  // namespace
 
+namespace bnb {
+int capi_fail(int code, const std::string& msg) { return fail(code, msg); }
+}  // namespace bnb
+
 extern "C" {
 
 int bnb_abi_version(void) { return BNB_ABI_VERSION; }

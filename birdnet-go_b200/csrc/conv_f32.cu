@@ -7,6 +7,7 @@
 // implementation in pw_tc.cu; launch_pw_conv here is their fp32 reference and the fallback for
 // shapes the tensor-core kernel does not take.
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace bnb {
 
@@ -25,7 +26,8 @@ constexpr int kStemCols = 4 * kStemThreads + 8;       // padded input columns co
 constexpr int kStemQ = kStemCols / 4;                 // 130 column quads
 
 __global__ void __launch_bounds__(kStemThreads)
-stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restrict__ stem_out, float* __restrict__ out) {
+stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restrict__ stem_out, float* __restrict__ out,
+                __half* __restrict__ out_h, __half* __restrict__ out_l) {
   __shared__ __align__(16) float s_in[kStemKh][4][kStemQ][2];          // [row][col%4][col/4][ci]
   __shared__ __align__(16) float s_w[kStemKh * kStemKw * 2 * kStemCo];  // [kh][kw][ci][co]
   __shared__ __align__(16) float s_wm[kStemCo * 2 * kStemCo];           // [48][co] (transposed at load)
@@ -108,7 +110,20 @@ stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restr
       mix[2 * q + 1] = __ffma2_rn(pb, make_float2(wv.z, wv.w), mix[2 * q + 1]);
     }
   }
-  float* o = out + (((size_t)b * p.out_h + h) * (p.out_w / 2) + tid) * kStemCo;
+  const size_t opos = (((size_t)b * p.out_h + h) * (p.out_w / 2) + tid) * kStemCo;
+  if (out_h != nullptr) {
+    // F16X3 path: the block input leaves as fp16 hi / lo planes (x ~= hi + lo), ready for the TMA -> tcgen05 patch loads of mbconv2.cu
+    uint32_t hw[kStemCo / 2], lw[kStemCo / 2];
+#pragma unroll
+    for (int c = 0; c < kStemCo / 2; ++c) tc::split2(mix[c].x, mix[c].y, hw[c], lw[c]);
+#pragma unroll
+    for (int q = 0; q < kStemCo / 8; ++q) {
+      *reinterpret_cast<uint4*>(out_h + opos + 8 * q) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+      *reinterpret_cast<uint4*>(out_l + opos + 8 * q) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+    }
+    return;
+  }
+  float* o = out + opos;
 #pragma unroll
   for (int q = 0; q < kStemCo / 4; ++q)
     *reinterpret_cast<float4*>(o + 4 * q) = make_float4(mix[2 * q].x, mix[2 * q].y, mix[2 * q + 1].x, mix[2 * q + 1].y);
@@ -401,12 +416,74 @@ row_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int B, in
   out[idx] = s / (float)rows;
 }
 
+// ---- F16X3 path: the same two helpers on fp16 hi/lo planes -------------------------------------------------------------
+// relu(x*mul+add) + im2col: in planes [B][kh][in_w][cin] -> out planes [B*out_w][kh*kw*cin], 8 channels (16 B per plane) per thread
+__global__ void __launch_bounds__(256)
+post_prep2_kernel(const __half* __restrict__ ih, const __half* __restrict__ il, const float* __restrict__ mul, const float* __restrict__ add,
+                  __half* __restrict__ oh, __half* __restrict__ ol, int B, int kh, int kw, int in_w, int out_w, int cin) {
+  const int c8n = cin / 8, K8 = kh * kw * c8n;
+  const long long total = (long long)B * out_w * K8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k8 = (int)(idx % K8);
+    const long long row = idx / K8;
+    const int wo = (int)(row % out_w), b = (int)(row / out_w);
+    const int c8 = k8 % c8n, t = k8 / c8n, x = t % kw, y = t / kw;
+    const size_t src = ((((size_t)b * kh + y) * in_w + wo + x) * cin) + 8 * c8;
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(ih + src)), l = __ldg(reinterpret_cast<const uint4*>(il + src));
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(mul + 8 * c8)), m1 = __ldg(reinterpret_cast<const float4*>(mul + 8 * c8 + 4));
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(add + 8 * c8)), a1 = __ldg(reinterpret_cast<const float4*>(add + 8 * c8 + 4));
+    const float2 v0 = tc::join2(h.x, l.x), v1 = tc::join2(h.y, l.y), v2 = tc::join2(h.z, l.z), v3 = tc::join2(h.w, l.w);
+    uint4 ho, lo;
+    tc::split2(fmaxf(fmaf(v0.x, m0.x, a0.x), 0.f), fmaxf(fmaf(v0.y, m0.y, a0.y), 0.f), ho.x, lo.x);
+    tc::split2(fmaxf(fmaf(v1.x, m0.z, a0.z), 0.f), fmaxf(fmaf(v1.y, m0.w, a0.w), 0.f), ho.y, lo.y);
+    tc::split2(fmaxf(fmaf(v2.x, m1.x, a1.x), 0.f), fmaxf(fmaf(v2.y, m1.y, a1.y), 0.f), ho.z, lo.z);
+    tc::split2(fmaxf(fmaf(v3.x, m1.z, a1.z), 0.f), fmaxf(fmaf(v3.y, m1.w, a1.w), 0.f), ho.w, lo.w);
+    reinterpret_cast<uint4*>(oh)[idx] = ho;
+    reinterpret_cast<uint4*>(ol)[idx] = lo;
+  }
+}
+
+// mean over `rows` consecutive rows -> fp32 [B][C] (the embedding the API returns) and its hi/lo planes (the FC head's A operand)
+__global__ void __launch_bounds__(256)
+row_mean2_kernel(const float* __restrict__ in, float* __restrict__ out, __half* __restrict__ oh, __half* __restrict__ ol, int B, int rows, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // one thread = two adjacent channels
+  if (idx >= B * (C / 2)) return;
+  const int b = idx / (C / 2), c = 2 * (idx - b * (C / 2));
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(in + ((size_t)b * rows + r) * C + c));
+    s0 += v.x; s1 += v.y;
+  }
+  s0 /= (float)rows; s1 /= (float)rows;
+  *reinterpret_cast<float2*>(out + (size_t)b * C + c) = make_float2(s0, s1);
+  uint32_t h, l;
+  tc::split2(s0, s1, h, l);
+  *reinterpret_cast<uint32_t*>(oh + (size_t)b * C + c) = h;
+  *reinterpret_cast<uint32_t*>(ol + (size_t)b * C + c) = l;
+}
+
 }  // namespace
 
+void launch_post_prep2(const __half* ih, const __half* il, const float* mul, const float* add, __half* oh, __half* ol, int B, int kh, int kw,
+                       int in_w, int out_w, int cin, cudaStream_t s, LaunchCounter& lc) {
+  if (cin % 8) throw std::runtime_error("post_prep2: channel count must be a multiple of 8");
+  const long long total = (long long)B * out_w * kh * kw * (cin / 8);
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  post_prep2_kernel<<<(unsigned)blocks, 256, 0, s>>>(ih, il, mul, add, oh, ol, B, kh, kw, in_w, out_w, cin);
+  BNB_LAUNCH_CHECK(lc);
+}
+
+void launch_row_mean2(const float* in, float* out, __half* oh, __half* ol, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc) {
+  if (C % 2) throw std::runtime_error("row_mean2: channel count must be even");
+  row_mean2_kernel<<<ceil_div(B * (C / 2), 256), 256, 0, s>>>(in, out, oh, ol, B, rows, C);
+  BNB_LAUNCH_CHECK(lc);
+}
+
 void launch_stem_mix(const StemMixDev& p, const float* in, float* stem_out_or_null, float* out, int B,
-                     cudaStream_t s, LaunchCounter& lc) {
+                     cudaStream_t s, LaunchCounter& lc, __half* out_h, __half* out_l) {
   dim3 grid(p.out_h, B);
-  stem_mix_kernel<<<grid, kStemThreads, 0, s>>>(p, in, stem_out_or_null, out);
+  stem_mix_kernel<<<grid, kStemThreads, 0, s>>>(p, in, stem_out_or_null, out, out_h, out_l);
   BNB_LAUNCH_CHECK(lc);
 }
 

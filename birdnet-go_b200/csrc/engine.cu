@@ -8,6 +8,10 @@
 // micro-batch i (compute stream).
 #include "engine.h"
 #include "mbconv_tc.h"
+#include "mbconv2.h"
+#include "pw2.h"
+
+#include <mutex>
 
 #include <math.h>
 #include <string.h>
@@ -15,6 +19,28 @@
 #include <algorithm>
 
 namespace bnb {
+
+void frontend_set_attributes();      // frontend.cu
+void pw_tc_set_attributes();         // pw_tc.cu
+void mbconv_tc_set_attributes();     // mbconv_tc.cu
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: do it once per device ordinal, under a lock
+// (a process may hold classifiers on several GPUs).  The caller has made `device` current.
+namespace {
+std::mutex g_prep_mu;
+bool g_prep_done[64] = {};
+}  // namespace
+// test hooks only: after cudaDeviceReset() the per-device attributes are gone
+void tc_forget_devices() { std::lock_guard<std::mutex> lk(g_prep_mu); for (bool& b : g_prep_done) b = false; }
+
+void tc_prepare_device(int device) {
+  bool* done = g_prep_done;
+  std::lock_guard<std::mutex> lk(g_prep_mu);
+  if (device < 0 || device >= 64) throw std::invalid_argument("device ordinal out of range");
+  if (done[device]) return;
+  frontend_set_attributes(); pw_tc_set_attributes(); mbconv_tc_set_attributes(); mb2_set_attributes(); pw2_set_attributes();
+  done[device] = true;
+}
 
 namespace {
 constexpr double kPi = 3.14159265358979323846;
@@ -42,6 +68,7 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
   BNB_CUDA(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) throw std::runtime_error(std::string("device '") + prop.name + "' is not compute capability 10.x (sm_100a kernels only)");
   device_name_ = std::string("CUDA:") + std::to_string(dev) + " " + prop.name;
+  tc_prepare_device(dev);
   max_batch_ = opts.max_batch > 0 ? opts.max_batch : 256;
   micro_ = opts.micro_batch > 0 ? opts.micro_batch : 32;
   n_lanes_ = opts.reserved[0] > 0 ? std::min<int>(opts.reserved[0], kMaxLanes) : 2;
@@ -50,6 +77,8 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
   if (micro_ > max_batch_) micro_ = max_batch_;
   precision_ = opts.precision == BNB_PRECISION_DEFAULT ? BNB_PRECISION_F16X3 : opts.precision;
   precision_name_ = precision_ == BNB_PRECISION_F16X3 ? "FP16x3(tcgen05)+FP32" : "FP32";
+  // F16X3: round-2 kernels on fp16 hi/lo activation planes (mbconv2.cu + pw2.cu); BNB_V2=0 keeps the round-1 fp32-activation chain
+  v2_ = precision_ == BNB_PRECISION_F16X3 && !(getenv("BNB_V2") && atoi(getenv("BNB_V2")) == 0);
 
   TfModel model = parse_tflite(tflite, len);
   NetPlan P = build_plan(model);
@@ -91,6 +120,7 @@ Engine::~Engine() {
   if (ev_in_) cudaEventDestroy(ev_in_);
   for (void* p : allocs_) cudaFree(p);
   for (auto& kv : keep_bufs_) cudaFree(kv.second.first);
+  for (auto& kv : keep_planes_) { cudaFree(kv.second.first.h); cudaFree(kv.second.first.l); }
   if (h_in_) cudaFreeHost(h_in_);
   if (h_out_) cudaFreeHost(h_out_);
   for (cudaEvent_t e : ev_h2d_) cudaEventDestroy(e);
@@ -209,6 +239,18 @@ void Engine::upload_weights(const NetPlan& P) {
       d.se2 = upconv(t, (size_t)b.cexp * b.cse);
     }
     d.proj = upconv(b.proj, (size_t)b.cout * b.cexp, true);
+    if (v2_) {
+      static const bool sw128_only = getenv("BNB_MB2_SW128") && atoi(getenv("BNB_MB2_SW128")) != 0;
+      d.mb2 = mb2_plan(b.in_h, b.in_w, b.out_h, b.out_w, b.stride, b.cin, b.cexp, !sw128_only);
+      if (!d.mb2.ok) throw unsupported_model("MBConv block geometry does not fit the fused expand+depthwise kernel");
+      if (b.has_se && d.mb2.tiles_h * d.mb2.tiles_w > kMaxDwParts) throw unsupported_model("squeeze-excite block needs more partial-sum slots than the buffer holds");
+      std::vector<uint8_t> img;
+      mb2_prepare_weights(d.mb2, b.expand.w, &img);
+      d.mb2_img = up_t<uint8_t>(img.data(), img.size());
+      std::vector<float> be((size_t)d.mb2.n_units * 128 + 64, 0.f);
+      if (b.expand.b) memcpy(be.data(), b.expand.b, (size_t)b.cexp * sizeof(float));
+      d.mb2_bias = up(be.data(), be.size());
+    }
     blocks_.push_back(d);
   }
   // ---- post + head ------------------------------------------------------------------------------------------
@@ -244,18 +286,43 @@ void Engine::alloc_workspace() {
     w.e = dmalloc(cap_n * ce); w.d = dmalloc(cap_n * cd); w.g = dmalloc(cap_n * cg);
     w.sep = dmalloc(cap_n * kMaxDwParts * cg);   // SE partial sums: <= kMaxDwParts parts per chunk (rows, or fused-kernel tiles)
   };
+  // the same for the plane path: x planes hold block inputs / outputs (pitch = channels rounded up to 8), d planes the depthwise output
+  auto alloc_work2 = [&](Work2& w, size_t cap_n, int lo, int hi, size_t cx) {
+    size_t cd = 0, cg = 0;
+    for (int i = lo; i < hi; ++i) {
+      const BlockPlan& g = blocks_[i].g;
+      cd = std::max(cd, (size_t)g.out_h * g.out_w * g.cexp);
+      cx = std::max(cx, (size_t)g.out_h * g.out_w * plane_pitch(g.cout));
+      cx = std::max(cx, (size_t)g.in_h * g.in_w * plane_pitch(g.cin));
+      cg = std::max(cg, (size_t)g.cexp);
+    }
+    w.x_elems = cx; w.d_elems = cd;
+    w.x0 = alloc_planes(cap_n * cx); w.x1 = alloc_planes(cap_n * cx); w.d = alloc_planes(cap_n * cd);
+    w.g = dmalloc(cap_n * cg);
+    w.sep = dmalloc(cap_n * kMaxDwParts * cg);
+  };
   for (int l = 0; l < n_lanes_; ++l) {
-    alloc_work(lanes_[l].w, mb, 0, split_, (size_t)stem_.out_h * (stem_.out_w / 2) * 24);
+    if (v2_) alloc_work2(lanes_[l].w2, mb, 0, split_, (size_t)stem_.out_h * (stem_.out_w / 2) * 24);
+    else alloc_work(lanes_[l].w, mb, 0, split_, (size_t)stem_.out_h * (stem_.out_w / 2) * 24);
     lanes_[l].partial = dmalloc(mb * kMinMaxParts * 2);
     lanes_[l].fe = dmalloc(mb * fe_.n_mel * fe_.n_frames * 2);
   }
-  alloc_work(work_back_, bb, split_, (int)blocks_.size(), 0);
   const BlockPlan& gs = blocks_[split_ - 1].g;
-  mid_sz_ = (size_t)gs.out_h * gs.out_w * gs.cout;
-  ws_mid_ = dmalloc(bb * mid_sz_);
   ws_pc_ = dmalloc(bb * post_g_.out_w * post_g_.conv.cout);
-  ws_im2col_ = dmalloc(bb * post_g_.out_w * post_g_.conv.kh * post_g_.conv.kw * post_g_.conv.cin);
   ws_emb_ = dmalloc(bb * emb_dim_);
+  const size_t im2col_sz = (size_t)post_g_.out_w * post_g_.conv.kh * post_g_.conv.kw * post_g_.conv.cin;
+  if (v2_) {
+    alloc_work2(work2_back_, bb, split_, (int)blocks_.size(), 0);
+    mid_sz_ = (size_t)gs.out_h * gs.out_w * plane_pitch(gs.cout);
+    mid2_ = alloc_planes(bb * mid_sz_);
+    im2col2_ = alloc_planes(bb * im2col_sz);
+    emb2_ = alloc_planes(bb * emb_dim_);
+  } else {
+    alloc_work(work_back_, bb, split_, (int)blocks_.size(), 0);
+    mid_sz_ = (size_t)gs.out_h * gs.out_w * gs.cout;
+    ws_mid_ = dmalloc(bb * mid_sz_);
+    ws_im2col_ = dmalloc(bb * im2col_sz);
+  }
 }
 
 float* Engine::scratch(int tensor_id, float* normal, size_t per_chunk, int n) {
@@ -268,6 +335,29 @@ float* Engine::scratch(int tensor_id, float* normal, size_t per_chunk, int n) {
     BNB_CUDA(cudaMalloc(&p, need * sizeof(float)));
     keep_bufs_[tensor_id] = {static_cast<float*>(p), need};
     return static_cast<float*>(p);
+  }
+  return it->second.first;
+}
+
+Planes Engine::alloc_planes(size_t elems) {
+  Planes p;
+  void* q = nullptr;
+  BNB_CUDA(cudaMalloc(&q, std::max<size_t>(elems, 8) * sizeof(__half))); allocs_.push_back(q); p.h = static_cast<__half*>(q);
+  BNB_CUDA(cudaMalloc(&q, std::max<size_t>(elems, 8) * sizeof(__half))); allocs_.push_back(q); p.l = static_cast<__half*>(q);
+  return p;
+}
+
+Planes Engine::scratch_planes(int tensor_id, Planes normal, size_t elems_per_chunk, int n) {
+  if (!keep_ || tensor_id < 0) return normal;
+  auto it = keep_planes_.find(tensor_id);
+  const size_t need = elems_per_chunk * (size_t)std::max(micro_, n);
+  if (it == keep_planes_.end() || it->second.second < need) {
+    if (it != keep_planes_.end()) { cudaFree(it->second.first.h); cudaFree(it->second.first.l); }
+    Planes p; void* q = nullptr;
+    BNB_CUDA(cudaMalloc(&q, need * sizeof(__half))); p.h = static_cast<__half*>(q);
+    BNB_CUDA(cudaMalloc(&q, need * sizeof(__half))); p.l = static_cast<__half*>(q);
+    keep_planes_[tensor_id] = {p, need};
+    return p;
   }
   return it->second.first;
 }
@@ -337,8 +427,72 @@ float* Engine::run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream
   return cur;
 }
 
-// frontend -> stem -> blocks [0, split_) for one micro-batch; result (the split-point tensor) goes to `mid`
-void Engine::run_front(const void* d_pcm, int fmt, int n, float* mid, Lane& L, cudaStream_t s) {
+// F16X3 path: every block = mbconv2 (expand + SiLU + depthwise + SiLU + SE sums) -> [SE gate] -> pw2 (project, + gate, + residual).
+// Activations travel as fp16 hi/lo planes; `final_out` (optional) receives the last block's output directly.
+Planes Engine::run_blocks2(int lo, int hi, Planes cur, int n, Work2& w, cudaStream_t s, const Planes* final_out) {
+  Planes nxt_normal = (cur.h == w.x0.h) ? w.x1 : w.x0;
+  for (int bi = lo; bi < hi; ++bi) {
+    const DevBlock& b = blocks_[bi];
+    const BlockPlan& g = b.g;
+    const int hw_out = g.out_h * g.out_w;
+    Planes d = scratch_planes(g.dw_tensor, w.d, (size_t)hw_out * g.cexp, n);
+    Mb2Launch ml{};
+    ml.xh = cur.h; ml.xl = cur.l; ml.x_pitch = plane_pitch(g.cin); ml.Wimg = b.mb2_img; ml.bias_e = b.mb2_bias;
+    ml.w_dw = b.dw.w; ml.bias_dw = b.dw.b; ml.dh = d.h; ml.dl = d.l; ml.partial = g.has_se ? w.sep : nullptr;
+    ml.B = n; ml.H = g.in_h; ml.W = g.in_w; ml.Ho = g.out_h; ml.Wo = g.out_w;
+    { ProfScope ps(this, C_PW_EXPAND, s); launch_mbconv2(b.mb2, ml, s, lc_); }
+    record_planes(g.dw_tensor, d, hw_out, g.cexp, n);
+    float* gate = nullptr;
+    if (g.has_se) {
+      gate = scratch(g.gate_tensor, w.g, (size_t)g.cexp, n);
+      SeArgs se{w.sep, b.se1.w, b.se1.b, b.se2.w, b.se2.b, gate, n, hw_out, g.cexp, g.cse, b.mb2.tiles_h * b.mb2.tiles_w};
+      { ProfScope ps(this, C_SE, s); launch_se_gate(se, s, lc_); }
+      record(g.gate_tensor, gate, (size_t)g.cexp, n);
+    }
+    const int op = plane_pitch(g.cout);
+    Planes out = (final_out && bi == hi - 1 && !keep_) ? *final_out : scratch_planes(g.out_tensor, nxt_normal, (size_t)hw_out * op, n);
+    Pw2Launch pj{};
+    pj.ah = d.h; pj.al = d.l; pj.a_pitch = g.cexp; pj.Wimg = b.proj.tc_img; pj.bias = b.proj.b; pj.gate = gate;
+    if (g.residual) { pj.rh = cur.h; pj.rl = cur.l; pj.r_pitch = plane_pitch(g.cin); }
+    pj.oh = out.h; pj.ol = out.l; pj.o_pitch = op;
+    pj.M = n * hw_out; pj.N = g.cout; pj.K = g.cexp; pj.rows_per_chunk = hw_out; pj.act = ACT_NONE;
+    { ProfScope ps(this, C_PW_PROJECT, s); launch_pw2(b.proj.tc, pj, s, lc_); }
+    record_planes(g.out_tensor, out, hw_out, g.cout, n);
+    if (!keep_) nxt_normal = (cur.h == w.x0.h || cur.h == w.x1.h) ? cur : ((out.h == w.x0.h) ? w.x1 : w.x0);
+    cur = out;
+  }
+  if (final_out && keep_ && hi > lo) {   // debug mode kept private buffers: copy the result to where the caller expects it
+    const BlockPlan& g = blocks_[hi - 1].g;
+    const size_t bytes = (size_t)n * g.out_h * g.out_w * plane_pitch(g.cout) * sizeof(__half);
+    BNB_CUDA(cudaMemcpyAsync(final_out->h, cur.h, bytes, cudaMemcpyDeviceToDevice, s));
+    BNB_CUDA(cudaMemcpyAsync(final_out->l, cur.l, bytes, cudaMemcpyDeviceToDevice, s));
+    cur = *final_out;
+  }
+  return cur;
+}
+
+void Engine::run_back2(Planes mid, int n, float* d_logits, float* d_emb, cudaStream_t s) {
+  Planes cur = run_blocks2(split_, (int)blocks_.size(), mid, n, work2_back_, s, nullptr);
+  const PostPlan& q = post_g_;
+  { ProfScope ps(this, C_POST_CONV, s); launch_post_prep2(cur.h, cur.l, post_mul_, post_add_, im2col2_.h, im2col2_.l, n, q.conv.kh, q.conv.kw, q.in_w, q.out_w, q.conv.cin, s, lc_); }
+  float* pc = scratch(q.conv_tensor, ws_pc_, (size_t)q.out_w * q.conv.cout, n);
+  Pw2Launch pa{};
+  pa.ah = im2col2_.h; pa.al = im2col2_.l; pa.a_pitch = q.conv.kh * q.conv.kw * q.conv.cin; pa.Wimg = post_conv_.tc_img; pa.bias = post_conv_.b;
+  pa.out32 = pc; pa.M = n * q.out_w; pa.N = q.conv.cout; pa.K = pa.a_pitch; pa.rows_per_chunk = q.out_w; pa.act = ACT_RELU;
+  { ProfScope ps(this, C_POST_CONV, s); launch_pw2(post_conv_.tc, pa, s, lc_); }
+  record(q.conv_tensor, pc, (size_t)q.out_w * q.conv.cout, n);
+  float* emb = d_emb ? d_emb : ws_emb_;
+  { ProfScope ps(this, C_ROW_MEAN, s); launch_row_mean2(pc, emb, emb2_.h, emb2_.l, n, q.out_w, q.conv.cout, s, lc_); }
+  record(q.emb_tensor, emb, (size_t)emb_dim_, n);
+  Pw2Launch fa{};
+  fa.ah = emb2_.h; fa.al = emb2_.l; fa.a_pitch = emb_dim_; fa.Wimg = fc_.tc_img; fa.bias = fc_.b; fa.out32 = d_logits;
+  fa.M = n; fa.N = n_species_; fa.K = emb_dim_; fa.rows_per_chunk = 1; fa.act = ACT_NONE;
+  { ProfScope ps(this, C_FC, s); launch_pw2(fc_.tc, fa, s, lc_); }
+  record(logits_tensor_, d_logits, (size_t)n_species_, n);
+}
+
+// frontend -> stem -> blocks [0, split_) for one micro-batch; result (the split-point tensor) goes to slot `chunk0` of the mid buffer
+void Engine::run_front(const void* d_pcm, int fmt, int n, int chunk0, Lane& L, cudaStream_t s) {
   Work& w = L.w;
   float* ws_partial_ = L.partial; float* ws_fe_ = L.fe;
   { ProfScope ps(this, C_MINMAX, s); launch_minmax(d_pcm, fmt, n, n_samples_, ws_partial_, s, lc_); }
@@ -348,16 +502,26 @@ void Engine::run_front(const void* d_pcm, int fmt, int n, float* mid, Lane& L, c
   record(fe_tensor_, fe_out, fe_sz, n);
   const size_t stem_sz = (size_t)stem_.out_h * stem_.out_w * 24, mix_sz = stem_sz / 2;
   float* stem_dump = keep_ ? scratch(stem_tensor_, nullptr, stem_sz, n) : nullptr;
+  if (v2_) {
+    Planes cur = scratch_planes(mix_tensor_, L.w2.x0, mix_sz, n);
+    { ProfScope ps(this, C_STEM_MIX, s); launch_stem_mix(stem_, fe_out, stem_dump, nullptr, n, s, lc_, cur.h, cur.l); }
+    if (stem_dump) record(stem_tensor_, stem_dump, stem_sz, n);
+    record_planes(mix_tensor_, cur, (int)(mix_sz / 24), 24, n);
+    const Planes mid{mid2_.h + (size_t)chunk0 * mid_sz_, mid2_.l + (size_t)chunk0 * mid_sz_};
+    run_blocks2(0, split_, cur, n, L.w2, s, &mid);
+    return;
+  }
   float* cur = scratch(mix_tensor_, w.x0, mix_sz, n);
   { ProfScope ps(this, C_STEM_MIX, s); launch_stem_mix(stem_, fe_out, stem_dump, cur, n, s, lc_); }
   if (stem_dump) record(stem_tensor_, stem_dump, stem_sz, n);
   record(mix_tensor_, cur, mix_sz, n);
   float* out = run_blocks(0, split_, cur, n, w, s);
-  BNB_CUDA(cudaMemcpyAsync(mid, out, (size_t)n * mid_sz_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  BNB_CUDA(cudaMemcpyAsync(ws_mid_ + (size_t)chunk0 * mid_sz_, out, (size_t)n * mid_sz_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
 }
 
 // blocks [split_, end) -> post conv -> embedding -> FC head over `n` chunks at once
 void Engine::run_back(const float* mid, int n, float* d_logits, float* d_emb, cudaStream_t s) {
+  if (v2_) { run_back2(mid2_, n, d_logits, d_emb, s); return; }
   Work& w = work_back_;
   BNB_CUDA(cudaMemcpyAsync(w.x0, mid, (size_t)n * mid_sz_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
   float* cur = run_blocks(split_, (int)blocks_.size(), w.x0, n, w, s);
@@ -398,7 +562,7 @@ void Engine::predict_device(const void* d_pcm, int fmt, int B, float* d_logits, 
     for (int i = 0; i < nb; i += micro_, ++mi) {
       const int n = std::min(micro_, nb - i);
       Lane& L = lanes_[mi % lanes];
-      run_front(static_cast<const char*>(d_pcm) + (size_t)(j + i) * cb, fmt, n, ws_mid_ + (size_t)i * mid_sz_, L, L.stream);
+      run_front(static_cast<const char*>(d_pcm) + (size_t)(j + i) * cb, fmt, n, i, L, L.stream);
     }
     for (int l = 0; l < lanes; ++l) { BNB_CUDA(cudaEventRecord(lanes_[l].done, lanes_[l].stream)); BNB_CUDA(cudaStreamWaitEvent(s, lanes_[l].done, 0)); }
     run_back(ws_mid_, nb, d_logits + (size_t)j * n_species_, d_emb ? d_emb + (size_t)j * emb_dim_ : nullptr, s);
@@ -483,7 +647,7 @@ void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, in
     BNB_CUDA(cudaEventRecord(ev_h2d_[mi], copy_));
     Lane& L = lanes_[mi % lanes];
     BNB_CUDA(cudaStreamWaitEvent(L.stream, ev_h2d_[mi], 0));
-    run_front(static_cast<const char*>(d_in_) + (size_t)i * cb, fmt, n, ws_mid_ + (size_t)i * mid_sz_, L, L.stream);
+    run_front(static_cast<const char*>(d_in_) + (size_t)i * cb, fmt, n, i, L, L.stream);
     i += n;
   }
   for (int l = 0; l < lanes; ++l) { BNB_CUDA(cudaEventRecord(lanes_[l].done, lanes_[l].stream)); BNB_CUDA(cudaStreamWaitEvent(compute_, lanes_[l].done, 0)); }
@@ -542,6 +706,16 @@ long long Engine::read_tensor(int tensor, float* out, size_t cap) {
   const size_t n = it->second.per_chunk * (size_t)it->second.chunks;
   if (n > cap) return BNB_ERR_INVALID_ARGUMENT;
   BNB_CUDA(cudaDeviceSynchronize());
+  if (it->second.h != nullptr) {            // fp16 hi/lo planes: join and drop the pitch padding on the host
+    const TensorView& v = it->second;
+    const size_t pixels = n / (size_t)v.ch, elems = pixels * (size_t)v.pitch;
+    std::vector<__half> h(elems), l(elems);
+    BNB_CUDA(cudaMemcpy(h.data(), v.h, elems * sizeof(__half), cudaMemcpyDeviceToHost));
+    BNB_CUDA(cudaMemcpy(l.data(), v.l, elems * sizeof(__half), cudaMemcpyDeviceToHost));
+    for (size_t p = 0; p < pixels; ++p)
+      for (int c = 0; c < v.ch; ++c) out[p * v.ch + c] = __half2float(h[p * v.pitch + c]) + __half2float(l[p * v.pitch + c]);
+    return (long long)n;
+  }
   BNB_CUDA(cudaMemcpy(out, it->second.ptr, n * sizeof(float), cudaMemcpyDeviceToHost));
   return (long long)n;
 }

@@ -12,6 +12,8 @@
 #include "../../include/birdnet_b200.h"
 #include "kernels.h"
 #include "net_plan.h"
+#include "mbconv2.h"
+#include "pw2.h"
 #include "pw_tc.h"
 
 namespace bnb {
@@ -21,9 +23,18 @@ struct DevConv { const float* w = nullptr; const float* b = nullptr; PwTcLayer t
 struct DevBlock {
   BlockPlan g;          // geometry + tensor ids (host weight pointers are dead after upload)
   DevConv expand, dw, se1, se2, proj;
+  // F16X3 path (mbconv2.cu): tile plan, (unit, stage) weight image, expand bias padded to whole units
+  Mb2Plan mb2; const uint8_t* mb2_img = nullptr; const float* mb2_bias = nullptr;
 };
 
-struct TensorView { const float* ptr = nullptr; size_t per_chunk = 0; int chunks = 0; };
+// fp16 hi / lo planes of one activation tensor (x ~= hi + lo); `pitch` = channels per pixel in memory (multiple of 8)
+struct Planes { __half* h = nullptr; __half* l = nullptr; };
+inline int plane_pitch(int c) { return (c + 7) / 8 * 8; }
+
+struct TensorView {
+  const float* ptr = nullptr; size_t per_chunk = 0; int chunks = 0;
+  const __half* h = nullptr; const __half* l = nullptr; int pitch = 0, ch = 0;     // plane tensors: per_chunk counts pixels * ch
+};
 
 class Engine {
  public:
@@ -62,13 +73,24 @@ class Engine {
   void pw(const PwArgs& a, const DevConv& c, int cat, cudaStream_t s);
   static constexpr int kMaxDwParts = 32;
   struct Work { float *x0 = nullptr, *x1 = nullptr, *e = nullptr, *d = nullptr, *g = nullptr, *sep = nullptr; size_t cap_n = 0; };
+  struct Work2 { Planes x0, x1, d; float* g = nullptr; float* sep = nullptr; size_t x_elems = 0, d_elems = 0; };   // F16X3 plane path
   static constexpr int kMaxLanes = 4;
-  struct Lane { Work w; float* partial = nullptr; float* fe = nullptr; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; };
+  struct Lane { Work w; Work2 w2; float* partial = nullptr; float* fe = nullptr; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; };
   float* run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream_t s);
-  void run_front(const void* d_pcm, int fmt, int n, float* mid, Lane& L, cudaStream_t s);
+  // ---- F16X3 path on fp16 hi/lo planes (mbconv2.cu + pw2.cu) ----
+  Planes run_blocks2(int lo, int hi, Planes cur, int n, Work2& w, cudaStream_t s, const Planes* final_out);
+  void run_back2(Planes mid, int n, float* d_logits, float* d_emb, cudaStream_t s);
+  Planes scratch_planes(int tensor_id, Planes normal, size_t elems_per_chunk, int n);
+  void record_planes(int tensor_id, Planes p, int pixels, int ch, int n) {
+    if (tensor_id >= 0) { TensorView v; v.per_chunk = (size_t)pixels * ch; v.chunks = n; v.h = p.h; v.l = p.l; v.pitch = plane_pitch(ch); v.ch = ch; views_[tensor_id] = v; }
+  }
+  Planes alloc_planes(size_t elems);
+  bool v2_ = false;        // F16X3 precision: every block runs mbconv2 + pw2 on planes
+  Work2 work2_back_; Planes mid2_, im2col2_, emb2_;
+  void run_front(const void* d_pcm, int fmt, int n, int chunk0, Lane& L, cudaStream_t s);   // chunk0: slot of the first chunk in the split-point buffer
   void run_back(const float* mid, int n, float* d_logits, float* d_emb, cudaStream_t s);
   float* scratch(int tensor_id, float* normal, size_t per_chunk, int n);
-  void record(int tensor_id, const float* p, size_t per_chunk, int n) { if (tensor_id >= 0) views_[tensor_id] = TensorView{p, per_chunk, n}; }
+  void record(int tensor_id, const float* p, size_t per_chunk, int n) { if (tensor_id >= 0) { TensorView v; v.ptr = p; v.per_chunk = per_chunk; v.chunks = n; views_[tensor_id] = v; } }
   void upload_weights(const NetPlan& P);
   void alloc_workspace();
   void ensure_host_staging();
@@ -112,6 +134,7 @@ class Engine {
   int split_ = 0;         // first block of the back phase
   size_t mid_sz_ = 0;     // floats per chunk of the split-point tensor
   std::map<int, std::pair<float*, size_t>> keep_bufs_;   // tensor id -> (device buffer, capacity in floats)
+  std::map<int, std::pair<Planes, size_t>> keep_planes_; // tensor id -> (plane pair, capacity in elements)
   std::map<int, TensorView> views_;
 
   // full-batch device buffers for the host path

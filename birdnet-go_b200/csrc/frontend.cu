@@ -365,6 +365,12 @@ minmax_partial_kernel(const void* __restrict__ pcm, int n_samples, float* __rest
 
 size_t frontend_smem_bytes() { return (size_t)kSmemFloats * sizeof(float); }
 
+// per-device attribute (called once per device by tc_prepare_device, engine.cu)
+void frontend_set_attributes() {
+  BNB_CUDA(cudaFuncSetAttribute(frontend_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)frontend_smem_bytes()));
+  BNB_CUDA(cudaFuncSetAttribute(frontend_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)frontend_smem_bytes()));
+}
+
 void launch_minmax(const void* pcm, int fmt, int B, int n_samples, float* partial, cudaStream_t s, LaunchCounter& lc) {
   dim3 grid(kMinMaxParts, B);
   if (fmt == 0) minmax_partial_kernel<0><<<grid, 256, 0, s>>>(pcm, n_samples, partial);
@@ -374,13 +380,7 @@ void launch_minmax(const void* pcm, int fmt, int B, int n_samples, float* partia
 
 void launch_frontend(const FrontendDev& fe, const void* pcm, int fmt, int B, const float* partial, float* out,
                      cudaStream_t s, LaunchCounter& lc) {
-  static bool attr_set = false;
   const size_t smem = frontend_smem_bytes();
-  if (!attr_set) {
-    BNB_CUDA(cudaFuncSetAttribute(frontend_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BNB_CUDA(cudaFuncSetAttribute(frontend_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   dim3 grid(ceil_div(fe.n_frames, kFeFramesPerCta), B);
   if (fmt == 0) frontend_kernel<0><<<grid, kWarps * 32, smem, s>>>(fe, pcm, partial, out);
   else frontend_kernel<1><<<grid, kWarps * 32, smem, s>>>(fe, pcm, partial, out);

@@ -25,6 +25,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <map>
 #include <type_traits>
 #include <vector>
@@ -432,15 +433,14 @@ static CUtensorMap encode_x_map(const float* x, int B, int H, int W, int C, int 
   return m;
 }
 
+void mbconv_tc_set_attributes() {
+  BNB_CUDA(cudaFuncSetAttribute(mbconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMbSmemLimit));
+}
+
 void launch_mbconv_tc(const MbLaunch& L, cudaStream_t s, LaunchCounter& lc) {
-  static size_t max_set = 0;
   const MbGeom g = mbconv_geometry(L.H, L.W, L.Ho, L.Wo, L.stride, L.Cin, L.C, L.B_nominal, L.max_tiles);
   if (g.th == 0) throw std::runtime_error("mbconv_tc: no tile geometry fits 128 patch positions");
   if (g.smem_bytes > kMbSmemLimit) throw std::runtime_error("mbconv_tc: shared memory budget exceeded");
-  if (g.smem_bytes > max_set) {
-    BNB_CUDA(cudaFuncSetAttribute(mbconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    max_set = g.smem_bytes;
-  }
   MbArgs a{};
   a.Wimg = L.Wimg; a.bias_e = L.bias_e; a.w_dw = L.w_dw; a.bias_dw = L.bias_dw; a.D = L.D; a.partial = L.partial;
   a.B = L.B; a.H = L.H; a.W = L.W; a.Cin = L.Cin; a.C = L.C; a.Ho = L.Ho; a.Wo = L.Wo; a.stride = L.stride;
@@ -450,12 +450,12 @@ void launch_mbconv_tc(const MbLaunch& L, cudaStream_t s, LaunchCounter& lc) {
   const CUtensorMap xmap = encode_x_map(L.x, L.B, L.H, L.W, L.Cin, g.box_c, g.pw, g.ph);
   const long long tiles = (long long)L.B * g.tiles_h * g.tiles_w;
   const int grid = tiles < kNumSMs ? (int)tiles : kNumSMs;
-  static long long launch_idx = 0;
+  static std::atomic<long long> launch_idx{0};
   static const char* trace_path = getenv("BNB_MB_TRACE");
   static const long long trace_idx = getenv("BNB_MB_TRACE_IDX") ? atoll(getenv("BNB_MB_TRACE_IDX")) : 0;
   long long* trace = nullptr;
-  if (trace_path && launch_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 8 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 8 * 64 * sizeof(long long), s)); a.trace = trace; }
-  ++launch_idx;
+  const long long my_idx = launch_idx.fetch_add(1);
+  if (trace_path && my_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 8 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 8 * 64 * sizeof(long long), s)); a.trace = trace; }
   mbconv_tc_kernel<<<grid, kThreads, g.smem_bytes, s>>>(a, xmap);
   if (trace) {
     std::vector<long long> h(8 * 64);

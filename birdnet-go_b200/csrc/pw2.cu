@@ -1,0 +1,370 @@
+// pw2.cu — the dense GEMM layers of the conv stack that are NOT fused into mbconv2.cu: every 1x1 project conv
+// (+ optional SE gate on the input, + residual), the final 3x3 VALID conv (after a tiny im2col prep) and the FC head,
+// on the 5th-gen tensor cores (tcgen05.mma kind::f16, fp32 accumulators in TMEM), sm_100a only.
+//
+// Replaces the CONV_2D 1x1 / FULLY_CONNECTED ops the reference executes inside TFLite-XNNPACK
+// (/root/reference/internal/inference/tflite/classifier.go:107).
+//
+// Round-2 design (against pw_tc.cu, VERDICT r1 "weak" #4): the A operand arrives as fp16 hi and lo PLANES written by
+// the producing kernel, so an A tile goes  TMA (2-D box, 128-byte hardware swizzle) -> shared memory -> tcgen05.mma
+// directly: no converter warps, no in-place overwrite, no bar.sync between the load and the MMA.  Three MMAs per
+// K-step keep the fp32-level accuracy:  D += Ahi*Bhi + Alo*Bhi + Ahi*Blo.
+// Layers with a squeeze-excite gate on A still pass through 8 converter warps, but those now rewrite each 16-byte chunk
+// in place thread-privately (hi+lo -> *gate -> hi/lo), with no barrier among them.
+// The epilogue adds bias (+ residual read as planes), and writes either fp32 (post conv, logits) or hi/lo planes (the next
+// block's input) in 64-byte coalesced row segments through a swizzled shared-memory transpose.
+#include "pw2.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "tc_common.cuh"
+#include "tma_host.h"
+
+namespace bnb {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 576;       // 18 warps: 8 epilogue, MMA issuer, loader, 8 converters (gate layers only)
+constexpr int kEpiWarps = 8, kMmaWarp = 8, kLoadWarp = 9, kConvWarp0 = 10, kConvThreads = 256;
+constexpr int kAccCols = 256;
+constexpr uint32_t kABytes = kBM * 128u;      // one fp16 [128][64] plane tile
+
+struct Pw2Args {
+  const uint8_t* Wimg; const float* bias; const float* gate;
+  const __half* rh; const __half* rl; __half* oh; __half* ol; float* out32;
+  int M, N, K, rows_per_chunk, act;
+  int r_pitch, o_pitch;
+  int n_pad, k_pad, n_tiles, bn, stages, b_res, conv, out_vec;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t b_bytes = (uint32_t)a.bn * 128u;
+  const uint32_t stage_bytes = 2 * kABytes + (a.b_res ? 0u : 2 * b_bytes);
+  const uint32_t bres_bytes = a.b_res ? 2 * b_bytes : 0u;
+  const uint32_t bres = base + (uint32_t)a.stages * stage_bytes;
+  const uint32_t stg = bres + bres_bytes;                                  // 8 x 4 KB epilogue staging
+  const uint32_t bars = stg + kEpiWarps * 4096u;
+  auto tma_bar = [&](int s) { return bars + 8u * s; };
+  auto full_bar = [&](int s) { return bars + 8u * (a.stages + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * a.stages + s); };
+  auto tfull_bar = [&](int b) { return bars + 8u * (3 * a.stages + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (3 * a.stages + 2 + b); };
+  const uint32_t bres_bar = bars + 8u * (3 * a.stages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (3 * a.stages + 5));
+  float* s_bias_all = reinterpret_cast<float*>(base_ptr + (bars - base) + ((8u * (3 * a.stages + 5) + 16 + 15) & ~15u));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(tma_bar(s), 1); mbar_init(full_bar(s), kConvThreads); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps * 32); }
+    mbar_init(bres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * kAccCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // N-stationary CTAs (as pw_tc.cu): CTA b keeps n-tile (b % n_tiles) and walks over m-tiles b / n_tiles + i * gridDim.x / n_tiles
+  const int m_tiles = (a.M + kBM - 1) / kBM;
+  const int nt_fix = blockIdx.x % a.n_tiles, mt_first = blockIdx.x / a.n_tiles, mt_step = gridDim.x / a.n_tiles;
+  const int k_stages = (a.K + kBK - 1) / kBK;
+
+  if (warp >= kConvWarp0) {
+    // ============================== converters (gate layers): A <- split((hi + lo) * gate), in place, thread-private ===
+    if (a.conv) {
+      const int pt = threadIdx.x - kConvWarp0 * 32;
+      const int c = pt & 7, r0 = pt >> 3;
+      uint32_t it = 0;
+      for (int mt = mt_first; mt < m_tiles; mt += mt_step) {
+        const int m0 = mt * kBM;
+        for (int ks = 0; ks < k_stages; ++ks, ++it) {
+          const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
+          uint8_t* hi_p = base_ptr + (size_t)s * stage_bytes;
+          uint8_t* lo_p = hi_p + kABytes;
+          const int k = ks * kBK + c * 8;
+          const bool live = k < a.K;                                  // K % 8 == 0 for every gated layer (checked at launch)
+          float4 g0[4], g1[4];
+          if (live) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int m = m0 + r0 + 32 * q;
+              g0[q] = make_float4(1.f, 1.f, 1.f, 1.f); g1[q] = g0[q];
+              if (m < a.M) {
+                const float* gp = a.gate + (size_t)(m / a.rows_per_chunk) * a.K + k;
+                g0[q] = __ldg(reinterpret_cast<const float4*>(gp));
+                g1[q] = __ldg(reinterpret_cast<const float4*>(gp + 4));
+              }
+            }
+          }
+          mbar_wait_relaxed(tma_bar(s), ph);
+          if (live) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int r = r0 + 32 * q;
+              if (m0 + r >= a.M) continue;                            // rows past M arrived as zeros
+              const uint32_t off = swz_off((uint32_t)r, (uint32_t)c, 128u);
+              const uint4 h = *reinterpret_cast<const uint4*>(hi_p + off);
+              const uint4 l = *reinterpret_cast<const uint4*>(lo_p + off);
+              float2 v0 = join2(h.x, l.x), v1 = join2(h.y, l.y), v2 = join2(h.z, l.z), v3 = join2(h.w, l.w);
+              v0.x *= g0[q].x; v0.y *= g0[q].y; v1.x *= g0[q].z; v1.y *= g0[q].w;
+              v2.x *= g1[q].x; v2.y *= g1[q].y; v3.x *= g1[q].z; v3.y *= g1[q].w;
+              uint4 ho, lo;
+              split2(v0.x, v0.y, ho.x, lo.x); split2(v1.x, v1.y, ho.y, lo.y);
+              split2(v2.x, v2.y, ho.z, lo.z); split2(v3.x, v3.y, ho.w, lo.w);
+              *reinterpret_cast<uint4*>(hi_p + off) = ho;
+              *reinterpret_cast<uint4*>(lo_p + off) = lo;
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(full_bar(s));
+        }
+      }
+    }
+  } else if (warp == kLoadWarp) {
+    // ============================== loader: A hi / lo tiles by TMA, weight slabs by bulk copies ========================
+    uint32_t it = 0;
+    const int n0 = nt_fix * a.bn;
+    const uint32_t bn_bytes = (uint32_t)min(a.bn, a.n_pad - n0) * 128u;
+    if (a.b_res && lane == 0) {
+      const uint8_t* wsrc = a.Wimg + (size_t)n0 * 128;
+      mbar_arrive_expect_tx(bres_bar, 2 * bn_bytes);
+      bulk_g2s(bres, wsrc, bn_bytes, bres_bar);
+      bulk_g2s(bres + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, bres_bar);
+    }
+    for (int mt = mt_first; mt < m_tiles; mt += mt_step) {
+      const int m0 = mt * kBM;
+      for (int ks = 0; ks < k_stages; ++ks, ++it) {
+        const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
+        mbar_wait_relaxed(empty_bar(s), ph ^ 1);
+        const uint32_t dst = base + (uint32_t)s * stage_bytes;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(tma_bar(s), 2 * kABytes + (a.b_res ? 0u : 2 * bn_bytes));
+          tma_load_2d(dst, &map_hi, ks * kBK, m0, tma_bar(s));
+          tma_load_2d(dst + kABytes, &map_lo, ks * kBK, m0, tma_bar(s));
+          if (!a.b_res) {
+            const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
+            bulk_g2s(dst + 2 * kABytes, wsrc, bn_bytes, tma_bar(s));
+            bulk_g2s(dst + 2 * kABytes + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, tma_bar(s));
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ============================== MMA issuer ===========================================================================
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      if (a.b_res) mbar_wait(bres_bar, 0);
+      const int n0 = nt_fix * a.bn;
+      const int bn = min(a.bn, a.n_pad - n0);
+      const uint32_t idesc = make_idesc((uint32_t)bn);
+      for (int mt = mt_first; mt < m_tiles; mt += mt_step, ++tcount) {
+        const int buf = tcount & 1;
+        mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccCols;
+        for (int ks = 0; ks < k_stages; ++ks, ++it) {
+          const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
+          mbar_wait(a.conv ? full_bar(s) : tma_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)s * stage_bytes;
+          const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + kABytes);
+          const uint32_t sb = a.b_res ? bres : sa + 2 * kABytes;
+          const uint64_t d_bhi = make_desc(sb), d_blo = make_desc(sb + b_bytes);
+          const int kk_n = min(kBK, a.k_pad - ks * kBK) / 16;
+          for (int kk = 0; kk < kk_n; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);
+            umma(d_tmem, d_ahi + adv, d_bhi + adv, idesc, (ks | kk) != 0);
+            umma(d_tmem, d_alo + adv, d_bhi + adv, idesc, 1);
+            umma(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    // ============================== epilogue (warps 0-7) ================================================================
+    // warp w owns TMEM lanes 32*(w%4).. (rows) and one half of the tile's columns, 32 columns per tcgen05.ld.  A thread
+    // holds one ROW, so the 32x32 fp32 sub-tile goes through a warp-private XOR-swizzled staging buffer and is read back
+    // row-segment-wise: every global access of the store loop covers whole 64-byte (planes) / 128-byte (fp32) row pieces.
+    const int quarter = warp & 3, half = warp >> 2;
+    float* s_bias = s_bias_all + warp * 128;
+    uint8_t* s_out = base_ptr + (stg - base) + warp * 4096;
+    const int n0 = nt_fix * a.bn;
+    const int bn = min(a.bn, a.n_pad - n0);
+    const int c_split = min(bn, ((bn / 2 + 31) / 32) * 32);
+    const int c_begin = half ? c_split : 0, c_end = half ? bn : c_split;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c_begin + lane + 32 * j;
+      s_bias[lane + 32 * j] = (cc < c_end + 16 && n0 + cc < a.n_pad + 16) ? __ldg(a.bias + n0 + cc) : 0.f;
+    }
+    __syncwarp();
+    uint32_t tcount = 0;
+    for (int mt = mt_first; mt < m_tiles; mt += mt_step, ++tcount) {
+      const int buf = tcount & 1;
+      mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
+      tc_fence_after();
+      const int m_w = mt * kBM + quarter * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kAccCols;
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        const int n = n0 + c0;
+        // residual pieces of this 32-column chunk in the read-back pattern (row = 8*j + lane/4, 8 columns per lane), issued early
+        uint4 rvh[4], rvl[4];
+        const int piece = lane & 3, pcol = n + 8 * piece;
+        const bool plane_mode = a.oh != nullptr;
+        if (plane_mode && a.rh != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int mrow = m_w + 8 * j + (lane >> 2);
+            const bool ok = mrow < a.M && pcol < a.r_pitch;
+            rvh[j] = ok ? __ldg(reinterpret_cast<const uint4*>(a.rh + (size_t)mrow * a.r_pitch + pcol)) : make_uint4(0, 0, 0, 0);
+            rvl[j] = ok ? __ldg(reinterpret_cast<const uint4*>(a.rl + (size_t)mrow * a.r_pitch + pcol)) : make_uint4(0, 0, 0, 0);
+          }
+        }
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        __syncwarp();                                      // previous chunk's read-back of s_out is complete
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bz = *reinterpret_cast<const float4*>(s_bias + (c0 - c_begin) + 4 * j4);
+          float4 o;
+          o.x = __uint_as_float(r[4 * j4 + 0]) + bz.x; o.y = __uint_as_float(r[4 * j4 + 1]) + bz.y;
+          o.z = __uint_as_float(r[4 * j4 + 2]) + bz.z; o.w = __uint_as_float(r[4 * j4 + 3]) + bz.w;
+          if (a.act == ACT_SILU) silu4(o.x, o.y, o.z, o.w);
+          else if (a.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          *reinterpret_cast<float4*>(s_out + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o;
+        }
+        __syncwarp();
+        if (plane_mode) {
+          const bool col_ok = pcol < a.o_pitch;            // pad columns of the pitch receive exact zeros (zero weights, zero bias)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int row = 8 * j + (lane >> 2), mrow = m_w + row;
+            if (col_ok && mrow < a.M) {
+              const float4 p0 = *reinterpret_cast<const float4*>(s_out + row * 128 + (((2 * piece) ^ (row & 7)) << 4));
+              const float4 p1 = *reinterpret_cast<const float4*>(s_out + row * 128 + (((2 * piece + 1) ^ (row & 7)) << 4));
+              float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+              if (a.rh != nullptr) {
+                const float2 q0 = join2(rvh[j].x, rvl[j].x), q1 = join2(rvh[j].y, rvl[j].y), q2 = join2(rvh[j].z, rvl[j].z), q3 = join2(rvh[j].w, rvl[j].w);
+                v[0] += q0.x; v[1] += q0.y; v[2] += q1.x; v[3] += q1.y; v[4] += q2.x; v[5] += q2.y; v[6] += q3.x; v[7] += q3.y;
+              }
+              uint4 ho, lo;
+              split2(v[0], v[1], ho.x, lo.x); split2(v[2], v[3], ho.y, lo.y); split2(v[4], v[5], ho.z, lo.z); split2(v[6], v[7], ho.w, lo.w);
+              *reinterpret_cast<uint4*>(a.oh + (size_t)mrow * a.o_pitch + pcol) = ho;
+              *reinterpret_cast<uint4*>(a.ol + (size_t)mrow * a.o_pitch + pcol) = lo;
+            }
+          }
+        } else {
+          const int chunk = lane & 7, ncol = n + 4 * chunk;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = 4 * j + (lane >> 3), mrow = m_w + row;
+            if (mrow < a.M && c0 + 4 * chunk < bn) {
+              const float4 o = *reinterpret_cast<const float4*>(s_out + row * 128 + ((chunk ^ (row & 7)) << 4));
+              float* dst = a.out32 + (size_t)mrow * a.N + ncol;
+              if (a.out_vec == 4) { if (ncol + 4 <= a.N) *reinterpret_cast<float4*>(dst) = o; }
+              else if (a.out_vec == 2) {
+                if (ncol + 2 <= a.N) *reinterpret_cast<float2*>(dst) = make_float2(o.x, o.y);
+                if (ncol + 4 <= a.N) *reinterpret_cast<float2*>(dst + 2) = make_float2(o.z, o.w);
+              } else {
+                if (ncol < a.N) dst[0] = o.x;
+                if (ncol + 1 < a.N) dst[1] = o.y;
+                if (ncol + 2 < a.N) dst[2] = o.z;
+                if (ncol + 3 < a.N) dst[3] = o.w;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kAccCols));
+  }
+}
+
+size_t smem_for(int bn, int stages, bool b_res) {
+  const size_t stage = 2 * (size_t)kABytes + (b_res ? 0 : 2 * (size_t)bn * 128);
+  return (size_t)stages * stage + (b_res ? 2 * (size_t)bn * 128 : 0) + 1024 /*alignment*/ + kEpiWarps * 4096 +
+         ((8 * (3 * stages + 5) + 16 + 15) & ~15) + kEpiWarps * 128 * sizeof(float);
+}
+
+}  // namespace
+
+void pw2_tiling(const PwTcLayer& L, int M, bool conv, int* bn_out, int* stages_out, size_t* smem_out, int* b_res_out) {
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const size_t budget = 227 * 1024;
+  const bool b_res = L.k_stages == 1;
+  int n_tiles = (L.n_pad + 255) / 256;
+  auto bn_of = [&](int nt) { return nt == 1 ? L.n_pad : ((L.n_pad + nt - 1) / nt + 31) / 32 * 32; };
+  int bn = bn_of(n_tiles);
+  while (smem_for(bn, 2, b_res) > budget) { ++n_tiles; bn = bn_of(n_tiles); }
+  if (L.k_stages >= 3) while (bn > 128) { ++n_tiles; bn = bn_of(n_tiles); }
+  while (m_tiles * ((L.n_pad + bn - 1) / bn) < kNumSMs && bn > 64) { ++n_tiles; bn = bn_of(n_tiles); }
+  int stages = conv ? 6 : 5;
+  while (stages > 2 && smem_for(bn, stages, b_res) > budget) --stages;
+  if (stages > L.k_stages * 3 && stages > 2) stages = L.k_stages * 3 > 2 ? L.k_stages * 3 : 2;   // no point in a ring far deeper than the work
+  *bn_out = bn; *stages_out = stages; *smem_out = smem_for(bn, stages, b_res);
+  if (b_res_out) *b_res_out = b_res ? 1 : 0;
+}
+
+void pw2_set_attributes() {
+  BNB_CUDA(cudaFuncSetAttribute(pw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
+void launch_pw2(const PwTcLayer& L, const Pw2Launch& p, cudaStream_t s, LaunchCounter& lc) {
+  if ((p.oh != nullptr) == (p.out32 != nullptr)) throw std::runtime_error("pw2: exactly one of the plane / fp32 outputs must be set");
+  if (p.a_pitch % 8 || (p.oh && (p.o_pitch % 8 || p.o_pitch < p.N)) || (p.rh && p.r_pitch % 8)) throw std::runtime_error("pw2: plane pitches must be multiples of 8");
+  if (p.gate && (p.K % 8 || p.rows_per_chunk <= 0)) throw std::runtime_error("pw2: gated layers need K % 8 == 0");
+  int bn = 0, stages = 0, b_res = 0;
+  size_t smem_bytes = 0;
+  pw2_tiling(L, p.M, p.gate != nullptr, &bn, &stages, &smem_bytes, &b_res);
+  if (smem_bytes > 227 * 1024) throw std::runtime_error("pw2: shared memory budget exceeded");
+  if (smem_bytes < 116 * 1024) smem_bytes = 116 * 1024;          // one CTA per SM (all 512 TMEM columns)
+  Pw2Args a{};
+  a.Wimg = p.Wimg; a.bias = p.bias; a.gate = p.gate; a.rh = p.rh; a.rl = p.rl; a.oh = p.oh; a.ol = p.ol; a.out32 = p.out32;
+  a.M = p.M; a.N = p.N; a.K = p.K; a.rows_per_chunk = p.rows_per_chunk > 0 ? p.rows_per_chunk : 1; a.act = p.act;
+  a.r_pitch = p.r_pitch; a.o_pitch = p.o_pitch;
+  a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.bn = bn; a.n_tiles = (L.n_pad + bn - 1) / bn; a.stages = stages; a.b_res = b_res;
+  a.conv = p.gate != nullptr ? 1 : 0;
+  a.out_vec = (p.N % 4 == 0) ? 4 : ((p.N % 2 == 0) ? 2 : 1);
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int tiles = m_tiles * a.n_tiles;
+  const int grid = tiles < kNumSMs ? tiles : (kNumSMs / a.n_tiles) * a.n_tiles;
+  const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
+  const uint64_t strides[1] = {(uint64_t)p.a_pitch * 2};
+  const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)kBM};
+  const CUtensorMap mh = tma_encode(p.ah, 2, 2, dims, strides, box, 128);
+  const CUtensorMap ml = tma_encode(p.al, 2, 2, dims, strides, box, 128);
+  pw2_kernel<<<grid, kThreads, smem_bytes, s>>>(a, mh, ml);
+  BNB_LAUNCH_CHECK(lc);
+}
+
+}  // namespace bnb

@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -454,18 +455,17 @@ static CUtensorMap encode_map(const float* A, int M, int K, int box_k, int box_r
   return m;
 }
 
+void pw_tc_set_attributes() {
+  BNB_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
 void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, cudaStream_t s, LaunchCounter& lc) {
-  static size_t max_set = 0;
   if (p.a_mode != A_PLAIN || p.a_mul) throw std::runtime_error("pw_tc: A must be a plain [M][K] matrix (run the prep kernel first)");
   int bn = 0, stages = 0;
   size_t smem_bytes = 0;
   int b_res = 0;
   pw_tc_tiling(L, p.M, &bn, &stages, &smem_bytes, &b_res);
   if (smem_bytes > 227 * 1024) throw std::runtime_error("pw_tc: shared memory budget exceeded");
-  if (smem_bytes > max_set) {
-    BNB_CUDA(cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    max_set = smem_bytes;
-  }
   PwTcArgs a{};
   a.A = p.A; a.Wimg = d_image; a.bias = p.bias; a.C = p.C; a.residual = p.residual; a.gate = p.gate;
   a.M = p.M; a.N = p.N; a.K = p.K; a.rows_per_chunk = p.rows_per_chunk; a.act = p.act;
@@ -480,12 +480,12 @@ void launch_pw_tc(const PwTcLayer& L, const PwArgs& p, const uint8_t* d_image, c
   // debug timeline: BNB_PWTC_TRACE=<file> BNB_PWTC_TRACE_IDX=<n-th pw_tc launch of the process>
   static const int dbg_flags = getenv("BNB_PWTC_DBG") ? atoi(getenv("BNB_PWTC_DBG")) : 0;
   a.dbg = dbg_flags;
-  static long long launch_idx = 0;
+  static std::atomic<long long> launch_idx{0};
   static const char* trace_path = getenv("BNB_PWTC_TRACE");
   static const long long trace_idx = getenv("BNB_PWTC_TRACE_IDX") ? atoll(getenv("BNB_PWTC_TRACE_IDX")) : 0;
   long long* trace = nullptr;
-  if (trace_path && launch_idx == trace_idx) { BNB_CUDA(cudaMallocManaged(&trace, 8 * 64 * sizeof(long long))); memset(trace, 0, 8 * 64 * sizeof(long long)); a.trace = trace; }
-  ++launch_idx;
+  const long long my_idx = launch_idx.fetch_add(1);
+  if (trace_path && my_idx == trace_idx) { BNB_CUDA(cudaMallocManaged(&trace, 8 * 64 * sizeof(long long))); memset(trace, 0, 8 * 64 * sizeof(long long)); a.trace = trace; }
   pw_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(a, amap);
   if (trace) {
     BNB_CUDA(cudaStreamSynchronize(s));

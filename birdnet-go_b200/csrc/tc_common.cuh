@@ -133,5 +133,104 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
   lo = *reinterpret_cast<const uint32_t*>(&ll);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// round-2 additions: shared-memory descriptors for the three K-major swizzle modes, narrow TMEM loads at arbitrary
+// column offsets, fp16 hi/lo "plane" helpers, four-way shared-reciprocal SiLU
+// ---------------------------------------------------------------------------------------------------------------
+// K-major swizzled operand tile with `row_bytes` per row (128 / 64 / 32 = SWIZZLE_128B / 64B / 32B); 8-row atoms are
+// contiguous (stride byte offset = 8 * row_bytes).  layout_type: 2 / 4 / 6 (sm_100 encoding).
+__device__ __forceinline__ uint64_t make_desc_rb(uint32_t saddr, uint32_t row_bytes) {
+  const uint64_t lt = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= lt << 61;
+  return d;
+}
+// byte offset of 16-byte chunk `chunk` of row `r` inside a swizzled plane whose base is aligned to 8 * row_bytes
+__host__ __device__ __forceinline__ uint32_t swz_off(uint32_t r, uint32_t chunk, uint32_t row_bytes) {
+  const uint32_t a = r * row_bytes + chunk * 16u;
+  const uint32_t mask = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
+  return a ^ (((a >> 7) & mask) << 4);
+}
+
+#define BNB_TMEM_LD_FN(NAME, XN, OUTS, ...)                                                                     \
+  __device__ __forceinline__ void NAME(uint32_t taddr, uint32_t* r) {                                            \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b." XN ".b32 {" __VA_ARGS__ "}, [%" #OUTS "];" : BNB_TMEM_OUT_##OUTS : "r"(taddr)); \
+  }
+#define BNB_TMEM_OUT_1 "=r"(r[0])
+#define BNB_TMEM_OUT_2 "=r"(r[0]), "=r"(r[1])
+#define BNB_TMEM_OUT_4 "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+#define BNB_TMEM_OUT_8 "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+BNB_TMEM_LD_FN(tmem_ld1, "x1", 1, "%0")
+BNB_TMEM_LD_FN(tmem_ld2, "x2", 2, "%0, %1")
+BNB_TMEM_LD_FN(tmem_ld4, "x4", 4, "%0, %1, %2, %3")
+BNB_TMEM_LD_FN(tmem_ld8, "x8", 8, "%0, %1, %2, %3, %4, %5, %6, %7")
+// N consecutive 32-bit columns starting at ANY column (pieces of 16 / 8 / 4 / 2 / 1)
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
+  if constexpr (N >= 16) { tmem_ld16(taddr, r); tmem_ld_n<N - 16>(taddr + 16, r + 16); }
+  else if constexpr (N >= 8) { tmem_ld8(taddr, r); tmem_ld_n<N - 8>(taddr + 8, r + 8); }
+  else if constexpr (N >= 4) { tmem_ld4(taddr, r); tmem_ld_n<N - 4>(taddr + 4, r + 4); }
+  else if constexpr (N >= 2) { tmem_ld2(taddr, r); tmem_ld_n<N - 2>(taddr + 2, r + 2); }
+  else if constexpr (N == 1) { tmem_ld1(taddr, r); }
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 2-D / 4-D TMA loads are above; instruction descriptor with explicit M (128) and N
+__device__ __forceinline__ uint32_t make_idesc_mn(uint32_t m, uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24); }
+
+// ---- fp16 hi/lo planes: x ~= hi + lo (22 significant bits), each plane a plain fp16 tensor ----------------------------
+// two fp32 values -> packed hi pair and packed lo pair (one packed cvt each; the hi halves are widened back exactly)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 hh = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+__device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  return make_float2(h.x + l.x, h.y + l.y);
+}
+
+// SiLU of four values with ONE reciprocal.  The exponent argument is capped at 30 (x >= -20.8: below that
+// silu(x) is within 2e-8 of the capped value), so every 1 + exp(-x) <= 2^30 + 1 and the product of four stays finite.
+__device__ __forceinline__ float silu_e(float t) {       // 1 + exp(-x) from t = -x * log2(e)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(t, 30.f)));
+  return 1.0f + e;
+}
+__device__ __forceinline__ float rcp_f(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+constexpr float kNegLog2e = -1.4426950408889634f;
+__device__ __forceinline__ void silu4(float& x0, float& x1, float& x2, float& x3) {
+  const float a = silu_e(x0 * kNegLog2e), b = silu_e(x1 * kNegLog2e), c = silu_e(x2 * kNegLog2e), d = silu_e(x3 * kNegLog2e);
+  const float ab = a * b, cd = c * d;
+  const float r = rcp_f(ab * cd);
+  const float rab = r * cd, rcd = r * ab;
+  x0 *= rab * b; x1 *= rab * a; x2 *= rcd * d; x3 *= rcd * c;
+}
+__device__ __forceinline__ void silu2b(float& x0, float& x1) {
+  const float a = silu_e(x0 * kNegLog2e), b = silu_e(x1 * kNegLog2e);
+  const float r = rcp_f(a * b);
+  x0 *= r * b; x1 *= r * a;
+}
+__device__ __forceinline__ void silu1b(float& x0) { x0 *= rcp_f(silu_e(x0 * kNegLog2e)); }
+template <int N>
+__device__ __forceinline__ void silu_n(float* v) {
+#pragma unroll
+  for (int i = 0; i + 4 <= N; i += 4) silu4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  if constexpr (N % 4 == 3) { silu2b(v[N - 3], v[N - 2]); silu1b(v[N - 1]); }
+  if constexpr (N % 4 == 2) silu2b(v[N - 2], v[N - 1]);
+  if constexpr (N % 4 == 1) silu1b(v[N - 1]);
+}
+
 }  // namespace tc
 }  // namespace bnb

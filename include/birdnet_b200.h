@@ -164,6 +164,20 @@ BNB_API int64_t bnb_debug_read_tensor(bnb_classifier* h, int tensor, float* out,
 /* Keep every intermediate alive (no buffer reuse) so bnb_debug_read_tensor can see all of them. */
 BNB_API int bnb_debug_keep_intermediates(bnb_classifier* h, int on);
 
+/* Kernel-level test hooks (tests/test_gpu_kernels.py): run ONE tensor-core kernel of the F16X3 path on host data.
+ * bnb_debug_tmem_probe: out4 = {mismatches of 18-, 17-, 10-column tcgen05.ld at unaligned columns, threads run}.
+ * bnb_debug_mbconv2: fused 1x1 expand + SiLU + 3x3 depthwise + SiLU of one MBConv block; x [B,H,W,Cin], w_exp [C,Cin],
+ *   w_dw [9,C] -> d_out [B,Ho,Wo,C] (+ se_sum [B,C] = per-channel sums over pixels, may be NULL); flags bit 0 forbids the
+ *   32/64-byte swizzle stage shapes; info10 = {TH, TW, PH, PW, n_mma, k_stages, a_resident, a_slots, b_slots, smem}.
+ * bnb_debug_pw2: out [M,N] = act(A' W^T + bias) (+ residual), A' = A (* gate[m / rows_per_chunk] when gate != NULL);
+ *   planes_out selects the hi/lo-plane epilogue (joined on the host) or the fp32 one; info4 = {bn, stages, b_res, smem}. */
+BNB_API int bnb_debug_tmem_probe(int32_t* out4);
+BNB_API int bnb_debug_mbconv2(const float* x, int B, int H, int W, int Cin, const float* w_exp, const float* b_exp,
+                              const float* w_dw, const float* b_dw, int C, int stride, int flags, float* d_out, float* se_sum,
+                              int32_t* info10);
+BNB_API int bnb_debug_pw2(const float* A, int M, int K, const float* W, const float* bias, int N, const float* gate,
+                          int rows_per_chunk, const float* residual, int act, int planes_out, float* out, int32_t* info4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,32 @@ def test_intermediate_tensors_match_oracle(lib_path, audio):
     c.close()
 
 
+def test_intermediate_tensors_of_the_tensor_core_path(lib_path, audio):
+    """The production F16X3 path (fp16 hi/lo planes, mbconv2 + pw2 kernels): depthwise outputs, SE gates and block outputs of
+    all 16 blocks + the embedding vs the float64 oracle."""
+    c = bb.B200Classifier(max_batch=4, micro_batch=4, precision=bb.PRECISION_F16X3)
+    c.keep_intermediates(True)
+    chunks = np.stack([audio["tawnyowl"][:144000], audio["soundscape"][:144000]])
+    plan = json.loads(bb.describe_model(open(bb.DEFAULT_MODEL, "rb").read()))
+    ids = [plan["frontend_out_tensor"], plan["mix"]["out_tensor"]]
+    for b in plan["blocks"]:
+        ids += [b["tensors"]["dw"], b["tensors"]["out"]] + ([b["tensors"]["gate"]] if b["tensors"].get("gate", -1) >= 0 else [])
+    ids += [545]
+    ref = bo.Oracle(dtype=torch.float64).run(chunks, fetch=tuple(ids), batch=2)
+    got_logits = c.predict_batch(chunks)
+    worst = 0.0
+    for t in ids:
+        r = np.asarray(ref[t], np.float64).reshape(2, -1)
+        g = c.read_tensor(t).reshape(2, -1)
+        rel = np.abs(g - r).max() / np.abs(r).max()
+        worst = max(worst, rel)
+        assert rel < 1.5e-3, (t, rel)
+    print("worst relative error over %d tensors: %.2e" % (len(ids), worst))
+    c.keep_intermediates(False)
+    assert np.array_equal(c.predict_batch(chunks), got_logits)          # keep mode and production mode: same bits
+    c.close()
+
+
 def test_full_size_property_linearity_of_batching(clf):
     """BASELINE config 3 shape (synthetic pink noise + chirp): duplicated chunks give identical rows, and
     gain-invariance of the min/max normalisation: logits(x) == logits(0.5 x) up to fp32 rounding."""
