@@ -29,7 +29,7 @@ DEFAULT_TOP_K = 10   # internal/classifier/tracing.go:59
 
 class Options(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("max_batch", C.c_int32), ("micro_batch", C.c_int32),
-                ("precision", C.c_int32), ("use_graphs", C.c_int32), ("reserved", C.c_int32 * 9)]
+                ("precision", C.c_int32), ("use_graphs", C.c_int32), ("lanes", C.c_int32), ("reserved", C.c_int32 * 8)]
 
 
 class B200Error(RuntimeError):
@@ -151,7 +151,7 @@ class B200Classifier:
         o = Options()
         o.struct_size = C.sizeof(Options)
         o.device, o.max_batch, o.micro_batch, o.precision, o.use_graphs = device, max_batch, micro_batch, precision, use_graphs
-        o.reserved[0] = lanes      # concurrent front-phase streams (0 = library default)
+        o.lanes = lanes            # concurrent front-phase streams (0 = library default)
         h = C.c_void_p()
         _check(lib.bnb_classifier_create(model_data, len(model_data), C.byref(o), C.byref(h)))
         self._lib, self._h = lib, h
@@ -201,11 +201,22 @@ class B200Classifier:
             return PCM_F32
         raise TypeError("pcm must be float32 or int16")
 
-    def predict_batch(self, pcm, with_embeddings=False, out=None):
-        """pcm [B,144000] float32|int16 (host) -> logits [B,6522] (and embeddings [B,1024])."""
+    def _check_batch(self, pcm, k=None):
+        """Shared argument validation of the batch entry points: the C side copies B*n_samples samples out of the buffer,
+        so a wrong-width or 1-D array must be rejected here with the reference's "input size mismatch" error
+        (tflite/classifier.go:102-104)."""
+        if self._h is None:
+            raise B200Error(ERR_CLOSED, "classifier is closed")
         pcm = np.ascontiguousarray(pcm)
         if pcm.ndim != 2 or pcm.shape[1] != self.n_samples:
             raise B200Error(ERR_INVALID_ARGUMENT, "input size mismatch: expected [B,%d], got %s" % (self.n_samples, pcm.shape))
+        if k is not None and not (0 < int(k) <= 64):
+            raise B200Error(ERR_INVALID_ARGUMENT, "k must be in 1..64, got %r" % (k,))
+        return pcm
+
+    def predict_batch(self, pcm, with_embeddings=False, out=None):
+        """pcm [B,144000] float32|int16 (host) -> logits [B,6522] (and embeddings [B,1024])."""
+        pcm = self._check_batch(pcm)
         B = pcm.shape[0]
         logits = out if out is not None else np.empty((B, self.n_species), np.float32)
         emb = np.empty((B, self.emb_dim), np.float32) if with_embeddings else None
@@ -213,7 +224,7 @@ class B200Classifier:
         return (logits, emb) if with_embeddings else logits
 
     def analyze_batch(self, pcm, sensitivity=1.0, k=DEFAULT_TOP_K, want_logits=False):
-        pcm = np.ascontiguousarray(pcm)
+        pcm = self._check_batch(pcm, k)
         B = pcm.shape[0]
         idx = np.empty((B, k), np.int32)
         conf = np.empty((B, k), np.float32)

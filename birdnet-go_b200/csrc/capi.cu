@@ -4,6 +4,7 @@
 // (/root/reference/internal/inference/openvino/backend_openvino.go:462-470), never abort.
 #include <mutex>
 #include <new>
+#include <set>
 
 #include "engine.h"
 #include "mbconv_tc.h"
@@ -39,11 +40,28 @@ int guarded(F&& f) {
   } catch (...) { return fail(BNB_ERR_INTERNAL, "unknown exception"); }
 }
 
+// Registry of live handles: a destroyed handle is recognised WITHOUT dereferencing it (bnb_classifier_destroy frees the
+// object), so use-after-Close reports BNB_ERR_CLOSED like the reference's ErrSessionClosed (onnx.go:89-91) instead of
+// reading freed memory.  (A later create may reuse the address; such a handle is then simply live again.)
+std::mutex g_live_mu;
+std::set<const bnb_classifier*> g_live;
+
 int check_handle(const bnb_classifier* h) {
   if (!h) return fail(BNB_ERR_INVALID_ARGUMENT, "classifier handle is NULL");
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    if (!g_live.count(h)) return fail(BNB_ERR_CLOSED, "classifier is closed");
+  }
   if (h->closed || !h->eng) return fail(BNB_ERR_CLOSED, "classifier is closed");
   return BNB_OK;
 }
+
+// every entry point leaves the calling thread's current CUDA device as it found it
+struct DeviceRestore {
+  int prev = -1;
+  DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+  ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int check_batch(const bnb_classifier* h, const void* pcm, int format, int B) {
   if (int rc = check_handle(h)) return rc;
@@ -103,14 +121,23 @@ int bnb_classifier_create(const void* tflite, size_t tflite_len, const bnb_optio
   if ((rc = bnb_init()) != BNB_OK) return rc;
   bnb_classifier* h = new (std::nothrow) bnb_classifier();
   if (!h) return fail(BNB_ERR_OUT_OF_MEMORY, "host allocation failed");
-  rc = guarded([&] { h->eng = new Engine(tflite, tflite_len, o); });
+  {
+    DeviceRestore dr;
+    rc = guarded([&] { h->eng = new Engine(tflite, tflite_len, o); });
+  }
   if (rc != BNB_OK) { delete h; return rc; }
+  { std::lock_guard<std::mutex> lk(g_live_mu); g_live.insert(h); }
   *out = h;
   return BNB_OK;
 }
 
 void bnb_classifier_destroy(bnb_classifier* h) {
   if (!h) return;
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    if (!g_live.erase(h)) return;                 // already destroyed: Close() is idempotent (tflite/classifier.go:129-134)
+  }
+  DeviceRestore dr;
   try { delete h->eng; } catch (...) {}
   h->eng = nullptr; h->closed = true;
   delete h;
@@ -132,6 +159,7 @@ int bnb_predict_with_embeddings(bnb_classifier* h, const float* samples, size_t 
   if (!samples || !logits) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL samples/logits pointer");
   if (n_samples != (size_t)h->eng->n_samples())
     return fail(BNB_ERR_INVALID_ARGUMENT, "input size mismatch: expected " + std::to_string(h->eng->n_samples()) + " samples, got " + std::to_string(n_samples));
+  DeviceRestore dr;
   return guarded([&] { h->eng->predict_host(samples, BNB_PCM_F32, 1, logits, embeddings); });
 }
 
@@ -140,6 +168,7 @@ int bnb_predict_batch(bnb_classifier* h, const void* pcm, int format, int B, flo
   if (!logits) return fail(BNB_ERR_INVALID_ARGUMENT, "logits pointer is NULL");
   if (B > h->eng->max_batch()) return fail(BNB_ERR_INVALID_ARGUMENT, "batch exceeds max_batch");
   if (B == 0) return BNB_OK;
+  DeviceRestore dr;
   return guarded([&] { h->eng->predict_host(pcm, format, B, logits, embeddings); });
 }
 
@@ -149,6 +178,7 @@ int bnb_analyze_batch(bnb_classifier* h, const void* pcm, int format, int B, flo
   if (!idx || !conf || k <= 0) return fail(BNB_ERR_INVALID_ARGUMENT, "idx/conf NULL or k <= 0");
   if (B > h->eng->max_batch()) return fail(BNB_ERR_INVALID_ARGUMENT, "batch exceeds max_batch");
   if (B == 0) return BNB_OK;
+  DeviceRestore dr;
   return guarded([&] { h->eng->analyze_host(pcm, format, B, sensitivity, k, idx, conf, logits_or_null); });
 }
 
@@ -156,6 +186,7 @@ int bnb_predict_batch_device(bnb_classifier* h, const void* d_pcm, int format, i
   if (int rc = check_batch(h, d_pcm, format, B)) return rc;
   if (!d_logits) return fail(BNB_ERR_INVALID_ARGUMENT, "logits pointer is NULL");
   if (B == 0) return BNB_OK;
+  DeviceRestore dr;
   return guarded([&] { h->eng->predict_device(d_pcm, format, B, d_logits, d_embeddings, static_cast<cudaStream_t>(stream)); });
 }
 
@@ -165,6 +196,7 @@ int bnb_analyze_batch_device(bnb_classifier* h, const void* d_pcm, int format, i
   if (!d_idx || !d_conf || k <= 0) return fail(BNB_ERR_INVALID_ARGUMENT, "idx/conf NULL or k <= 0");
   if (!d_logits_or_null && B > h->eng->max_batch()) return fail(BNB_ERR_INVALID_ARGUMENT, "batch exceeds max_batch (pass a logits buffer for larger batches)");
   if (B == 0) return BNB_OK;
+  DeviceRestore dr;
   return guarded([&] { h->eng->analyze_device(d_pcm, format, B, sensitivity, k, d_idx, d_conf, d_logits_or_null, static_cast<cudaStream_t>(stream)); });
 }
 

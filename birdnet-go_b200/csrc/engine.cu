@@ -60,6 +60,11 @@ const T* Engine::up_t(const T* host, size_t n) {
 }
 
 Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
+  // a constructor that throws never runs the destructor: release streams / events / device memory here
+  try { init(tflite, len, opts); } catch (...) { release(); throw; }
+}
+
+void Engine::init(const void* tflite, size_t len, const bnb_options& opts) {
   int dev = opts.device;
   if (dev < 0) BNB_CUDA(cudaGetDevice(&dev));
   BNB_CUDA(cudaSetDevice(dev));
@@ -71,7 +76,7 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
   tc_prepare_device(dev);
   max_batch_ = opts.max_batch > 0 ? opts.max_batch : 256;
   micro_ = opts.micro_batch > 0 ? opts.micro_batch : 32;
-  n_lanes_ = opts.reserved[0] > 0 ? std::min<int>(opts.reserved[0], kMaxLanes) : 2;
+  n_lanes_ = opts.lanes > 0 ? std::min<int>(opts.lanes, kMaxLanes) : 2;
   fused_ = !(getenv("BNB_FUSED") && atoi(getenv("BNB_FUSED")) == 0);
   fused_force_ = getenv("BNB_FUSED") && atoi(getenv("BNB_FUSED")) == 2;   // also in keep-intermediates mode (debug)
   if (micro_ > max_batch_) micro_ = max_batch_;
@@ -113,7 +118,9 @@ Engine::Engine(const void* tflite, size_t len, const bnb_options& opts) {
   alloc_workspace();
 }
 
-Engine::~Engine() {
+Engine::~Engine() { release(); }
+
+void Engine::release() noexcept {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   for (int i = 0; i < n_lanes_; ++i) { if (lanes_[i].stream) cudaStreamDestroy(lanes_[i].stream); if (lanes_[i].done) cudaEventDestroy(lanes_[i].done); }

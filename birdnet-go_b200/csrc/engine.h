@@ -40,6 +40,8 @@ class Engine {
  public:
   Engine(const void* tflite, size_t len, const bnb_options& opts);
   ~Engine();
+  void init(const void* tflite, size_t len, const bnb_options& opts);
+  void release() noexcept;
   Engine(const Engine&) = delete;
   Engine& operator=(const Engine&) = delete;
 

@@ -134,7 +134,7 @@ struct Matcher {
     ConvW c;
     if (op.in.size() < 2 || !is_const(op.in[1])) fail(std::string(what) + ": weights not constant");
     const TfTensor& w = m.tensors[op.in[1]];
-    if (w.type != TT_F32 || w.shape.size() != 4) fail(std::string(what) + ": weights must be 4-D float32");
+    if (w.type != TT_F32 || w.shape.size() != 4 || !w.has_bytes(4)) fail(std::string(what) + ": weights must be a 4-D float32 constant of matching size");
     c.w = w.f32(); c.w_tensor = op.in[1];
     c.kh = w.shape[1]; c.kw = w.shape[2];
     if (depthwise) { if (w.shape[0] != 1) fail(std::string(what) + ": depth multiplier"); c.cin = c.cout = w.shape[3]; }
@@ -166,7 +166,7 @@ inline NetPlan build_plan(const TfModel& m) {
     const TfOp& fc = M.prod(m.outputs[0], OP_FULLY_CONNECTED, "head");
     if (fc.act != 0) M.fail("head: fused activation");
     const TfTensor& w = m.tensors[fc.in[1]];
-    if (!w.is_const() || w.shape.size() != 2 || w.type != TT_F32) M.fail("head: weights");
+    if (fc.in.size() < 2 || !w.is_const() || w.shape.size() != 2 || w.type != TT_F32 || !w.has_bytes(4)) M.fail("head: weights");
     P.head.fc.w = w.f32(); P.head.fc.w_tensor = fc.in[1];
     P.head.fc.cout = w.shape[0]; P.head.fc.cin = w.shape[1];
     if (fc.in.size() > 2 && fc.in[2] >= 0) { P.head.fc.b = M.cf32(fc.in[2], (size_t)w.shape[0], "head bias"); P.head.fc.b_tensor = fc.in[2]; }
@@ -243,7 +243,7 @@ inline NetPlan build_plan(const TfModel& m) {
       if (M.prod_code(e) == OP_PAD) {
         const TfOp& pad = m.ops[M.producer[e]];
         const TfTensor& pc = m.tensors[pad.in[1]];
-        if (!pc.is_const() || pc.numel() != 8) M.fail("pad: constant");
+        if (!pc.is_const() || pc.numel() != 8 || pc.type != TT_I32 || !pc.has_bytes(4)) M.fail("pad: constant");
         const int32_t* p = pc.i32();
         if (!(p[0] == 0 && p[1] == 0 && p[2] == 1 && p[3] == 1 && p[4] == 1 && p[5] == 1 && p[6] == 0 && p[7] == 0)) M.fail("pad: expected 1 pixel on H and W");
         explicit_pad = true; e = pad.in[0];
@@ -327,14 +327,14 @@ inline NetPlan build_plan(const TfModel& m) {
       int y = M.skip_reshape(sq.in[0]);
       const TfOp& fc = M.prod(y, OP_FULLY_CONNECTED, "mel projection");
       const TfTensor& mw = m.tensors[fc.in[1]];
-      if (!mw.is_const() || mw.shape.size() != 2 || mw.type != TT_F32 || (fc.in.size() > 2 && fc.in[2] >= 0)) M.fail("mel projection: expected bias-free constant matrix");
+      if (!mw.is_const() || mw.shape.size() != 2 || mw.type != TT_F32 || !mw.has_bytes(4) || (fc.in.size() > 2 && fc.in[2] >= 0)) M.fail("mel projection: expected bias-free constant matrix");
       S.n_mel = mw.shape[0]; S.n_bins = mw.shape[1]; S.mel = mw.f32();
       int z = M.skip_reshape(fc.in[0]);
       const TfOp& cast = M.prod(z, OP_CAST, "complex->real cast");
       int r = M.skip_reshape(cast.in[0]);
       const TfOp& fft = M.prod(r, OP_RFFT2D, "rfft");
       const TfTensor& fl = m.tensors[fft.in[1]];
-      if (!fl.is_const() || fl.numel() != 2 || fl.i32()[0] != 1) M.fail("rfft: fft_length");
+      if (!fl.is_const() || fl.numel() != 2 || fl.type != TT_I32 || !fl.has_bytes(4) || fl.i32()[0] != 1) M.fail("rfft: fft_length");
       S.frame_len = fl.i32()[1];
       if (S.n_bins != S.frame_len / 2 + 1) M.fail("rfft: bin count vs mel matrix");
       int w = M.skip_reshape(fft.in[0]);
@@ -349,13 +349,13 @@ inline NetPlan build_plan(const TfModel& m) {
       const TfOp& idx_add = M.prod(gat.in[1], OP_ADD, "frame index");
       int ia, ic; M.split_const(idx_add, &ia, &ic, "frame index");
       const TfTensor& offs = m.tensors[ic];
-      if (offs.type != TT_I32 || group <= 0 || (int)offs.numel() * group != S.frame_len) M.fail("framing: offsets vs frame length");
+      if (offs.type != TT_I32 || !offs.has_bytes(4) || group <= 0 || (int)offs.numel() * group != S.frame_len) M.fail("framing: offsets vs frame length");
       for (size_t i = 0; i < offs.numel(); ++i) if (offs.i32()[i] != (int)i) M.fail("framing: offsets not contiguous");
       int im = M.skip_reshape(ia);
       const TfOp& idx_mul = M.prod(im, OP_MUL, "frame stride");
       int ra, rc; M.split_const(idx_mul, &ra, &rc, "frame stride");
       const TfTensor& st = m.tensors[rc];
-      if (st.type != TT_I32 || st.numel() != 1) M.fail("frame stride const");
+      if (st.type != TT_I32 || st.numel() != 1 || !st.has_bytes(4)) M.fail("frame stride const");
       S.hop = st.i32()[0] * group;
       if (S.hop <= 0 || F.n_samples < S.frame_len) M.fail("framing geometry");
       S.n_frames = (F.n_samples - S.frame_len) / S.hop + 1;

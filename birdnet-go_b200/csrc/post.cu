@@ -25,10 +25,15 @@ sigmoid_topk_kernel(const float* __restrict__ logits, int n, float sensitivity, 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* x = logits + (size_t)b * n;
   const double sens = (double)sensitivity;
-  for (int i = tid; i < n; i += kTopkThreads) s_conf[i] = (float)(1.0 / (1.0 + exp(-sens * (double)__ldg(x + i))));
+  // NaN logits (a NaN/Inf PCM sample propagates to every logit) become confidence NaN in the reference too; here they
+  // rank below every real confidence (-1 sentinel) so the arg-max rounds below always find an in-range index
+  for (int i = tid; i < n; i += kTopkThreads) {
+    const float c = (float)(1.0 / (1.0 + exp(-sens * (double)__ldg(x + i))));
+    s_conf[i] = (c == c) ? c : -1.f;
+  }
   __syncthreads();
   for (int r = 0; r < k; ++r) {
-    float bv = -2.f; int bi = 0x7fffffff;
+    float bv = -3.f; int bi = 0x7fffffff;
     for (int i = tid; i < n; i += kTopkThreads) { const float v = s_conf[i]; if (better(v, i, bv, bi)) { bv = v; bi = i; } }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -39,8 +44,11 @@ sigmoid_topk_kernel(const float* __restrict__ logits, int n, float sensitivity, 
     __syncthreads();
     if (tid == 0) {
       for (int w = 1; w < kTopkThreads / 32; ++w) if (better(s_v[w], s_i[w], bv, bi)) { bv = s_v[w]; bi = s_i[w]; }
-      if (r < n) { idx[(size_t)b * k + r] = bi; conf[(size_t)b * k + r] = bv; s_conf[bi] = -1.f; }
-      else { idx[(size_t)b * k + r] = -1; conf[(size_t)b * k + r] = 0.f; }
+      if (r < n && bi >= 0 && bi < n) {
+        idx[(size_t)b * k + r] = bi;
+        conf[(size_t)b * k + r] = bv < 0.f ? __int_as_float(0x7fc00000) : bv;      // a consumed / NaN slot reports NaN, like the reference would
+        s_conf[bi] = -2.f;
+      } else { idx[(size_t)b * k + r] = -1; conf[(size_t)b * k + r] = 0.f; }
     }
     __syncthreads();
   }

@@ -34,6 +34,8 @@ struct TfTensor {
   std::string name;
   bool is_const() const { return data != nullptr && nbytes > 0; }
   size_t numel() const { size_t n = 1; for (int d : shape) n *= (size_t)d; return n; }
+  // constant with at least numel * elem_bytes bytes behind it (negative / dynamic dims make numel huge -> false)
+  bool has_bytes(size_t elem_bytes) const { const size_t n = numel(); return is_const() && n <= nbytes / elem_bytes; }
   const float* f32() const { return reinterpret_cast<const float*>(data); }
   const int32_t* i32() const { return reinterpret_cast<const int32_t*>(data); }
 };
@@ -59,12 +61,14 @@ class FlatReader {
  public:
   FlatReader(const uint8_t* b, size_t n) : b_(b), n_(n) {}
   template <class T> T rd(size_t p) const {
-    if (p + sizeof(T) > n_) throw std::runtime_error("tflite: read past end of buffer");
+    if (p > n_ || sizeof(T) > n_ - p) throw std::runtime_error("tflite: read past end of buffer");   // no wrap-around for huge p
     T v; std::memcpy(&v, b_ + p, sizeof(T)); return v;
   }
   size_t field(size_t table, int slot) const {
     int32_t so = rd<int32_t>(table);
-    size_t vt = (size_t)((int64_t)table - so);
+    const int64_t vt64 = (int64_t)table - so;
+    if (vt64 < 0 || (uint64_t)vt64 > n_) throw std::runtime_error("tflite: vtable offset out of range");
+    size_t vt = (size_t)vt64;
     uint16_t vlen = rd<uint16_t>(vt);
     size_t off_pos = 4 + 2 * (size_t)slot;
     if (off_pos + 2 > vlen) return 0;
@@ -79,6 +83,7 @@ class FlatReader {
     if (!p) { *len = 0; return 0; }
     size_t v = indirect(p);
     *len = rd<uint32_t>(v);
+    if ((uint64_t)*len > n_) throw std::runtime_error("tflite: vector length exceeds the buffer");
     return v + 4;
   }
   std::vector<size_t> table_vec(size_t table, int slot) const {
@@ -170,12 +175,29 @@ inline TfModel parse_tflite(const void* data, size_t len) {
         default: break;
       }
     }
-    for (int32_t i : op.in) if (i >= (int32_t)m.tensors.size()) throw std::runtime_error("tflite: bad tensor index");
+    for (int32_t i : op.in) if (i < -1 || i >= (int32_t)m.tensors.size()) throw std::runtime_error("tflite: bad tensor index");   // -1 = optional input absent
+    // minimum arity of the ops the plan matcher dereferences (a malformed file must fail here, not read past op.in)
+    {
+      size_t need = 1;
+      switch (op.code) {
+        case OP_CONV_2D: case OP_DEPTHWISE_CONV_2D: case OP_FULLY_CONNECTED: case OP_ADD: case OP_MUL: case OP_SUB: case OP_DIV:
+        case OP_PAD: case OP_GATHER: case OP_POW: case OP_RFFT2D: case OP_RESHAPE: case OP_TRANSPOSE: case OP_MEAN: case OP_REVERSE_V2:
+        case OP_MAXIMUM: case OP_REDUCE_MAX: case OP_REDUCE_MIN: case OP_EXPAND_DIMS: need = 2; break;
+        case OP_STRIDED_SLICE: need = 4; break;
+        default: break;
+      }
+      if (op.code == OP_RESHAPE) need = 1;      // the shape operand of RESHAPE is optional in the schema
+      if (op.in.size() < need) throw std::runtime_error("tflite: operator has too few inputs");
+      for (size_t k = 0; k < need; ++k) if (op.in[k] < 0) throw std::runtime_error("tflite: required operator input is absent");
+      if (op.out.empty()) throw std::runtime_error("tflite: operator has no output");
+    }
     for (int32_t i : op.out) if (i < 0 || i >= (int32_t)m.tensors.size()) throw std::runtime_error("tflite: bad tensor index");
     m.ops.push_back(std::move(op));
   }
   m.inputs = fb.i32_vec(sg, 1);
   m.outputs = fb.i32_vec(sg, 2);
+  for (int32_t i : m.inputs) if (i < 0 || i >= (int32_t)m.tensors.size()) throw std::runtime_error("tflite: bad graph input index");
+  for (int32_t i : m.outputs) if (i < 0 || i >= (int32_t)m.tensors.size()) throw std::runtime_error("tflite: bad graph output index");
   return m;
 }
 

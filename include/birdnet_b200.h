@@ -65,7 +65,8 @@ typedef struct bnb_options {
   int32_t micro_batch;  /* chunks per kernel-chain launch (L2-resident tiling); 0 -> library default */
   int32_t precision;    /* bnb_precision                                                             */
   int32_t use_graphs;   /* 1 = replay the kernel chain from CUDA graphs; 0 = plain launches          */
-  int32_t reserved[9];
+  int32_t lanes;        /* concurrent front-phase streams (micro-batches in flight); 0 -> library default (2) */
+  int32_t reserved[8];
 } bnb_options;
 
 /* Input sample formats for the batch entry points. */
