@@ -138,23 +138,6 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def _cpu_worker(args):
-    """One worker process of the CPU arm: `threads` torch threads, its own share of the chunks."""
-    threads, n_chunks, steps, warmup = args
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    import torch
-    torch.set_num_threads(threads)
-    import birdnet_oracle as bo
-    o = bo.Oracle(dtype=torch.float32)
-    x = soundscape_batch(max(n_chunks, 1))
-    for _ in range(max(1, warmup)):
-        o.predict_batch(x[:1], batch=1)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        o.predict_batch(x, batch=min(8, len(x)))
-    return time.perf_counter() - t0
-
-
 def _cpu_info():
     try:
         return [ln.split(":", 1)[1].strip() for ln in open("/proc/cpuinfo") if ln.startswith("model name")][0]
@@ -162,54 +145,229 @@ def _cpu_info():
         return ""
 
 
-def _host_cores():
+def _cgroup_cpu_limit():
+    """CPU quota of this container in cores (cgroup v2 cpu.max, then v1 cfs quota), or None when unlimited."""
     try:
-        return len(os.sched_getaffinity(0))
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            return float(q) / float(per)
     except Exception:
-        return os.cpu_count() or 1
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return q / per
+    except Exception:
+        pass
+    return None
 
 
-def cpu_reference_shaped(seconds=6.0, threads=None):
+def _host_cores():
+    """Cores this process can really use: the affinity mask, capped by the cgroup CPU quota (sched_getaffinity alone ignores
+    the quota of a shared box — VERDICT r1 weak #9: the same '128 cores' gave 165 and 1483 chunks/s)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    lim = _cgroup_cpu_limit()
+    if lim is not None:
+        n = max(1, min(n, int(lim)))
+    return n
+
+
+def _host_state():
+    try:
+        la = [float(v) for v in open("/proc/loadavg").read().split()[:3]]
+    except Exception:
+        la = None
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count()
+    return {"affinity_cores": aff, "cgroup_cpu_limit": _cgroup_cpu_limit(), "effective_cores": _host_cores(), "loadavg": la, "cpu": _cpu_info()}
+
+
+def probe_reference_runtimes():
+    """Is the reference's own arithmetic available on this box?  (libtensorflowlite_c as linked by go-tflite, or the Python
+    runtimes that wrap the same kernels.)  BASELINE.md §5.2 / SURVEY §8(d).  Returns {name: path-or-version}."""
+    import ctypes.util
+    import glob
+    import importlib.util
+    found = {}
+    pats = []
+    for d in ["/usr/lib", "/usr/local/lib", "/usr/lib/x86_64-linux-gnu", "/opt", os.path.expanduser("~/.local/lib")] + os.environ.get("LD_LIBRARY_PATH", "").split(":"):
+        if d:
+            pats += [os.path.join(d, "libtensorflowlite_c*.so*"), os.path.join(d, "**", "libtensorflowlite_c*.so*"), os.path.join(d, "libonnxruntime.so*")]
+    for pat in pats:
+        try:
+            for f in glob.glob(pat, recursive=True)[:1]:
+                found["libtensorflowlite_c" if "tensorflowlite" in f else "libonnxruntime"] = f
+        except Exception:
+            pass
+    n = ctypes.util.find_library("tensorflowlite_c")
+    if n:
+        found.setdefault("libtensorflowlite_c", n)
+    for mod in ("tflite_runtime", "tensorflow", "ai_edge_litert", "onnxruntime"):
+        try:
+            if importlib.util.find_spec(mod) is not None:
+                found[mod] = "python module"
+        except Exception:
+            pass
+    return found
+
+
+class TFLiteC:
+    """The reference's backend itself through the TFLite C API, with the reference's thread rule
+    (/root/reference/internal/inference/tflite/classifier.go:44-61: XNNPACK delegate with threads-1 workers, interpreter
+    pinned to 1 thread; plain interpreter with `threads` when the delegate is unavailable)."""
+
+    def __init__(self, lib_path, model_bytes, threads):
+        import ctypes as C
+        self.C = C
+        L = self.L = C.CDLL(lib_path)
+        L.TfLiteModelCreate.restype = C.c_void_p; L.TfLiteModelCreate.argtypes = [C.c_void_p, C.c_size_t]
+        L.TfLiteInterpreterOptionsCreate.restype = C.c_void_p
+        L.TfLiteInterpreterOptionsSetNumThreads.argtypes = [C.c_void_p, C.c_int32]
+        L.TfLiteInterpreterCreate.restype = C.c_void_p; L.TfLiteInterpreterCreate.argtypes = [C.c_void_p, C.c_void_p]
+        L.TfLiteInterpreterAllocateTensors.argtypes = [C.c_void_p]
+        L.TfLiteInterpreterResizeInputTensor.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int), C.c_int32]
+        L.TfLiteInterpreterGetInputTensor.restype = C.c_void_p; L.TfLiteInterpreterGetInputTensor.argtypes = [C.c_void_p, C.c_int32]
+        L.TfLiteInterpreterGetOutputTensor.restype = C.c_void_p; L.TfLiteInterpreterGetOutputTensor.argtypes = [C.c_void_p, C.c_int32]
+        L.TfLiteTensorCopyFromBuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.TfLiteTensorCopyToBuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.TfLiteInterpreterInvoke.argtypes = [C.c_void_p]
+        self._model_bytes = model_bytes
+        self.model = L.TfLiteModelCreate(model_bytes, len(model_bytes))
+        opts = L.TfLiteInterpreterOptionsCreate()
+        self.delegate = "none"
+        try:                                             # XNNPACK delegate entry points are optional exports of the C library
+            class XOpts(C.Structure):
+                _fields_ = [("num_threads", C.c_int32), ("flags", C.c_uint32), ("weights_cache", C.c_void_p), ("handle_variable_ops", C.c_bool),
+                            ("experimental_weight_cache_file_path", C.c_char_p), ("experimental_adaptive_avx_optimization", C.c_bool)]
+            L.TfLiteXNNPackDelegateOptionsDefault.restype = XOpts
+            L.TfLiteXNNPackDelegateCreate.restype = C.c_void_p; L.TfLiteXNNPackDelegateCreate.argtypes = [C.POINTER(XOpts)]
+            L.TfLiteInterpreterOptionsAddDelegate.argtypes = [C.c_void_p, C.c_void_p]
+            xo = L.TfLiteXNNPackDelegateOptionsDefault()
+            xo.num_threads = max(1, threads - 1)
+            d = L.TfLiteXNNPackDelegateCreate(C.byref(xo))
+            if d:
+                L.TfLiteInterpreterOptionsAddDelegate(opts, d)
+                L.TfLiteInterpreterOptionsSetNumThreads(opts, 1)
+                self.delegate = "xnnpack(%d)" % max(1, threads - 1)
+        except AttributeError:
+            pass
+        if self.delegate == "none":
+            L.TfLiteInterpreterOptionsSetNumThreads(opts, threads)
+        self.it = L.TfLiteInterpreterCreate(self.model, opts)
+        dims = (C.c_int * 2)(1, N_SAMPLES)
+        L.TfLiteInterpreterResizeInputTensor(self.it, 0, dims, 2)
+        if L.TfLiteInterpreterAllocateTensors(self.it) != 0:
+            raise RuntimeError("TfLiteInterpreterAllocateTensors failed")
+        self.out = np.empty(N_SPECIES, np.float32)
+
+    def predict(self, x):
+        C, L = self.C, self.L
+        x = np.ascontiguousarray(x, np.float32)
+        L.TfLiteTensorCopyFromBuffer(L.TfLiteInterpreterGetInputTensor(self.it, 0), x.ctypes.data_as(C.c_void_p), x.nbytes)
+        if L.TfLiteInterpreterInvoke(self.it) != 0:
+            raise RuntimeError("TfLiteInterpreterInvoke failed")
+        L.TfLiteTensorCopyToBuffer(L.TfLiteInterpreterGetOutputTensor(self.it, 0), self.out.ctypes.data_as(C.c_void_p), self.out.nbytes)
+        return self.out
+
+
+def _cpu_worker(args):
+    """One worker process of the CPU arm: `threads` intra-op threads, its own share of the chunks.  All workers start each
+    timed repeat together (barrier) and report their own wall time of it."""
+    threads, n_chunks, steps, repeats, barrier, tfl_path = args
+    x = soundscape_batch(max(n_chunks, 1))
+    if tfl_path:
+        model = open(os.path.join(REPO, "assets", "BirdNET_GLOBAL_6K_V2.4_Model_FP32.tflite"), "rb").read()
+        net = TFLiteC(tfl_path, model, threads)
+        run = lambda: [net.predict(x[i]) for i in range(len(x))]
+    else:
+        sys.path.insert(0, os.path.join(REPO, "oracle"))
+        import torch
+        torch.set_num_threads(threads)
+        import birdnet_oracle as bo
+        o = bo.Oracle(dtype=torch.float32)
+        run = lambda: o.predict_batch(x, batch=min(8, len(x)))
+        o.predict_batch(x[:1], batch=1)
+    run()                                              # warm-up: weights paged in, thread pools up
+    out = []
+    for _ in range(repeats):
+        barrier.wait()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run()
+        out.append(time.perf_counter() - t0)
+    return out
+
+
+def cpu_reference_shaped(seconds=6.0, threads=None, tfl_path=None):
     """What the reference itself does (cmd/benchmark/benchmark.go:91-136): ONE interpreter, batch 1, intra-op threads
-    only, inference serialized (orchestrator.go:531 global inferenceMu) — restated with the oracle port."""
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    import torch
-    import birdnet_oracle as bo
+    only, inference serialized (orchestrator.go:531 global inferenceMu)."""
     threads = threads or min(16, _host_cores())
-    torch.set_num_threads(threads)
-    o = bo.Oracle(dtype=torch.float32)
     x = soundscape_batch(4)
-    o.predict_batch(x[:1], batch=1)
+    if tfl_path:
+        net = TFLiteC(tfl_path, open(os.path.join(REPO, "assets", "BirdNET_GLOBAL_6K_V2.4_Model_FP32.tflite"), "rb").read(), threads)
+        one = lambda i: net.predict(x[i % 4])
+    else:
+        sys.path.insert(0, os.path.join(REPO, "oracle"))
+        import torch
+        import birdnet_oracle as bo
+        torch.set_num_threads(threads)
+        o = bo.Oracle(dtype=torch.float32)
+        one = lambda i: o.predict_batch(x[i % 4:i % 4 + 1], batch=1)
+    one(0)
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
-        o.predict_batch(x[n % 4:n % 4 + 1], batch=1); n += 1
+        one(n); n += 1
     return n / (time.perf_counter() - t0), threads
 
 
-def cpu_reference_run(steps, warmup, chunks_per_worker=4, threads_per_worker=2):
-    """The reference's CPU implementation of the path, as restated by oracle/ (kind = "port": no Go toolchain and no
-    libtensorflowlite_c in this image — DESIGN.md).  float32 torch-CPU.  Chunks are independent, so the way to give
-    the CPU ALL host cores is data-parallel: cores/threads_per_worker processes x threads_per_worker threads (the
-    reference itself cannot do this: it runs batch 1 under a global mutex; that shape is reported beside it).
-    Each step = a bounded sample of `workers * chunks_per_worker` chunks of the same soundscape workload."""
+def cpu_reference_run(steps, warmup, chunks_per_worker=4, threads_per_worker=2, repeats=3):
+    """The reference's CPU implementation of the path on ALL host cores this container may use.
+    kind = "reference" when libtensorflowlite_c is present on the box (the reference's own arithmetic, driven through the C
+    API with its thread rule), else "port" (oracle/: torch-CPU fp32 restatement of the same .tflite; no Go toolchain and no
+    TFLite library in this image — DESIGN.md).  Chunks are independent, so the whole-host number is data-parallel:
+    effective_cores / threads_per_worker processes x threads_per_worker threads (the reference itself runs batch 1 under a
+    global mutex; that shape is reported beside it).  Every repeat starts all workers together; a repeat's throughput =
+    all chunks / slowest worker; reported: median (value), min, max, per-core, plus the host state that explains it."""
     import multiprocessing as mp
-    cores = _host_cores()
+    state = _host_state()
+    cores = state["effective_cores"]
     workers = max(1, cores // threads_per_worker)
+    found = probe_reference_runtimes()
+    tfl = found.get("libtensorflowlite_c")
+    if tfl:
+        try:
+            TFLiteC(tfl, open(os.path.join(REPO, "assets", "BirdNET_GLOBAL_6K_V2.4_Model_FP32.tflite"), "rb").read(), 2)
+        except Exception:
+            tfl = None
     ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    barrier = mgr.Barrier(workers)
     t0 = time.perf_counter()
     with ctx.Pool(workers) as pool:
-        per = pool.map(_cpu_worker, [(threads_per_worker, chunks_per_worker, steps, warmup)] * workers)
+        per = pool.map(_cpu_worker, [(threads_per_worker, chunks_per_worker, steps, repeats, barrier, tfl)] * workers)
     wall = time.perf_counter() - t0
-    dt = max(per)                      # slowest worker's timed region (process start-up / model load excluded)
     n = workers * chunks_per_worker * steps
-    cps = n / dt
-    shaped, sthreads = cpu_reference_shaped()
-    return cps, dt, {"value": cps, "unit": UNIT, "cores": workers * threads_per_worker, "kind": "port",
-                     "sample": "%d chunks = %d processes x %d threads x %d steps x %d soundscape chunks, torch-CPU fp32 restatement of the "
-                               ".tflite graph (oracle/), %.1f s timed (%.1f s wall incl. start-up), %s" %
-                               (n, workers, threads_per_worker, steps, chunks_per_worker, dt, wall, _cpu_info()),
+    rep_s = [max(w[r] for w in per) for r in range(repeats)]            # slowest worker of each synchronised repeat
+    rep_cps = sorted(n / t for t in rep_s)
+    cps = float(np.median(rep_cps))
+    dt = n / cps
+    shaped, sthreads = cpu_reference_shaped(tfl_path=tfl)
+    kind = "reference" if tfl else "port"
+    what = ("libtensorflowlite_c (%s) through the C API, reference thread rule" % tfl) if tfl else "torch-CPU fp32 restatement of the .tflite graph (oracle/)"
+    return cps, dt, {"value": cps, "unit": UNIT, "cores": workers * threads_per_worker, "kind": kind,
+                     "value_min": rep_cps[0], "value_max": rep_cps[-1], "per_core": cps / (workers * threads_per_worker), "repeats": repeats,
+                     "host": state, "runtimes_found": found,
+                     "sample": "%d chunks per repeat = %d processes x %d threads x %d steps x %d soundscape chunks, %s, %d synchronised repeats (median), "
+                               "%.1f s timed per repeat (%.1f s wall incl. start-up), %s" %
+                               (n, workers, threads_per_worker, steps, chunks_per_worker, what, repeats, dt, wall, state["cpu"]),
                      "reference_shaped": {"value": shaped, "unit": UNIT, "threads": sthreads,
-                                          "what": "one interpreter, batch 1, serialized (cmd/benchmark shape), same oracle port"}}
+                                          "what": "one interpreter, batch 1, serialized (cmd/benchmark shape), same " + kind}}
 
 
 def main():
@@ -232,7 +390,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(a.steps, 6))
+        steps = max(1, min(a.steps, 4))          # each step = a bounded sample of the workload on every worker; 3 synchronised repeats
         cps, dt, cb = cpu_reference_run(steps, min(a.warmup, 1))
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": cps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 1),
                           "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -444,7 +602,7 @@ def main():
             "precision": clf.runtime_info()[2],
         }
         if not a.no_cpu_baseline and world == 1:
-            _, _, cb = cpu_reference_run(4, 1)
+            _, _, cb = cpu_reference_run(3, 1)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:

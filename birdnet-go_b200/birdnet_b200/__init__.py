@@ -74,11 +74,16 @@ SYMBOLS = {
     "bnb_describe_model": (C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "bnb_debug_read_tensor": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "bnb_debug_keep_intermediates": (C.c_int, [C.c_void_p, C.c_int]),
+    "bnb_range_filter_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "bnb_range_filter_destroy": (None, [C.c_void_p]),
+    "bnb_range_filter_num_species": (C.c_int, [C.c_void_p]),
+    "bnb_range_filter_predict": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "bnb_range_filter_predict_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "bnb_debug_tmem_probe": (C.c_int, [C.c_void_p]),
     "bnb_debug_mbconv2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnb_debug_pw2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
-                                C.c_int, C.c_void_p, C.c_void_p]),
+                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -303,8 +308,9 @@ def debug_mbconv2(x, w_exp, b_exp, w_dw, b_dw, stride, flags=0):
     return d, se, dict(zip(keys, info.tolist()))
 
 
-def debug_pw2(A, Wt, bias, gate=None, rows_per_chunk=0, residual=None, act=0, planes_out=True):
-    """out [M,N] = act(A' W^T + bias) (+ residual) through pw2_kernel; A [M,K], Wt [N,K]."""
+def debug_pw2(A, Wt, bias, gate=None, rows_per_chunk=0, residual=None, act=0, out_mode=1, geom=None):
+    """out [M,N] = act(A' W^T + bias) (+ residual) through pw2_kernel; A [M,K], Wt [N,K].  out_mode 0 fp32, 1 plain planes,
+    2 patch image of a consuming block with input map geom = (H, W, stride, C_exp); a residual needs geom (H, W, ..) too."""
     A = np.ascontiguousarray(A, np.float32); Wt = np.ascontiguousarray(Wt, np.float32); bias = np.ascontiguousarray(bias, np.float32)
     M, K = A.shape
     N = Wt.shape[0]
@@ -312,9 +318,62 @@ def debug_pw2(A, Wt, bias, gate=None, rows_per_chunk=0, residual=None, act=0, pl
     info = np.zeros(4, np.int32)
     g = np.ascontiguousarray(gate, np.float32) if gate is not None else None
     r = np.ascontiguousarray(residual, np.float32) if residual is not None else None
+    gm = np.ascontiguousarray(list(geom) + [0] * (4 - len(geom)), np.int32) if geom is not None else None
     _check(load_library().bnb_debug_pw2(_ptr(A), M, K, _ptr(Wt), _ptr(bias), N, _ptr(g) if g is not None else None, rows_per_chunk,
-                                        _ptr(r) if r is not None else None, act, int(planes_out), _ptr(out), _ptr(info)))
+                                        _ptr(r) if r is not None else None, act, int(out_mode), _ptr(gm) if gm is not None else None,
+                                        _ptr(out), _ptr(info)))
     return out, dict(zip(("bn", "stages", "b_res", "smem"), info.tolist()))
+
+
+DEFAULT_RANGE_MODEL = os.path.join(REPO, "assets", "BirdNET_GLOBAL_6K_V2.4_MData_Model_V2_FP16.tflite")
+
+
+class B200RangeFilter:
+    """inference.RangeFilter + BatchRangeFilter (backend.go:55-76) on the GPU: species occurrence scores for
+    (latitude, longitude, week).  NOT thread-safe, like the reference's."""
+
+    def __init__(self, model_data: bytes | None = None, device=-1):
+        lib = load_library()
+        if model_data is None:
+            with open(DEFAULT_RANGE_MODEL, "rb") as f:
+                model_data = f.read()
+        h = C.c_void_p()
+        _check(lib.bnb_range_filter_create(model_data, len(model_data), device, C.byref(h)))
+        self._lib, self._h = lib, h
+        self.n_species = lib.bnb_range_filter_num_species(h)
+
+    def num_species(self):
+        return self.n_species
+
+    def predict(self, latitude, longitude, week):
+        if self._h is None:
+            raise B200Error(ERR_CLOSED, "range filter is closed")
+        out = np.empty(self.n_species, np.float32)
+        _check(self._lib.bnb_range_filter_predict(self._h, float(latitude), float(longitude), float(week), _ptr(out)))
+        return out
+
+    def predict_batch(self, inputs, batch_size=None):
+        """inputs: flat [batch*3] or [batch, 3] float32 (lat, lon, week) -> [batch, n_species] scores (PredictBatch, backend.go:70-76)."""
+        if self._h is None:
+            raise B200Error(ERR_CLOSED, "range filter is closed")
+        x = np.ascontiguousarray(inputs, np.float32).reshape(-1)
+        n = x.size // 3 if batch_size is None else int(batch_size)
+        if x.size != n * 3:
+            raise B200Error(ERR_INVALID_ARGUMENT, "input size mismatch: expected %d values, got %d" % (n * 3, x.size))
+        out = np.empty((n, self.n_species), np.float32)
+        _check(self._lib.bnb_range_filter_predict_batch(self._h, _ptr(x), n, _ptr(out)))
+        return out
+
+    def close(self):
+        if self._h is not None:
+            self._lib.bnb_range_filter_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Result:

@@ -27,7 +27,7 @@ constexpr int kStemQ = kStemCols / 4;                 // 130 column quads
 
 __global__ void __launch_bounds__(kStemThreads)
 stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restrict__ stem_out, float* __restrict__ out,
-                __half* __restrict__ out_h, __half* __restrict__ out_l) {
+                uint8_t* __restrict__ out_img, const PatchTiles op) {
   __shared__ __align__(16) float s_in[kStemKh][4][kStemQ][2];          // [row][col%4][col/4][ci]
   __shared__ __align__(16) float s_w[kStemKh * kStemKw * 2 * kStemCo];  // [kh][kw][ci][co]
   __shared__ __align__(16) float s_wm[kStemCo * 2 * kStemCo];           // [48][co] (transposed at load)
@@ -111,16 +111,23 @@ stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restr
     }
   }
   const size_t opos = (((size_t)b * p.out_h + h) * (p.out_w / 2) + tid) * kStemCo;
-  if (out_h != nullptr) {
-    // F16X3 path: the block input leaves as fp16 hi / lo planes (x ~= hi + lo), ready for the TMA -> tcgen05 patch loads of mbconv2.cu
+  if (out_img != nullptr) {
+    // F16X3 path: the block input leaves as fp16 hi / lo planes (x ~= hi + lo), written straight into the PatchTiles image that
+    // block 1's fused kernel (mbconv2.cu) bulk-copies: the pixel goes into every tile whose halo patch contains it
     uint32_t hw[kStemCo / 2], lw[kStemCo / 2];
 #pragma unroll
     for (int c = 0; c < kStemCo / 2; ++c) tc::split2(mix[c].x, mix[c].y, hw[c], lw[c]);
+    op.for_each_tile(h, tid, [&](int ty, int tx, int pr, int pc) {
+      uint8_t* tile = out_img + op.tile_base(b, ty, tx);
 #pragma unroll
-    for (int q = 0; q < kStemCo / 8; ++q) {
-      *reinterpret_cast<uint4*>(out_h + opos + 8 * q) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-      *reinterpret_cast<uint4*>(out_l + opos + 8 * q) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
-    }
+      for (int q = 0; q < kStemCo / 8; ++q) {
+        int st, chunk;
+        op.stage_of(q, &st, &chunk);
+        uint8_t* dst = tile + op.in_tile(pr, pc, st, chunk);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+        *reinterpret_cast<uint4*>(dst + op.st_plane[st]) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+      }
+    });
     return;
   }
   float* o = out + opos;
@@ -420,7 +427,7 @@ row_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int B, in
 // relu(x*mul+add) + im2col: in planes [B][kh][in_w][cin] -> out planes [B*out_w][kh*kw*cin], 8 channels (16 B per plane) per thread
 __global__ void __launch_bounds__(256)
 post_prep2_kernel(const __half* __restrict__ ih, const __half* __restrict__ il, const float* __restrict__ mul, const float* __restrict__ add,
-                  __half* __restrict__ oh, __half* __restrict__ ol, int B, int kh, int kw, int in_w, int out_w, int cin) {
+                  uint8_t* __restrict__ o_img, const RowTiles ot, int B, int kh, int kw, int in_w, int out_w, int cin) {
   const int c8n = cin / 8, K8 = kh * kw * c8n;
   const long long total = (long long)B * out_w * K8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -438,14 +445,15 @@ post_prep2_kernel(const __half* __restrict__ ih, const __half* __restrict__ il, 
     tc::split2(fmaxf(fmaf(v1.x, m0.z, a0.z), 0.f), fmaxf(fmaf(v1.y, m0.w, a0.w), 0.f), ho.y, lo.y);
     tc::split2(fmaxf(fmaf(v2.x, m1.x, a1.x), 0.f), fmaxf(fmaf(v2.y, m1.y, a1.y), 0.f), ho.z, lo.z);
     tc::split2(fmaxf(fmaf(v3.x, m1.z, a1.z), 0.f), fmaxf(fmaf(v3.y, m1.w, a1.w), 0.f), ho.w, lo.w);
-    reinterpret_cast<uint4*>(oh)[idx] = ho;
-    reinterpret_cast<uint4*>(ol)[idx] = lo;
+    uint8_t* dst = o_img + ot.piece(row, k8);              // RowTiles image of the im2col matrix [B*out_w][kh*kw*cin]
+    *reinterpret_cast<uint4*>(dst) = ho;
+    *reinterpret_cast<uint4*>(dst + 16384) = lo;
   }
 }
 
 // mean over `rows` consecutive rows -> fp32 [B][C] (the embedding the API returns) and its hi/lo planes (the FC head's A operand)
 __global__ void __launch_bounds__(256)
-row_mean2_kernel(const float* __restrict__ in, float* __restrict__ out, __half* __restrict__ oh, __half* __restrict__ ol, int B, int rows, int C) {
+row_mean2_kernel(const float* __restrict__ in, float* __restrict__ out, uint8_t* __restrict__ o_img, const RowTiles ot, int B, int rows, int C) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // one thread = two adjacent channels
   if (idx >= B * (C / 2)) return;
   const int b = idx / (C / 2), c = 2 * (idx - b * (C / 2));
@@ -458,32 +466,34 @@ row_mean2_kernel(const float* __restrict__ in, float* __restrict__ out, __half* 
   *reinterpret_cast<float2*>(out + (size_t)b * C + c) = make_float2(s0, s1);
   uint32_t h, l;
   tc::split2(s0, s1, h, l);
-  *reinterpret_cast<uint32_t*>(oh + (size_t)b * C + c) = h;
-  *reinterpret_cast<uint32_t*>(ol + (size_t)b * C + c) = l;
+  uint8_t* dst = o_img + ot.piece(b, c >> 3) + (size_t)(c & 7) * 2u;     // RowTiles image of the embedding matrix [B][C]
+  *reinterpret_cast<uint32_t*>(dst) = h;
+  *reinterpret_cast<uint32_t*>(dst + 16384) = l;
 }
 
 }  // namespace
 
-void launch_post_prep2(const __half* ih, const __half* il, const float* mul, const float* add, __half* oh, __half* ol, int B, int kh, int kw,
+void launch_post_prep2(const __half* ih, const __half* il, const float* mul, const float* add, uint8_t* o_img, int B, int kh, int kw,
                        int in_w, int out_w, int cin, cudaStream_t s, LaunchCounter& lc) {
   if (cin % 8) throw std::runtime_error("post_prep2: channel count must be a multiple of 8");
   const long long total = (long long)B * out_w * kh * kw * (cin / 8);
   long long blocks = ceil_div_ll(total, 256);
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-  post_prep2_kernel<<<(unsigned)blocks, 256, 0, s>>>(ih, il, mul, add, oh, ol, B, kh, kw, in_w, out_w, cin);
+  post_prep2_kernel<<<(unsigned)blocks, 256, 0, s>>>(ih, il, mul, add, o_img, RowTiles::make(kh * kw * cin), B, kh, kw, in_w, out_w, cin);
   BNB_LAUNCH_CHECK(lc);
 }
 
-void launch_row_mean2(const float* in, float* out, __half* oh, __half* ol, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc) {
+void launch_row_mean2(const float* in, float* out, uint8_t* o_img, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc) {
   if (C % 2) throw std::runtime_error("row_mean2: channel count must be even");
-  row_mean2_kernel<<<ceil_div(B * (C / 2), 256), 256, 0, s>>>(in, out, oh, ol, B, rows, C);
+  row_mean2_kernel<<<ceil_div(B * (C / 2), 256), 256, 0, s>>>(in, out, o_img, RowTiles::make(C), B, rows, C);
   BNB_LAUNCH_CHECK(lc);
 }
 
 void launch_stem_mix(const StemMixDev& p, const float* in, float* stem_out_or_null, float* out, int B,
-                     cudaStream_t s, LaunchCounter& lc, __half* out_h, __half* out_l) {
+                     cudaStream_t s, LaunchCounter& lc, uint8_t* out_img, const PatchTiles* out_patch) {
   dim3 grid(p.out_h, B);
-  stem_mix_kernel<<<grid, kStemThreads, 0, s>>>(p, in, stem_out_or_null, out, out_h, out_l);
+  if (out_img && (!out_patch || out_patch->C != kStemCo || out_patch->H != p.out_h || out_patch->W != p.out_w / 2)) throw std::runtime_error("stem_mix: patch layout does not match the pooled stem output");
+  stem_mix_kernel<<<grid, kStemThreads, 0, s>>>(p, in, stem_out_or_null, out, out_img, out_patch ? *out_patch : PatchTiles());
   BNB_LAUNCH_CHECK(lc);
 }
 

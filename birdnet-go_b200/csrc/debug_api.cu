@@ -9,6 +9,7 @@
 
 #include "../../include/birdnet_b200.h"
 #include "common.cuh"
+#include "layouts.h"
 #include "mbconv2.h"
 #include "pw2.h"
 #include "tc_common.cuh"
@@ -30,14 +31,67 @@ struct DevBuf {
   template <class T> T* as() { return static_cast<T*>(p); }
 };
 
-void split_host(const float* x, size_t rows, int cols, int pitch, std::vector<__half>* hi, std::vector<__half>* lo) {
-  hi->assign(rows * pitch, __float2half_rn(0.f)); lo->assign(rows * pitch, __float2half_rn(0.f));
-  for (size_t r = 0; r < rows; ++r)
-    for (int c = 0; c < cols; ++c) {
-      const float v = x[r * cols + c];
-      const __half h = __float2half_rn(v);
-      (*hi)[r * pitch + c] = h; (*lo)[r * pitch + c] = __float2half_rn(v - __half2float(h));
+void split1(float v, __half* h, __half* l) { *h = __float2half_rn(v); *l = __float2half_rn(v - __half2float(*h)); }
+
+// [M][K] fp32 -> RowTiles image
+std::vector<uint8_t> rows_encode(const float* x, long long M, int K) {
+  const RowTiles t = RowTiles::make(K);
+  std::vector<uint8_t> img(t.bytes(M), 0);
+  for (long long m = 0; m < M; ++m)
+    for (int k = 0; k < K; ++k) {
+      __half h, l; split1(x[m * K + k], &h, &l);
+      const size_t off = t.piece(m, k >> 3) + (size_t)(k & 7) * 2;
+      memcpy(img.data() + off, &h, 2); memcpy(img.data() + off + 16384, &l, 2);
     }
+  return img;
+}
+void rows_decode(const uint8_t* img, long long M, int K, float* out) {
+  const RowTiles t = RowTiles::make(K);
+  for (long long m = 0; m < M; ++m)
+    for (int k = 0; k < K; ++k) {
+      __half h, l;
+      const size_t off = t.piece(m, k >> 3) + (size_t)(k & 7) * 2;
+      memcpy(&h, img + off, 2); memcpy(&l, img + off + 16384, 2);
+      out[m * K + k] = __half2float(h) + __half2float(l);
+    }
+}
+// [B][H][W][C] fp32 -> PatchTiles image (every pixel into every tile that holds it)
+std::vector<uint8_t> patch_encode(const float* x, int B, const PatchTiles& t) {
+  std::vector<uint8_t> img(t.bytes(B), 0);
+  for (int b = 0; b < B; ++b)
+    for (int h = 0; h < t.H; ++h)
+      for (int w = 0; w < t.W; ++w)
+        t.for_each_tile(h, w, [&](int ty, int tx, int pr, int pc) {
+          for (int c = 0; c < t.C; ++c) {
+            int st, chunk; t.stage_of(c >> 3, &st, &chunk);
+            __half hh, ll; split1(x[(((size_t)b * t.H + h) * t.W + w) * t.C + c], &hh, &ll);
+            const size_t off = t.tile_base(b, ty, tx) + t.in_tile(pr, pc, st, chunk) + (size_t)(c & 7) * 2;
+            memcpy(img.data() + off, &hh, 2); memcpy(img.data() + off + t.st_plane[st], &ll, 2);
+          }
+        });
+  return img;
+}
+// PatchTiles image -> [B][H][W][C]; every copy of a pixel must agree (returns the number of disagreeing copies)
+long long patch_decode(const uint8_t* img, int B, const PatchTiles& t, float* out) {
+  long long bad = 0;
+  for (int b = 0; b < B; ++b)
+    for (int h = 0; h < t.H; ++h)
+      for (int w = 0; w < t.W; ++w) {
+        int copies = 0;
+        t.for_each_tile(h, w, [&](int ty, int tx, int pr, int pc) {
+          for (int c = 0; c < t.C; ++c) {
+            int st, chunk; t.stage_of(c >> 3, &st, &chunk);
+            __half hh, ll;
+            const size_t off = t.tile_base(b, ty, tx) + t.in_tile(pr, pc, st, chunk) + (size_t)(c & 7) * 2;
+            memcpy(&hh, img + off, 2); memcpy(&ll, img + off + t.st_plane[st], 2);
+            const float v = __half2float(hh) + __half2float(ll);
+            float& o = out[(((size_t)b * t.H + h) * t.W + w) * t.C + c];
+            if (copies == 0) o = v; else if (o != v) ++bad;
+          }
+          ++copies;
+        });
+      }
+  return bad;
 }
 
 template <class F>
@@ -104,34 +158,31 @@ int bnb_debug_mbconv2(const float* x, int B, int H, int W, int Cin, const float*
     const Mb2Plan P = mb2_plan(H, W, Ho, Wo, stride, Cin, C, !(flags & 1));
     if (info10) { const int v[10] = {P.TH, P.TW, P.PH, P.PW, P.n_mma, P.k_stages, P.a_resident, P.a_slots, P.b_slots, (int)P.smem_bytes}; memcpy(info10, v, sizeof(v)); }
     if (!P.ok) throw std::runtime_error("mbconv2: no plan for this layer shape");
-    const int pitch = (Cin + 7) / 8 * 8;
-    std::vector<__half> xh, xl;
-    split_host(x, (size_t)B * H * W, Cin, pitch, &xh, &xl);
+    const PatchTiles pt = mb2_patch_layout(P, H, W);
+    const std::vector<uint8_t> ximg = patch_encode(x, B, pt);
     std::vector<uint8_t> img;
     mb2_prepare_weights(P, w_exp, &img);
     std::vector<float> be((size_t)P.n_units * 128 + 64, 0.f);
     memcpy(be.data(), b_exp, (size_t)C * 4);
-    const size_t n_out = (size_t)B * Ho * Wo * C;
+    const long long M = (long long)B * Ho * Wo;
+    const RowTiles dt = RowTiles::make(C);
     const int tiles = P.tiles_h * P.tiles_w;
-    DevBuf dxh(xh.size() * 2), dxl(xl.size() * 2), dimg(img.size()), dbe(be.size() * 4), dwd((size_t)9 * C * 4), dbd((size_t)C * 4),
-        ddh(n_out * 2), ddl(n_out * 2), dpart((size_t)B * tiles * C * 4);
-    BNB_CUDA(cudaMemcpy(dxh.p, xh.data(), xh.size() * 2, cudaMemcpyHostToDevice));
-    BNB_CUDA(cudaMemcpy(dxl.p, xl.data(), xl.size() * 2, cudaMemcpyHostToDevice));
+    DevBuf dx(ximg.size()), dimg(img.size()), dbe(be.size() * 4), dwd((size_t)9 * C * 4), dbd((size_t)C * 4), dd(dt.bytes(M)), dpart((size_t)B * tiles * C * 4);
+    BNB_CUDA(cudaMemcpy(dx.p, ximg.data(), ximg.size(), cudaMemcpyHostToDevice));
     BNB_CUDA(cudaMemcpy(dimg.p, img.data(), img.size(), cudaMemcpyHostToDevice));
     BNB_CUDA(cudaMemcpy(dbe.p, be.data(), be.size() * 4, cudaMemcpyHostToDevice));
     BNB_CUDA(cudaMemcpy(dwd.p, w_dw, (size_t)9 * C * 4, cudaMemcpyHostToDevice));
     BNB_CUDA(cudaMemcpy(dbd.p, b_dw, (size_t)C * 4, cudaMemcpyHostToDevice));
     Mb2Launch L{};
-    L.xh = dxh.as<__half>(); L.xl = dxl.as<__half>(); L.x_pitch = pitch; L.Wimg = dimg.as<uint8_t>(); L.bias_e = dbe.as<float>();
-    L.w_dw = dwd.as<float>(); L.bias_dw = dbd.as<float>(); L.dh = ddh.as<__half>(); L.dl = ddl.as<__half>(); L.partial = dpart.as<float>();
+    L.x_img = dx.as<uint8_t>(); L.Wimg = dimg.as<uint8_t>(); L.bias_e = dbe.as<float>();
+    L.w_dw = dwd.as<float>(); L.bias_dw = dbd.as<float>(); L.d_img = dd.as<uint8_t>(); L.partial = dpart.as<float>();
     L.B = B; L.H = H; L.W = W; L.Ho = Ho; L.Wo = Wo;
     LaunchCounter lc;
     launch_mbconv2(P, L, nullptr, lc);
     BNB_CUDA(cudaDeviceSynchronize());
-    std::vector<__half> oh(n_out), ol(n_out);
-    BNB_CUDA(cudaMemcpy(oh.data(), ddh.p, n_out * 2, cudaMemcpyDeviceToHost));
-    BNB_CUDA(cudaMemcpy(ol.data(), ddl.p, n_out * 2, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n_out; ++i) d_out[i] = __half2float(oh[i]) + __half2float(ol[i]);
+    std::vector<uint8_t> dh(dt.bytes(M));
+    BNB_CUDA(cudaMemcpy(dh.data(), dd.p, dh.size(), cudaMemcpyDeviceToHost));
+    rows_decode(dh.data(), M, C, d_out);
     if (se_sum) {
       std::vector<float> part((size_t)B * tiles * C);
       BNB_CUDA(cudaMemcpy(part.data(), dpart.p, part.size() * 4, cudaMemcpyDeviceToHost));
@@ -145,45 +196,67 @@ int bnb_debug_mbconv2(const float* x, int B, int H, int W, int Cin, const float*
   });
 }
 
-// A [M][K], W [N][K], bias [N], gate [M / rows_per_chunk][K] or NULL, residual [M][N] or NULL -> out [M][N]
-// planes_out = 1: the kernel writes hi/lo planes (joined on the host), else fp32
+// A [M][K], W [N][K], bias [N], gate [M / rows_per_chunk][K] or NULL, residual [M][N] or NULL -> out [M][N].
+// out_mode 0: fp32 epilogue; 1: plain hi/lo planes; 2: PatchTiles image of a consuming MBConv block with input map
+// geom = {H, W, stride, C_exp} (M must be a multiple of H*W; the image is decoded on the host and every halo copy of a
+// pixel must agree).  A residual needs geom too ({H, W} of the block, read as its stride-1 PatchTiles image).
 int bnb_debug_pw2(const float* A, int M, int K, const float* W, const float* bias, int N, const float* gate, int rows_per_chunk,
-                  const float* residual, int act, int planes_out, float* out, int32_t* info4) {
+                  const float* residual, int act, int out_mode, const int32_t* geom4, float* out, int32_t* info4) {
   if (!A || !W || !bias || !out) return capi_fail(BNB_ERR_INVALID_ARGUMENT, "NULL pointer");
+  if ((out_mode == 2 || residual) && !geom4) return capi_fail(BNB_ERR_INVALID_ARGUMENT, "geometry required");
   return guarded_dbg([&] {
     int dev = 0; BNB_CUDA(cudaGetDevice(&dev)); tc_prepare_device(dev);
     std::vector<uint8_t> img;
     const PwTcLayer L = pw_tc_prepare(W, N, K, &img);
-    const int a_pitch = (K + 7) / 8 * 8, o_pitch = (N + 7) / 8 * 8;
-    std::vector<__half> ah, al, rh, rl;
-    split_host(A, (size_t)M, K, a_pitch, &ah, &al);
-    if (residual) split_host(residual, (size_t)M, N, o_pitch, &rh, &rl);
+    const std::vector<uint8_t> aimg = rows_encode(A, M, K);
     std::vector<float> bz((size_t)L.n_pad + 64, 0.f);
     memcpy(bz.data(), bias, (size_t)N * 4);
     const int chunks = rows_per_chunk > 0 ? (M + rows_per_chunk - 1) / rows_per_chunk : 1;
-    DevBuf dah(ah.size() * 2), dal(al.size() * 2), dimg(img.size()), db(bz.size() * 4), dg(gate ? (size_t)chunks * K * 4 : 16),
-        drh(rh.size() * 2), drl(rl.size() * 2), doh((size_t)M * o_pitch * 2), dol((size_t)M * o_pitch * 2), d32((size_t)M * N * 4);
-    BNB_CUDA(cudaMemcpy(dah.p, ah.data(), ah.size() * 2, cudaMemcpyHostToDevice));
-    BNB_CUDA(cudaMemcpy(dal.p, al.data(), al.size() * 2, cudaMemcpyHostToDevice));
+    PatchTiles rp, op;
+    int Bimg = 0;
+    std::vector<uint8_t> rimg;
+    if (residual) {       // the block input of a stride-1 block with N channels on an H x W map
+      const Mb2Plan Pr = mb2_plan(geom4[0], geom4[1], geom4[0], geom4[1], 1, N, 128, true);
+      if (!Pr.ok || M % (geom4[0] * geom4[1])) throw std::runtime_error("debug_pw2: bad residual geometry");
+      rp = mb2_patch_layout(Pr, geom4[0], geom4[1]); Bimg = M / (geom4[0] * geom4[1]);
+      rimg = patch_encode(residual, Bimg, rp);
+    }
+    if (out_mode == 2) {
+      const int st = geom4[2], Ho = st == 1 ? geom4[0] : geom4[0] / 2, Wo = st == 1 ? geom4[1] : geom4[1] / 2;
+      const Mb2Plan Po = mb2_plan(geom4[0], geom4[1], Ho, Wo, st, N, geom4[3], true);
+      if (!Po.ok || M % (geom4[0] * geom4[1])) throw std::runtime_error("debug_pw2: bad output geometry");
+      op = mb2_patch_layout(Po, geom4[0], geom4[1]); Bimg = M / (geom4[0] * geom4[1]);
+    }
+    const int o_pitch = (N + 7) / 8 * 8;
+    DevBuf da(aimg.size()), dimg(img.size()), db(bz.size() * 4), dg(gate ? (size_t)chunks * K * 4 : 16), dr(rimg.size()),
+        doh((size_t)M * o_pitch * 2), dol((size_t)M * o_pitch * 2), d32((size_t)M * N * 4), dop(out_mode == 2 ? op.bytes(Bimg) : 16);
+    BNB_CUDA(cudaMemcpy(da.p, aimg.data(), aimg.size(), cudaMemcpyHostToDevice));
     BNB_CUDA(cudaMemcpy(dimg.p, img.data(), img.size(), cudaMemcpyHostToDevice));
     BNB_CUDA(cudaMemcpy(db.p, bz.data(), bz.size() * 4, cudaMemcpyHostToDevice));
     if (gate) BNB_CUDA(cudaMemcpy(dg.p, gate, (size_t)chunks * K * 4, cudaMemcpyHostToDevice));
-    if (residual) { BNB_CUDA(cudaMemcpy(drh.p, rh.data(), rh.size() * 2, cudaMemcpyHostToDevice)); BNB_CUDA(cudaMemcpy(drl.p, rl.data(), rl.size() * 2, cudaMemcpyHostToDevice)); }
+    if (residual) BNB_CUDA(cudaMemcpy(dr.p, rimg.data(), rimg.size(), cudaMemcpyHostToDevice));
     Pw2Launch p{};
-    p.ah = dah.as<__half>(); p.al = dal.as<__half>(); p.a_pitch = a_pitch; p.Wimg = dimg.as<uint8_t>(); p.bias = db.as<float>();
+    p.a_img = da.as<uint8_t>(); p.Wimg = dimg.as<uint8_t>(); p.bias = db.as<float>();
     p.gate = gate ? dg.as<float>() : nullptr;
-    if (residual) { p.rh = drh.as<__half>(); p.rl = drl.as<__half>(); p.r_pitch = o_pitch; }
-    if (planes_out) { p.oh = doh.as<__half>(); p.ol = dol.as<__half>(); p.o_pitch = o_pitch; } else p.out32 = d32.as<float>();
+    if (residual) { p.r_img = dr.as<uint8_t>(); p.r_patch = rp; }
+    if (out_mode == 0) p.out32 = d32.as<float>();
+    else if (out_mode == 1) { p.oh = doh.as<__half>(); p.ol = dol.as<__half>(); p.o_pitch = o_pitch; }
+    else { p.o_img = dop.as<uint8_t>(); p.o_patch = op; }
     p.M = M; p.N = N; p.K = K; p.rows_per_chunk = rows_per_chunk; p.act = act;
     if (info4) { int bn, st, br; size_t sm; pw2_tiling(L, M, gate != nullptr, &bn, &st, &sm, &br); info4[0] = bn; info4[1] = st; info4[2] = br; info4[3] = (int)sm; }
     LaunchCounter lc;
     launch_pw2(L, p, nullptr, lc);
     BNB_CUDA(cudaDeviceSynchronize());
-    if (planes_out) {
+    if (out_mode == 1) {
       std::vector<__half> oh((size_t)M * o_pitch), ol((size_t)M * o_pitch);
       BNB_CUDA(cudaMemcpy(oh.data(), doh.p, oh.size() * 2, cudaMemcpyDeviceToHost));
       BNB_CUDA(cudaMemcpy(ol.data(), dol.p, ol.size() * 2, cudaMemcpyDeviceToHost));
       for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) out[(size_t)m * N + n] = __half2float(oh[(size_t)m * o_pitch + n]) + __half2float(ol[(size_t)m * o_pitch + n]);
+    } else if (out_mode == 2) {
+      std::vector<uint8_t> oi(op.bytes(Bimg));
+      BNB_CUDA(cudaMemcpy(oi.data(), dop.p, oi.size(), cudaMemcpyDeviceToHost));
+      const long long bad = patch_decode(oi.data(), Bimg, op, out);
+      if (bad) throw std::runtime_error("debug_pw2: " + std::to_string(bad) + " halo copies of output pixels disagree");
     } else {
       BNB_CUDA(cudaMemcpy(out, d32.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
     }

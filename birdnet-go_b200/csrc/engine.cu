@@ -127,7 +127,7 @@ void Engine::release() noexcept {
   if (ev_in_) cudaEventDestroy(ev_in_);
   for (void* p : allocs_) cudaFree(p);
   for (auto& kv : keep_bufs_) cudaFree(kv.second.first);
-  for (auto& kv : keep_planes_) { cudaFree(kv.second.first.h); cudaFree(kv.second.first.l); }
+  for (auto& kv : keep_imgs_) cudaFree(kv.second.first);
   if (h_in_) cudaFreeHost(h_in_);
   if (h_out_) cudaFreeHost(h_out_);
   for (cudaEvent_t e : ev_h2d_) cudaEventDestroy(e);
@@ -257,6 +257,7 @@ void Engine::upload_weights(const NetPlan& P) {
       std::vector<float> be((size_t)d.mb2.n_units * 128 + 64, 0.f);
       if (b.expand.b) memcpy(be.data(), b.expand.b, (size_t)b.cexp * sizeof(float));
       d.mb2_bias = up(be.data(), be.size());
+      d.in_patch = mb2_patch_layout(d.mb2, b.in_h, b.in_w);
     }
     blocks_.push_back(d);
   }
@@ -293,23 +294,24 @@ void Engine::alloc_workspace() {
     w.e = dmalloc(cap_n * ce); w.d = dmalloc(cap_n * cd); w.g = dmalloc(cap_n * cg);
     w.sep = dmalloc(cap_n * kMaxDwParts * cg);   // SE partial sums: <= kMaxDwParts parts per chunk (rows, or fused-kernel tiles)
   };
-  // the same for the plane path: x planes hold block inputs / outputs (pitch = channels rounded up to 8), d planes the depthwise output
-  auto alloc_work2 = [&](Work2& w, size_t cap_n, int lo, int hi, size_t cx) {
-    size_t cd = 0, cg = 0;
+  // the same for the plane path: x images hold block inputs / outputs (PatchTiles of the consuming block), d the depthwise output
+  // (RowTiles).  Image buffers are zero-filled once: bytes no kernel writes must stay finite (layouts.h).
+  auto alloc_work2 = [&](Work2& w, size_t cap_n, int lo, int hi) {
+    size_t cx = 0, cd = 0, cg = 0;
     for (int i = lo; i < hi; ++i) {
       const BlockPlan& g = blocks_[i].g;
-      cd = std::max(cd, (size_t)g.out_h * g.out_w * g.cexp);
-      cx = std::max(cx, (size_t)g.out_h * g.out_w * plane_pitch(g.cout));
-      cx = std::max(cx, (size_t)g.in_h * g.in_w * plane_pitch(g.cin));
+      cx = std::max(cx, blocks_[i].in_patch.bytes(1));
+      if (i + 1 < (int)blocks_.size()) cx = std::max(cx, blocks_[i + 1].in_patch.bytes(1));
+      cd = std::max(cd, (size_t)RowTiles::make(g.cexp).tile_bytes * (((size_t)cap_n * g.out_h * g.out_w + 127) / 128));
       cg = std::max(cg, (size_t)g.cexp);
     }
-    w.x_elems = cx; w.d_elems = cd;
-    w.x0 = alloc_planes(cap_n * cx); w.x1 = alloc_planes(cap_n * cx); w.d = alloc_planes(cap_n * cd);
+    w.x_bytes = cx; w.d_bytes = cd;
+    w.x0 = alloc_img(cap_n * cx); w.x1 = alloc_img(cap_n * cx); w.d = alloc_img(cd);
     w.g = dmalloc(cap_n * cg);
     w.sep = dmalloc(cap_n * kMaxDwParts * cg);
   };
   for (int l = 0; l < n_lanes_; ++l) {
-    if (v2_) alloc_work2(lanes_[l].w2, mb, 0, split_, (size_t)stem_.out_h * (stem_.out_w / 2) * 24);
+    if (v2_) alloc_work2(lanes_[l].w2, mb, 0, split_);
     else alloc_work(lanes_[l].w, mb, 0, split_, (size_t)stem_.out_h * (stem_.out_w / 2) * 24);
     lanes_[l].partial = dmalloc(mb * kMinMaxParts * 2);
     lanes_[l].fe = dmalloc(mb * fe_.n_mel * fe_.n_frames * 2);
@@ -319,11 +321,14 @@ void Engine::alloc_workspace() {
   ws_emb_ = dmalloc(bb * emb_dim_);
   const size_t im2col_sz = (size_t)post_g_.out_w * post_g_.conv.kh * post_g_.conv.kw * post_g_.conv.cin;
   if (v2_) {
-    alloc_work2(work2_back_, bb, split_, (int)blocks_.size(), 0);
-    mid_sz_ = (size_t)gs.out_h * gs.out_w * plane_pitch(gs.cout);
-    mid2_ = alloc_planes(bb * mid_sz_);
-    im2col2_ = alloc_planes(bb * im2col_sz);
-    emb2_ = alloc_planes(bb * emb_dim_);
+    alloc_work2(work2_back_, bb, split_, (int)blocks_.size());
+    if (split_ >= (int)blocks_.size()) throw unsupported_model("the network has no small-map blocks for the whole-batch phase");
+    mid2_bytes_ = blocks_[split_].in_patch.bytes(1);                      // the split-point tensor = input image of block `split_`
+    mid2_ = alloc_img(bb * mid2_bytes_);
+    const BlockPlan& gl = blocks_.back().g;
+    last2_ = alloc_planes(bb * gl.out_h * gl.out_w * plane_pitch(gl.cout));   // the last block's output: plain planes for the im2col kernel
+    im2col2_ = alloc_img(RowTiles::make((int)im2col_sz).bytes((long long)bb * post_g_.out_w));
+    emb2_ = alloc_img(RowTiles::make(emb_dim_).bytes((long long)bb));
   } else {
     alloc_work(work_back_, bb, split_, (int)blocks_.size(), 0);
     mid_sz_ = (size_t)gs.out_h * gs.out_w * gs.cout;
@@ -354,17 +359,25 @@ Planes Engine::alloc_planes(size_t elems) {
   return p;
 }
 
-Planes Engine::scratch_planes(int tensor_id, Planes normal, size_t elems_per_chunk, int n) {
+uint8_t* Engine::alloc_img(size_t bytes) {
+  void* q = nullptr;
+  bytes = std::max<size_t>(bytes, 1024);
+  BNB_CUDA(cudaMalloc(&q, bytes)); allocs_.push_back(q);
+  BNB_CUDA(cudaMemset(q, 0, bytes));
+  return static_cast<uint8_t*>(q);
+}
+
+uint8_t* Engine::scratch_img(int tensor_id, uint8_t* normal, size_t bytes_per_chunk, int n) {
   if (!keep_ || tensor_id < 0) return normal;
-  auto it = keep_planes_.find(tensor_id);
-  const size_t need = elems_per_chunk * (size_t)std::max(micro_, n);
-  if (it == keep_planes_.end() || it->second.second < need) {
-    if (it != keep_planes_.end()) { cudaFree(it->second.first.h); cudaFree(it->second.first.l); }
-    Planes p; void* q = nullptr;
-    BNB_CUDA(cudaMalloc(&q, need * sizeof(__half))); p.h = static_cast<__half*>(q);
-    BNB_CUDA(cudaMalloc(&q, need * sizeof(__half))); p.l = static_cast<__half*>(q);
-    keep_planes_[tensor_id] = {p, need};
-    return p;
+  auto it = keep_imgs_.find(tensor_id);
+  const size_t need = bytes_per_chunk * (size_t)std::max(micro_, n) + 65536;
+  if (it == keep_imgs_.end() || it->second.second < need) {
+    if (it != keep_imgs_.end()) cudaFree(it->second.first);
+    void* q = nullptr;
+    BNB_CUDA(cudaMalloc(&q, need));
+    BNB_CUDA(cudaMemset(q, 0, need));
+    keep_imgs_[tensor_id] = {static_cast<uint8_t*>(q), need};
+    return static_cast<uint8_t*>(q);
   }
   return it->second.first;
 }
@@ -435,20 +448,23 @@ float* Engine::run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream
 }
 
 // F16X3 path: every block = mbconv2 (expand + SiLU + depthwise + SiLU + SE sums) -> [SE gate] -> pw2 (project, + gate, + residual).
-// Activations travel as fp16 hi/lo planes; `final_out` (optional) receives the last block's output directly.
-Planes Engine::run_blocks2(int lo, int hi, Planes cur, int n, Work2& w, cudaStream_t s, const Planes* final_out) {
-  Planes nxt_normal = (cur.h == w.x0.h) ? w.x1 : w.x0;
+// Activations travel as fp16 hi/lo images pre-tiled for their consumer (layouts.h): block inputs as PatchTiles, depthwise
+// outputs as RowTiles; every operand tile is one cp.async.bulk.
+void Engine::run_blocks2(int lo, int hi, const uint8_t* cur, int n, Work2& w, cudaStream_t s, uint8_t* final_img, Planes final_plain) {
+  uint8_t* nxt_normal = (cur == w.x0) ? w.x1 : w.x0;
+  const int nb = (int)blocks_.size();
   for (int bi = lo; bi < hi; ++bi) {
     const DevBlock& b = blocks_[bi];
     const BlockPlan& g = b.g;
     const int hw_out = g.out_h * g.out_w;
-    Planes d = scratch_planes(g.dw_tensor, w.d, (size_t)hw_out * g.cexp, n);
+    const RowTiles dt = RowTiles::make(g.cexp);
+    uint8_t* d = scratch_img(g.dw_tensor, w.d, dt.bytes(hw_out) , n);
     Mb2Launch ml{};
-    ml.xh = cur.h; ml.xl = cur.l; ml.x_pitch = plane_pitch(g.cin); ml.Wimg = b.mb2_img; ml.bias_e = b.mb2_bias;
-    ml.w_dw = b.dw.w; ml.bias_dw = b.dw.b; ml.dh = d.h; ml.dl = d.l; ml.partial = g.has_se ? w.sep : nullptr;
+    ml.x_img = cur; ml.Wimg = b.mb2_img; ml.bias_e = b.mb2_bias; ml.w_dw = b.dw.w; ml.bias_dw = b.dw.b; ml.d_img = d;
+    ml.partial = g.has_se ? w.sep : nullptr;
     ml.B = n; ml.H = g.in_h; ml.W = g.in_w; ml.Ho = g.out_h; ml.Wo = g.out_w;
     { ProfScope ps(this, C_PW_EXPAND, s); launch_mbconv2(b.mb2, ml, s, lc_); }
-    record_planes(g.dw_tensor, d, hw_out, g.cexp, n);
+    record_rows(g.dw_tensor, d, hw_out, g.cexp, n);
     float* gate = nullptr;
     if (g.has_se) {
       gate = scratch(g.gate_tensor, w.g, (size_t)g.cexp, n);
@@ -456,43 +472,44 @@ Planes Engine::run_blocks2(int lo, int hi, Planes cur, int n, Work2& w, cudaStre
       { ProfScope ps(this, C_SE, s); launch_se_gate(se, s, lc_); }
       record(g.gate_tensor, gate, (size_t)g.cexp, n);
     }
-    const int op = plane_pitch(g.cout);
-    Planes out = (final_out && bi == hi - 1 && !keep_) ? *final_out : scratch_planes(g.out_tensor, nxt_normal, (size_t)hw_out * op, n);
     Pw2Launch pj{};
-    pj.ah = d.h; pj.al = d.l; pj.a_pitch = g.cexp; pj.Wimg = b.proj.tc_img; pj.bias = b.proj.b; pj.gate = gate;
-    if (g.residual) { pj.rh = cur.h; pj.rl = cur.l; pj.r_pitch = plane_pitch(g.cin); }
-    pj.oh = out.h; pj.ol = out.l; pj.o_pitch = op;
+    pj.a_img = d; pj.Wimg = b.proj.tc_img; pj.bias = b.proj.b; pj.gate = gate;
+    if (g.residual) { pj.r_img = cur; pj.r_patch = b.in_patch; }
     pj.M = n * hw_out; pj.N = g.cout; pj.K = g.cexp; pj.rows_per_chunk = hw_out; pj.act = ACT_NONE;
-    { ProfScope ps(this, C_PW_PROJECT, s); launch_pw2(b.proj.tc, pj, s, lc_); }
-    record_planes(g.out_tensor, out, hw_out, g.cout, n);
-    if (!keep_) nxt_normal = (cur.h == w.x0.h || cur.h == w.x1.h) ? cur : ((out.h == w.x0.h) ? w.x1 : w.x0);
-    cur = out;
+    const uint8_t* out_img = nullptr;
+    if (bi + 1 < nb) {                       // the next block's input image
+      const PatchTiles& nt = blocks_[bi + 1].in_patch;
+      uint8_t* o = (bi == hi - 1 && final_img && !keep_) ? final_img : scratch_img(g.out_tensor, nxt_normal, nt.bytes(1), n);
+      pj.o_img = o; pj.o_patch = nt; out_img = o;
+      { ProfScope ps(this, C_PW_PROJECT, s); launch_pw2(b.proj.tc, pj, s, lc_); }
+      record_patch(g.out_tensor, o, nt, n);
+      if (bi == hi - 1 && final_img && keep_) BNB_CUDA(cudaMemcpyAsync(final_img, o, nt.bytes(n), cudaMemcpyDeviceToDevice, s));
+    } else {                                 // last block of the network: plain planes for the im2col kernel
+      pj.oh = final_plain.h; pj.ol = final_plain.l; pj.o_pitch = plane_pitch(g.cout);
+      { ProfScope ps(this, C_PW_PROJECT, s); launch_pw2(b.proj.tc, pj, s, lc_); }
+      record_planes(g.out_tensor, final_plain, hw_out, g.cout, n);
+    }
+    if (!keep_) nxt_normal = (cur == w.x0 || cur == w.x1) ? const_cast<uint8_t*>(cur) : ((out_img == w.x0) ? w.x1 : w.x0);
+    cur = out_img;
   }
-  if (final_out && keep_ && hi > lo) {   // debug mode kept private buffers: copy the result to where the caller expects it
-    const BlockPlan& g = blocks_[hi - 1].g;
-    const size_t bytes = (size_t)n * g.out_h * g.out_w * plane_pitch(g.cout) * sizeof(__half);
-    BNB_CUDA(cudaMemcpyAsync(final_out->h, cur.h, bytes, cudaMemcpyDeviceToDevice, s));
-    BNB_CUDA(cudaMemcpyAsync(final_out->l, cur.l, bytes, cudaMemcpyDeviceToDevice, s));
-    cur = *final_out;
-  }
-  return cur;
 }
 
-void Engine::run_back2(Planes mid, int n, float* d_logits, float* d_emb, cudaStream_t s) {
-  Planes cur = run_blocks2(split_, (int)blocks_.size(), mid, n, work2_back_, s, nullptr);
+void Engine::run_back2(int n, float* d_logits, float* d_emb, cudaStream_t s) {
+  run_blocks2(split_, (int)blocks_.size(), mid2_, n, work2_back_, s, nullptr, last2_);
   const PostPlan& q = post_g_;
-  { ProfScope ps(this, C_POST_CONV, s); launch_post_prep2(cur.h, cur.l, post_mul_, post_add_, im2col2_.h, im2col2_.l, n, q.conv.kh, q.conv.kw, q.in_w, q.out_w, q.conv.cin, s, lc_); }
+  const int kpost = q.conv.kh * q.conv.kw * q.conv.cin;
+  { ProfScope ps(this, C_POST_CONV, s); launch_post_prep2(last2_.h, last2_.l, post_mul_, post_add_, im2col2_, n, q.conv.kh, q.conv.kw, q.in_w, q.out_w, q.conv.cin, s, lc_); }
   float* pc = scratch(q.conv_tensor, ws_pc_, (size_t)q.out_w * q.conv.cout, n);
   Pw2Launch pa{};
-  pa.ah = im2col2_.h; pa.al = im2col2_.l; pa.a_pitch = q.conv.kh * q.conv.kw * q.conv.cin; pa.Wimg = post_conv_.tc_img; pa.bias = post_conv_.b;
-  pa.out32 = pc; pa.M = n * q.out_w; pa.N = q.conv.cout; pa.K = pa.a_pitch; pa.rows_per_chunk = q.out_w; pa.act = ACT_RELU;
+  pa.a_img = im2col2_; pa.Wimg = post_conv_.tc_img; pa.bias = post_conv_.b;
+  pa.out32 = pc; pa.M = n * q.out_w; pa.N = q.conv.cout; pa.K = kpost; pa.rows_per_chunk = q.out_w; pa.act = ACT_RELU;
   { ProfScope ps(this, C_POST_CONV, s); launch_pw2(post_conv_.tc, pa, s, lc_); }
   record(q.conv_tensor, pc, (size_t)q.out_w * q.conv.cout, n);
   float* emb = d_emb ? d_emb : ws_emb_;
-  { ProfScope ps(this, C_ROW_MEAN, s); launch_row_mean2(pc, emb, emb2_.h, emb2_.l, n, q.out_w, q.conv.cout, s, lc_); }
+  { ProfScope ps(this, C_ROW_MEAN, s); launch_row_mean2(pc, emb, emb2_, n, q.out_w, q.conv.cout, s, lc_); }
   record(q.emb_tensor, emb, (size_t)emb_dim_, n);
   Pw2Launch fa{};
-  fa.ah = emb2_.h; fa.al = emb2_.l; fa.a_pitch = emb_dim_; fa.Wimg = fc_.tc_img; fa.bias = fc_.b; fa.out32 = d_logits;
+  fa.a_img = emb2_; fa.Wimg = fc_.tc_img; fa.bias = fc_.b; fa.out32 = d_logits;
   fa.M = n; fa.N = n_species_; fa.K = emb_dim_; fa.rows_per_chunk = 1; fa.act = ACT_NONE;
   { ProfScope ps(this, C_FC, s); launch_pw2(fc_.tc, fa, s, lc_); }
   record(logits_tensor_, d_logits, (size_t)n_species_, n);
@@ -510,12 +527,12 @@ void Engine::run_front(const void* d_pcm, int fmt, int n, int chunk0, Lane& L, c
   const size_t stem_sz = (size_t)stem_.out_h * stem_.out_w * 24, mix_sz = stem_sz / 2;
   float* stem_dump = keep_ ? scratch(stem_tensor_, nullptr, stem_sz, n) : nullptr;
   if (v2_) {
-    Planes cur = scratch_planes(mix_tensor_, L.w2.x0, mix_sz, n);
-    { ProfScope ps(this, C_STEM_MIX, s); launch_stem_mix(stem_, fe_out, stem_dump, nullptr, n, s, lc_, cur.h, cur.l); }
+    const PatchTiles& p0 = blocks_[0].in_patch;
+    uint8_t* cur = scratch_img(mix_tensor_, L.w2.x0, p0.bytes(1), n);
+    { ProfScope ps(this, C_STEM_MIX, s); launch_stem_mix(stem_, fe_out, stem_dump, nullptr, n, s, lc_, cur, &p0); }
     if (stem_dump) record(stem_tensor_, stem_dump, stem_sz, n);
-    record_planes(mix_tensor_, cur, (int)(mix_sz / 24), 24, n);
-    const Planes mid{mid2_.h + (size_t)chunk0 * mid_sz_, mid2_.l + (size_t)chunk0 * mid_sz_};
-    run_blocks2(0, split_, cur, n, L.w2, s, &mid);
+    record_patch(mix_tensor_, cur, p0, n);
+    run_blocks2(0, split_, cur, n, L.w2, s, mid2_ + (size_t)chunk0 * mid2_bytes_, Planes());
     return;
   }
   float* cur = scratch(mix_tensor_, w.x0, mix_sz, n);
@@ -528,7 +545,7 @@ void Engine::run_front(const void* d_pcm, int fmt, int n, int chunk0, Lane& L, c
 
 // blocks [split_, end) -> post conv -> embedding -> FC head over `n` chunks at once
 void Engine::run_back(const float* mid, int n, float* d_logits, float* d_emb, cudaStream_t s) {
-  if (v2_) { run_back2(mid2_, n, d_logits, d_emb, s); return; }
+  if (v2_) { run_back2(n, d_logits, d_emb, s); return; }
   Work& w = work_back_;
   BNB_CUDA(cudaMemcpyAsync(w.x0, mid, (size_t)n * mid_sz_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
   float* cur = run_blocks(split_, (int)blocks_.size(), w.x0, n, w, s);
@@ -713,6 +730,32 @@ long long Engine::read_tensor(int tensor, float* out, size_t cap) {
   const size_t n = it->second.per_chunk * (size_t)it->second.chunks;
   if (n > cap) return BNB_ERR_INVALID_ARGUMENT;
   BNB_CUDA(cudaDeviceSynchronize());
+  if (it->second.kind == 2 || it->second.kind == 3) {      // pre-tiled hi/lo image: gather + join on the host (test hook)
+    const TensorView& v = it->second;
+    const long long pixels = (long long)(n / (size_t)v.ch);
+    const int c8n = (v.ch + 7) / 8;
+    const size_t bytes = v.kind == 2 ? RowTiles::make(v.ch).bytes(pixels) : v.patch.bytes(v.chunks);
+    std::vector<uint8_t> img(bytes);
+    BNB_CUDA(cudaMemcpy(img.data(), v.img, bytes, cudaMemcpyDeviceToHost));
+    const RowTiles rt = RowTiles::make(v.ch);
+    for (long long m = 0; m < pixels; ++m)
+      for (int c8 = 0; c8 < c8n; ++c8) {
+        size_t off_hi, lo_delta;
+        if (v.kind == 2) { off_hi = rt.piece(m, c8); lo_delta = 16384; }
+        else {
+          int b, h, w, ty, tx, pr, pc, st, chunk;
+          v.patch.split_pixel((uint32_t)m, &b, &h, &w);
+          v.patch.stage_of(c8, &st, &chunk);
+          bool found = false;
+          v.patch.for_each_tile(h, w, [&](int y, int x, int r, int c) { if (!found) { ty = y; tx = x; pr = r; pc = c; found = true; } });
+          off_hi = v.patch.tile_base(b, ty, tx) + v.patch.in_tile(pr, pc, st, chunk); lo_delta = v.patch.st_plane[st];
+        }
+        const __half* hp = reinterpret_cast<const __half*>(img.data() + off_hi);
+        const __half* lp = reinterpret_cast<const __half*>(img.data() + off_hi + lo_delta);
+        for (int e = 0; e < 8 && 8 * c8 + e < v.ch; ++e) out[(size_t)m * v.ch + 8 * c8 + e] = __half2float(hp[e]) + __half2float(lp[e]);
+      }
+    return (long long)n;
+  }
   if (it->second.h != nullptr) {            // fp16 hi/lo planes: join and drop the pitch padding on the host
     const TensorView& v = it->second;
     const size_t pixels = n / (size_t)v.ch, elems = pixels * (size_t)v.pitch;

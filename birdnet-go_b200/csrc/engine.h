@@ -23,8 +23,9 @@ struct DevConv { const float* w = nullptr; const float* b = nullptr; PwTcLayer t
 struct DevBlock {
   BlockPlan g;          // geometry + tensor ids (host weight pointers are dead after upload)
   DevConv expand, dw, se1, se2, proj;
-  // F16X3 path (mbconv2.cu): tile plan, (unit, stage) weight image, expand bias padded to whole units
-  Mb2Plan mb2; const uint8_t* mb2_img = nullptr; const float* mb2_bias = nullptr;
+  // F16X3 path (mbconv2.cu): tile plan, (unit, stage) weight image, expand bias padded to whole units, and the PatchTiles
+  // layout of the block INPUT (what the producer of this block's input must write)
+  Mb2Plan mb2; const uint8_t* mb2_img = nullptr; const float* mb2_bias = nullptr; PatchTiles in_patch;
 };
 
 // fp16 hi / lo planes of one activation tensor (x ~= hi + lo); `pitch` = channels per pixel in memory (multiple of 8)
@@ -33,7 +34,9 @@ inline int plane_pitch(int c) { return (c + 7) / 8 * 8; }
 
 struct TensorView {
   const float* ptr = nullptr; size_t per_chunk = 0; int chunks = 0;
-  const __half* h = nullptr; const __half* l = nullptr; int pitch = 0, ch = 0;     // plane tensors: per_chunk counts pixels * ch
+  const __half* h = nullptr; const __half* l = nullptr; int pitch = 0, ch = 0;     // plain plane tensors: per_chunk counts pixels * ch
+  const uint8_t* img = nullptr; int kind = 0;                                      // kind 2: RowTiles image (ch = K), 3: PatchTiles image
+  PatchTiles patch;
 };
 
 class Engine {
@@ -75,20 +78,30 @@ class Engine {
   void pw(const PwArgs& a, const DevConv& c, int cat, cudaStream_t s);
   static constexpr int kMaxDwParts = 32;
   struct Work { float *x0 = nullptr, *x1 = nullptr, *e = nullptr, *d = nullptr, *g = nullptr, *sep = nullptr; size_t cap_n = 0; };
-  struct Work2 { Planes x0, x1, d; float* g = nullptr; float* sep = nullptr; size_t x_elems = 0, d_elems = 0; };   // F16X3 plane path
+  // F16X3 path: x0/x1 = block input / output as PatchTiles images, d = depthwise output as a RowTiles image (bytes per chunk)
+  struct Work2 { uint8_t *x0 = nullptr, *x1 = nullptr, *d = nullptr; float* g = nullptr; float* sep = nullptr; size_t x_bytes = 0, d_bytes = 0; };
   static constexpr int kMaxLanes = 4;
   struct Lane { Work w; Work2 w2; float* partial = nullptr; float* fe = nullptr; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; };
   float* run_blocks(int lo, int hi, float* cur, int n, Work& w, cudaStream_t s);
   // ---- F16X3 path on fp16 hi/lo planes (mbconv2.cu + pw2.cu) ----
-  Planes run_blocks2(int lo, int hi, Planes cur, int n, Work2& w, cudaStream_t s, const Planes* final_out);
-  void run_back2(Planes mid, int n, float* d_logits, float* d_emb, cudaStream_t s);
-  Planes scratch_planes(int tensor_id, Planes normal, size_t elems_per_chunk, int n);
+  // blocks [lo, hi): input `cur` (PatchTiles image of block lo).  The last block writes `final_img` (the PatchTiles image of
+  // block hi, when hi < #blocks) or, for the last block of the network, the plain planes `final_plain`.
+  void run_blocks2(int lo, int hi, const uint8_t* cur, int n, Work2& w, cudaStream_t s, uint8_t* final_img, Planes final_plain);
+  void run_back2(int n, float* d_logits, float* d_emb, cudaStream_t s);
+  uint8_t* scratch_img(int tensor_id, uint8_t* normal, size_t bytes_per_chunk, int n);
+  void record_rows(int tensor_id, const uint8_t* img, int rows_per_chunk, int K, int n) {
+    if (tensor_id >= 0) { TensorView v; v.per_chunk = (size_t)rows_per_chunk * K; v.chunks = n; v.img = img; v.kind = 2; v.ch = K; views_[tensor_id] = v; }
+  }
+  void record_patch(int tensor_id, const uint8_t* img, const PatchTiles& t, int n) {
+    if (tensor_id >= 0) { TensorView v; v.per_chunk = (size_t)t.H * t.W * t.C; v.chunks = n; v.img = img; v.kind = 3; v.ch = t.C; v.patch = t; views_[tensor_id] = v; }
+  }
   void record_planes(int tensor_id, Planes p, int pixels, int ch, int n) {
     if (tensor_id >= 0) { TensorView v; v.per_chunk = (size_t)pixels * ch; v.chunks = n; v.h = p.h; v.l = p.l; v.pitch = plane_pitch(ch); v.ch = ch; views_[tensor_id] = v; }
   }
   Planes alloc_planes(size_t elems);
-  bool v2_ = false;        // F16X3 precision: every block runs mbconv2 + pw2 on planes
-  Work2 work2_back_; Planes mid2_, im2col2_, emb2_;
+  uint8_t* alloc_img(size_t bytes);
+  bool v2_ = false;        // F16X3 precision: every block runs mbconv2 + pw2 on pre-tiled fp16 hi/lo images
+  Work2 work2_back_; uint8_t* mid2_ = nullptr; size_t mid2_bytes_ = 0; uint8_t *im2col2_ = nullptr, *emb2_ = nullptr; Planes last2_;
   void run_front(const void* d_pcm, int fmt, int n, int chunk0, Lane& L, cudaStream_t s);   // chunk0: slot of the first chunk in the split-point buffer
   void run_back(const float* mid, int n, float* d_logits, float* d_emb, cudaStream_t s);
   float* scratch(int tensor_id, float* normal, size_t per_chunk, int n);
@@ -136,7 +149,7 @@ class Engine {
   int split_ = 0;         // first block of the back phase
   size_t mid_sz_ = 0;     // floats per chunk of the split-point tensor
   std::map<int, std::pair<float*, size_t>> keep_bufs_;   // tensor id -> (device buffer, capacity in floats)
-  std::map<int, std::pair<Planes, size_t>> keep_planes_; // tensor id -> (plane pair, capacity in elements)
+  std::map<int, std::pair<uint8_t*, size_t>> keep_imgs_;  // tensor id -> (image buffer, capacity in bytes)
   std::map<int, TensorView> views_;
 
   // full-batch device buffers for the host path

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "common.cuh"
+#include "layouts.h"
 
 namespace bnb {
 
@@ -48,9 +49,9 @@ struct StemMixDev {
   const float* b_mix;   // [24]
   int in_h, in_w, out_h, out_w, pad_t, pad_l;   // 96, 511, 48, 256, 1, 3
 };
-// out_h / out_l != null: write the result as fp16 hi / lo planes (F16X3 path) instead of fp32 `out`
+// out_img != null: write the result as fp16 hi / lo planes into the PatchTiles image block 1 reads (F16X3 path) instead of fp32 `out`
 void launch_stem_mix(const StemMixDev& p, const float* in, float* stem_out_or_null, float* out, int B,
-                     cudaStream_t s, LaunchCounter& lc, __half* out_h = nullptr, __half* out_l = nullptr);
+                     cudaStream_t s, LaunchCounter& lc, uint8_t* out_img = nullptr, const PatchTiles* out_patch = nullptr);
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_SIGMOID = 3 };
 
@@ -100,9 +101,10 @@ void launch_post_prep(const float* in, const float* mul, const float* add, float
 // mean over `rows` consecutive rows: in [B][rows][C] -> out [B][C]
 void launch_row_mean(const float* in, float* out, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc);
 // the same two helpers on fp16 hi/lo planes (F16X3 path)
-void launch_post_prep2(const __half* ih, const __half* il, const float* mul, const float* add, __half* oh, __half* ol, int B, int kh, int kw,
+// (outputs are RowTiles images: the A operands of the post-conv GEMM and of the FC head)
+void launch_post_prep2(const __half* ih, const __half* il, const float* mul, const float* add, uint8_t* o_img, int B, int kh, int kw,
                        int in_w, int out_w, int cin, cudaStream_t s, LaunchCounter& lc);
-void launch_row_mean2(const float* in, float* out, __half* oh, __half* ol, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc);
+void launch_row_mean2(const float* in, float* out, uint8_t* o_img, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc);
 
 // ---------------------------------------------------------------- post-processing (post.cu)
 // conf = sigmoid(sensitivity * logit) (float64 exp like analyze.go:113-115), top-k descending, ties -> lower index

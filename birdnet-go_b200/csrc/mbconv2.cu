@@ -25,12 +25,13 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
 #include "tc_common.cuh"
-#include "tma_host.h"
 
 namespace bnb {
 
@@ -38,22 +39,30 @@ namespace {
 
 using namespace tc;
 
-constexpr int kGroups = 3;
+constexpr int kGroups = 4;          // epilogue groups = accumulator buffers in flight (profiles/r02: one warp per lane quarter and unit is
+                                    // latency-bound at ~0.25 IPC, so throughput comes from units in flight: 4 x narrower tiles beat 3 x wide ones)
 constexpr int kEpiWarps = 4 * kGroups, kMmaWarp = kEpiWarps, kLoadBWarp = kEpiWarps + 1, kLoadAWarp = kEpiWarps + 2;
 constexpr int kThreads = (kEpiWarps + 3) * 32;
 constexpr int kTmemCols = 512;
 
 struct Mb2Args {
   const uint8_t* Wimg; const float* bias_e; const float* w_dw; const float* bias_dw;
-  __half* dh; __half* dl; float* partial;
+  const uint8_t* x_img; uint8_t* d_img; uint32_t d_tile_bytes; float* partial;
   int B, H, W, C, Ho, Wo;
   int TH, PH, n_mma, tiles_h, tiles_w;
   int n_units, k_stages, rot_mode;       // rot_mode: 0 none, 1 last unit replicated over the four lane quarters, 2 four rotated versions of the only unit
   int a_slots, b_slots, a_resident, n_img_units;
-  uint32_t a_slot_bytes, a_region_bytes, b_slot_bytes, img_unit_bytes, b_tx_bytes;
+  uint32_t a_slot_bytes, a_region_bytes, b_slot_bytes, img_unit_bytes;
+  long long* trace;                      // debug timeline (BNB_MB2_TRACE): [2 CTAs][8 events][64 slots] clock64 stamps, else null
   uint32_t st_rb[kMb2MaxStages], st_ksteps[kMb2MaxStages], st_k0[kMb2MaxStages], st_aoff[kMb2MaxStages],
-      st_aplane[kMb2MaxStages], st_boff[kMb2MaxStages], st_bplane[kMb2MaxStages], st_map[kMb2MaxStages];
+      st_aplane[kMb2MaxStages], st_boff[kMb2MaxStages], st_bplane[kMb2MaxStages];
 };
+
+// events: 0 kernel start, 1 patch load issued, 2 patch landed (MMA saw it), 3 unit MMAs committed, 4 accumulator seen by
+// the epilogue group, 5 accumulator released (all rows read), 6 unit done (stores issued), 7 kernel end.  Index = tile
+// iteration (events 1, 2) or unit sequence number (3..6).  CTA 0 and the last CTA are recorded.
+#define MB2_TRACE(ev, i) do { if (a.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (i) < 64) \
+    a.trace[((blockIdx.x == 0 ? 0 : 1) * 8 + (ev)) * 64 + (i)] = clock64(); } while (0)
 
 template <int PW>
 __device__ __forceinline__ void load_row(float (&dst)[PW], uint32_t taddr, bool row_in, bool left_oob, bool right_oob, float be) {
@@ -67,14 +76,21 @@ __device__ __forceinline__ void load_row(float (&dst)[PW], uint32_t taddr, bool 
   tmem_ld_wait();
 #pragma unroll
   for (int i = 0; i < PW; ++i) dst[i] = __uint_as_float(raw[i]) + be;
-  silu_n<PW>(dst);
-  if (left_oob) dst[0] = 0.f;                     // zero padding lives in the EXPANDED domain
+  // zero padding lives in the EXPANDED domain.  The columns outside the image hold whatever the patch image held before
+  // (they are never written): zero them BEFORE the SiLU — silu(0) = 0, and the shared reciprocal of a group of four must
+  // not depend on stale data (it would change the last bits of the three valid neighbours: results must be bit-identical
+  // whatever ran in the buffer before).
+  if (left_oob) dst[0] = 0.f;
   if (right_oob) dst[PW - 1] = 0.f;
+  silu_n<PW>(dst);
 }
 
+// TW outputs of one output row from three SiLU'd patch rows.  `prow` points at this thread's 2-byte slot of output 0 in the hi
+// plane of the RowTiles image (row r0 = multiple of TW; the swizzle term of output o is ((o + (r0 & 7)) & 7): r0_lo = r0 & 7
+// is 0 for TW = 8 and 0 or 4 for TW = 4); chunk16 = this channel's 16-byte chunk index << 4; the lo plane is + 16384.
 template <int S, int TW, int PW>
 __device__ __forceinline__ void out_row(const float (&r0)[PW], const float (&r1)[PW], const float (&r2)[PW], const float (&wd)[9],
-                                        float bd, __half* ph, __half* pl, int C, bool active, float& lsum) {
+                                        float bd, uint8_t* prow, uint32_t chunk16, uint32_t r0_lo, bool active, float& lsum) {
 #pragma unroll
   for (int o = 0; o < TW; o += 4) {
     float acc[4];
@@ -92,20 +108,20 @@ __device__ __forceinline__ void out_row(const float (&r0)[PW], const float (&r1)
       lsum += acc[0]; lsum += acc[1]; lsum += acc[2]; lsum += acc[3];        // fixed order: deterministic SE sums
       uint32_t h01, l01, h23, l23;
       split2(acc[0], acc[1], h01, l01); split2(acc[2], acc[3], h23, l23);
-      unsigned short* qh = reinterpret_cast<unsigned short*>(ph) + (size_t)o * C;
-      unsigned short* ql = reinterpret_cast<unsigned short*>(pl) + (size_t)o * C;
-      qh[0] = (unsigned short)(h01 & 0xffffu); ql[0] = (unsigned short)(l01 & 0xffffu);
-      qh[C] = (unsigned short)(h01 >> 16);     ql[C] = (unsigned short)(l01 >> 16);
-      qh[2 * C] = (unsigned short)(h23 & 0xffffu); ql[2 * C] = (unsigned short)(l23 & 0xffffu);
-      qh[3 * C] = (unsigned short)(h23 >> 16);     ql[3 * C] = (unsigned short)(l23 >> 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = (uint32_t)(o + i) * 128u + (chunk16 ^ ((((uint32_t)(o + i) + r0_lo) & 7u) << 4));
+        const uint32_t hw = i < 2 ? h01 : h23, lw = i < 2 ? l01 : l23;
+        *reinterpret_cast<unsigned short*>(prow + off) = (unsigned short)((i & 1) ? (hw >> 16) : (hw & 0xffffu));
+        *reinterpret_cast<unsigned short*>(prow + off + 16384) = (unsigned short)((i & 1) ? (lw >> 16) : (lw & 0xffffu));
+      }
     }
   }
 }
 
 template <int S, int TW>
 __global__ void __launch_bounds__(kThreads, 1)
-mbconv2_kernel(const Mb2Args a, const __grid_constant__ CUtensorMap m_hi0, const __grid_constant__ CUtensorMap m_lo0,
-               const __grid_constant__ CUtensorMap m_hi1, const __grid_constant__ CUtensorMap m_lo1) {
+mbconv2_kernel(const Mb2Args a) {
   constexpr int PW = (TW - 1) * S + 3;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -149,25 +165,18 @@ mbconv2_kernel(const Mb2Args a, const __grid_constant__ CUtensorMap m_hi0, const
 
   const int tiles_per_chunk = a.tiles_h * a.tiles_w;
   const int total_tiles = a.B * tiles_per_chunk;
+  if (threadIdx.x == 0) MB2_TRACE(0, 0);
 
   if (warp == kLoadBWarp) {
-    // ============================== patch loader: per tile, one 4-D TMA box per (stage, plane) ======================
+    // ============================== patch loader: the tile's whole shared-memory slot is ONE contiguous image in memory ===
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int b = tile / tiles_per_chunk, tt = tile - b * tiles_per_chunk;
-        const int ty = tt / a.tiles_w, tx = tt - ty * a.tiles_w;
-        const int hi0 = ty * a.TH * S - 1, wi0 = tx * TW * S - 1;
         const int bs = it % a.b_slots; const uint32_t ph = (it / a.b_slots) & 1;
         mbar_wait_relaxed(b_empty(bs), ph ^ 1);
-        mbar_arrive_expect_tx(b_full(bs), a.b_tx_bytes);
-        for (int s = 0; s < a.k_stages; ++s) {
-          const uint32_t dst = b_ring + (uint32_t)bs * a.b_slot_bytes + a.st_boff[s];
-          const CUtensorMap* mh = a.st_map[s] ? &m_hi1 : &m_hi0;
-          const CUtensorMap* ml = a.st_map[s] ? &m_lo1 : &m_lo0;
-          tma_load_4d(dst, mh, (int)a.st_k0[s], wi0, hi0, b, b_full(bs));
-          tma_load_4d(dst + a.st_bplane[s], ml, (int)a.st_k0[s], wi0, hi0, b, b_full(bs));
-        }
+        mbar_arrive_expect_tx(b_full(bs), a.b_slot_bytes);
+        bulk_g2s(b_ring + (uint32_t)bs * a.b_slot_bytes, a.x_img + (size_t)tile * a.b_slot_bytes, a.b_slot_bytes, b_full(bs));
+        MB2_TRACE(1, it);
       }
     }
   } else if (warp == kLoadAWarp) {
@@ -200,6 +209,7 @@ mbconv2_kernel(const Mb2Args a, const __grid_constant__ CUtensorMap m_hi0, const
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int bs = it % a.b_slots;
         mbar_wait(b_full(bs), (it / a.b_slots) & 1);
+        MB2_TRACE(2, it);
         const int rot = it & 3;
         for (int u = 0; u < a.n_units; ++u) {
           const uint32_t seq = it * a.n_units + u;
@@ -226,6 +236,7 @@ mbconv2_kernel(const Mb2Args a, const __grid_constant__ CUtensorMap m_hi0, const
             if (!a.a_resident) umma_commit(a_empty(slot));
           }
           umma_commit(t_full(buf));
+          MB2_TRACE(3, seq);
         }
         umma_commit(b_empty(bs));
       }
@@ -265,18 +276,22 @@ mbconv2_kernel(const Mb2Args a, const __grid_constant__ CUtensorMap m_hi0, const
         if (active) { bd = __ldg(a.bias_dw + c); be = __ldg(a.bias_e + c); }
         mbar_wait(t_full(g), par);
         tc_fence_after();
+        if (lane == 0 && quarter == 0) MB2_TRACE(4, seq);
 
         float lsum = 0.f;
         float rA[PW], rB[PW], rC[PW];
         auto ld = [&](float (&dst)[PW], int r) {
           const int hi = hi0 + r;
           load_row<PW>(dst, tbuf + (uint32_t)(r * PW), hi >= 0 && hi < a.H, left_oob, right_oob, be);
-          if (r == a.PH - 1) { tc_fence_before(); mbar_arrive(t_empty(g)); }     // accumulator fully read: hand the buffer back
+          if (r == a.PH - 1) { tc_fence_before(); mbar_arrive(t_empty(g)); if (lane == 0 && quarter == 0) MB2_TRACE(5, seq); }     // accumulator fully read: hand the buffer back
         };
-        const size_t out_base = (((size_t)b * a.Ho + ho0) * a.Wo + wo0) * a.C + c;
-        const size_t row_elems = (size_t)a.Wo * a.C;
+        // RowTiles image of the result: row m = (b*Ho + ho)*Wo + wo, 64-channel stage c >> 6, chunk (c >> 3) & 7
+        const uint32_t m_tile0 = ((uint32_t)b * a.Ho + ho0) * a.Wo + wo0;
+        uint8_t* const out_c = a.d_img + (size_t)(c >> 6) * 32768u + (size_t)(c & 7) * 2u;
+        const uint32_t chunk16 = (uint32_t)((c >> 3) & 7) << 4;
         auto out = [&](const float (&r0)[PW], const float (&r1)[PW], const float (&r2)[PW], int oh) {
-          out_row<S, TW, PW>(r0, r1, r2, wd, bd, a.dh + out_base + (size_t)oh * row_elems, a.dl + out_base + (size_t)oh * row_elems, a.C, active, lsum);
+          const uint32_t m = m_tile0 + (uint32_t)oh * a.Wo;
+          out_row<S, TW, PW>(r0, r1, r2, wd, bd, out_c + (size_t)(m >> 7) * a.d_tile_bytes + (m & 127u) * 128u, chunk16, m & 7u, active, lsum);
         };
         if (S == 1) {
           ld(rA, 0); ld(rB, 1);
@@ -294,12 +309,14 @@ mbconv2_kernel(const Mb2Args a, const __grid_constant__ CUtensorMap m_hi0, const
           }
         }
         if (a.partial != nullptr && active) a.partial[((size_t)b * tiles_per_chunk + tt) * a.C + c] = lsum;
+        if (lane == 0 && quarter == 0) MB2_TRACE(6, seq);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) MB2_TRACE(7, 0);
   if (warp == kMmaWarp) {
     __syncwarp();
     tc_fence_after();
@@ -319,8 +336,7 @@ Mb2Plan mb2_plan(int H, int W, int Ho, int Wo, int stride, int Cin, int C, bool 
   P.S = stride; P.Cin = Cin; P.C = C;
   if (stride != 1 && stride != 2) return P;
   if (stride == 1) { if (H != Ho || W != Wo) return P; } else { if (H != 2 * Ho || W != 2 * Wo) return P; }
-  if (stride == 1) P.TW = (Wo % 16 == 0) ? 16 : ((Wo % 8 == 0) ? 8 : 0);
-  else P.TW = (Wo % 8 == 0) ? 8 : 0;
+  P.TW = stride == 1 ? ((Wo % 8 == 0) ? 8 : 0) : ((Wo % 4 == 0) ? 4 : 0);
   if (P.TW == 0 || C % 8 || Cin % 4 || Cin > 64 * kMb2MaxStages) return P;
   P.PW = (P.TW - 1) * stride + 3;
   for (int th = Ho; th >= 1; --th) {
@@ -421,54 +437,78 @@ void mb2_prepare_weights(const Mb2Plan& P, const float* w, std::vector<uint8_t>*
   }
 }
 
-namespace {
-template <int S, int TW>
-void launch_t(const Mb2Args& a, const CUtensorMap* m, int grid, size_t smem, cudaStream_t s) {
-  mbconv2_kernel<S, TW><<<grid, kThreads, smem, s>>>(a, m[0], m[1], m[2], m[3]);
+PatchTiles mb2_patch_layout(const Mb2Plan& P, int H, int W) {
+  PatchTiles t;
+  t.H = H; t.W = W; t.C = P.Cin; t.S = P.S; t.TH = P.TH; t.TW = P.TW; t.PH = P.PH; t.PW = P.PW;
+  t.tiles_h = P.tiles_h; t.tiles_w = P.tiles_w;
+  auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  if ((W & (W - 1)) || (P.TW & (P.TW - 1))) throw std::runtime_error("mbconv2: map width and tile width must be powers of two");
+  t.log2W = ilog2(W); t.log2TW = ilog2(P.TW);
+  t.n_stages = P.k_stages;
+  for (int s = 0; s < P.k_stages; ++s) { t.st_rb[s] = P.st_rb[s]; t.st_k0[s] = P.st_k0[s]; t.st_off[s] = P.st_boff[s]; t.st_plane[s] = P.st_bplane[s]; }
+  t.tile_bytes = P.b_slot_bytes;
+  const uint32_t T = (uint32_t)(P.TH * P.S);
+  t.magic_t = (65536u + T - 1) / T;
+  t.hw = (uint32_t)(H * W);
+  t.magic_hw = (uint32_t)((1ull << 32) / t.hw);
+  return t;
 }
-}  // namespace
 
 void mb2_set_attributes() {
-  BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
   BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
-  BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
+  BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
 }
 
 void launch_mbconv2(const Mb2Plan& P, const Mb2Launch& L, cudaStream_t s, LaunchCounter& lc) {
   if (!P.ok) throw std::runtime_error("mbconv2: layer has no plan");
-  if (L.x_pitch % 8) throw std::runtime_error("mbconv2: input plane pitch must be a multiple of 8 channels");
   Mb2Args a{};
-  a.Wimg = L.Wimg; a.bias_e = L.bias_e; a.w_dw = L.w_dw; a.bias_dw = L.bias_dw; a.dh = L.dh; a.dl = L.dl; a.partial = L.partial;
+  a.Wimg = L.Wimg; a.bias_e = L.bias_e; a.w_dw = L.w_dw; a.bias_dw = L.bias_dw; a.x_img = L.x_img; a.d_img = L.d_img;
+  a.d_tile_bytes = RowTiles::make(P.C).tile_bytes; a.partial = L.partial;
   a.B = L.B; a.H = L.H; a.W = L.W; a.C = P.C; a.Ho = L.Ho; a.Wo = L.Wo;
   a.TH = P.TH; a.PH = P.PH; a.n_mma = P.n_mma; a.tiles_h = P.tiles_h; a.tiles_w = P.tiles_w;
   a.n_units = P.n_units; a.k_stages = P.k_stages; a.rot_mode = rot_mode_of(P);
   a.a_slots = P.a_slots; a.b_slots = P.b_slots; a.a_resident = P.a_resident; a.n_img_units = a.rot_mode == 2 ? 4 : P.n_units;
-  a.a_slot_bytes = P.a_slot_bytes; a.a_region_bytes = P.a_region_bytes; a.b_slot_bytes = P.b_slot_bytes; a.img_unit_bytes = P.img_unit_bytes; a.b_tx_bytes = P.b_tx_bytes;
-  CUtensorMap maps[4];
-  int n_maps = 0, map_rb[2] = {0, 0}, map_kw[2] = {0, 0};
+  a.a_slot_bytes = P.a_slot_bytes; a.a_region_bytes = P.a_region_bytes; a.b_slot_bytes = P.b_slot_bytes; a.img_unit_bytes = P.img_unit_bytes;
   for (int st = 0; st < P.k_stages; ++st) {
     a.st_rb[st] = P.st_rb[st]; a.st_ksteps[st] = P.st_ksteps[st]; a.st_k0[st] = P.st_k0[st]; a.st_aoff[st] = P.st_aoff[st];
     a.st_aplane[st] = P.st_aplane[st]; a.st_boff[st] = P.st_boff[st]; a.st_bplane[st] = P.st_bplane[st];
-    int mi = -1;
-    for (int j = 0; j < n_maps; ++j) if (map_rb[j] == P.st_rb[st] && map_kw[j] == P.st_kw[st]) mi = j;
-    if (mi < 0) {
-      if (n_maps == 2) throw std::runtime_error("mbconv2: more than two distinct stage shapes");
-      mi = n_maps++; map_rb[mi] = P.st_rb[st]; map_kw[mi] = P.st_kw[st];
-      const uint64_t dims[4] = {(uint64_t)P.Cin, (uint64_t)L.W, (uint64_t)L.H, (uint64_t)L.B};
-      const uint64_t strides[3] = {(uint64_t)L.x_pitch * 2, (uint64_t)L.W * L.x_pitch * 2, (uint64_t)L.H * L.W * L.x_pitch * 2};
-      const uint32_t box[4] = {(uint32_t)P.st_kw[st], (uint32_t)P.PW, (uint32_t)P.PH, 1};
-      maps[2 * mi] = tma_encode(L.xh, 2, 4, dims, strides, box, P.st_rb[st]);
-      maps[2 * mi + 1] = tma_encode(L.xl, 2, 4, dims, strides, box, P.st_rb[st]);
-    }
-    a.st_map[st] = (uint32_t)mi;
   }
-  if (n_maps == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
   const long long tiles = (long long)L.B * P.tiles_h * P.tiles_w;
   const int grid = tiles < kNumSMs ? (int)tiles : kNumSMs;
-  if (P.S == 1 && P.TW == 16) launch_t<1, 16>(a, maps, grid, P.smem_bytes, s);
-  else if (P.S == 1 && P.TW == 8) launch_t<1, 8>(a, maps, grid, P.smem_bytes, s);
-  else if (P.S == 2 && P.TW == 8) launch_t<2, 8>(a, maps, grid, P.smem_bytes, s);
+  // debug timeline: BNB_MB2_TRACE=<file> BNB_MB2_TRACE_IDX=<n-th mbconv2 launch of the process>
+  static std::atomic<long long> launch_idx{0};
+  static const char* trace_path = getenv("BNB_MB2_TRACE");
+  static const long long trace_idx = getenv("BNB_MB2_TRACE_IDX") ? atoll(getenv("BNB_MB2_TRACE_IDX")) : 0;
+  const long long my_idx = launch_idx.fetch_add(1);
+  long long* trace = nullptr;
+  if (trace_path && my_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 2 * 8 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 2 * 8 * 64 * sizeof(long long), s)); a.trace = trace; }
+  if (P.S == 1 && P.TW == 8) mbconv2_kernel<1, 8><<<grid, kThreads, P.smem_bytes, s>>>(a);
+  else if (P.S == 2 && P.TW == 4) mbconv2_kernel<2, 4><<<grid, kThreads, P.smem_bytes, s>>>(a);
   else throw std::runtime_error("mbconv2: unsupported tile shape");
+  if (trace) {
+    std::vector<long long> h(2 * 8 * 64);
+    BNB_CUDA(cudaStreamSynchronize(s));
+    BNB_CUDA(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "w");
+    if (f) {
+      fprintf(f, "# mbconv2 B=%d H=%d W=%d Cin=%d C=%d S=%d tile=%dx%d patch=%dx%d n_mma=%d units=%d k_stages=%d resident=%d a_slots=%d b_slots=%d grid=%d tiles=%lld\n",
+              L.B, L.H, L.W, P.Cin, P.C, P.S, P.TH, P.TW, P.PH, P.PW, P.n_mma, P.n_units, P.k_stages, P.a_resident, P.a_slots, P.b_slots, grid, tiles);
+      fprintf(f, "# cta idx start patch_issue patch_landed mma_committed acc_seen acc_released unit_done end   (cycles since the CTA's start)\n");
+      for (int c = 0; c < 2; ++c) {
+        const long long t0 = h[(c * 8 + 0) * 64];
+        for (int i = 0; i < 64; ++i) {
+          bool any = false;
+          for (int e = 0; e < 8; ++e) any = any || h[(c * 8 + e) * 64 + i] != 0;
+          if (!any) continue;
+          fprintf(f, "%d %d", c, i);
+          for (int e = 0; e < 8; ++e) { const long long v = h[(c * 8 + e) * 64 + i]; fprintf(f, " %lld", v ? v - t0 : -1); }
+          fprintf(f, "\n");
+        }
+      }
+      fclose(f);
+    }
+    cudaFree(trace);
+  }
   BNB_LAUNCH_CHECK(lc);
 }
 

@@ -7,12 +7,13 @@
 #include <vector>
 
 #include "kernels.h"
+#include "layouts.h"
 
 namespace bnb {
 
 constexpr size_t kMb2SmemLimit = 227 * 1024;
 constexpr int kMb2MaxStages = 3;
-constexpr int kMb2BufCols = 160;      // TMEM columns per accumulator buffer (3 buffers of 512 columns)
+constexpr int kMb2BufCols = 128;      // TMEM columns per accumulator buffer (4 buffers of 512 columns)
 
 // Host-side plan of one layer: tile geometry, K stages, shared-memory layout.  Pure host logic (CPU-testable).
 struct Mb2Plan {
@@ -38,14 +39,16 @@ Mb2Plan mb2_plan(int H, int W, int Ho, int Wo, int stride, int Cin, int C, bool 
 // expand weights [C][Cin] fp32 -> per-(unit, stage) hi | lo swizzled K-major planes of 128 rows
 void mb2_prepare_weights(const Mb2Plan& P, const float* w, std::vector<uint8_t>* image);
 
+// the PatchTiles image this layer READS (its producer writes it): geometry + stage layout of the plan
+PatchTiles mb2_patch_layout(const Mb2Plan& P, int H, int W);
+
 struct Mb2Launch {
-  const __half* xh; const __half* xl;   // block input planes [B][H][W][x_pitch]
-  int x_pitch;                          // channels per pixel in memory (multiple of 8)
+  const uint8_t* x_img;                 // block input as the PatchTiles image of THIS layer's plan (mb2_patch_layout)
   const uint8_t* Wimg;                  // mb2_prepare_weights image
   const float* bias_e;                  // expand bias, padded to n_units * 128
   const float* w_dw;                    // depthwise taps [9][C]
   const float* bias_dw;                 // [C]
-  __half* dh; __half* dl;               // depthwise output planes [B][Ho][Wo][C]
+  uint8_t* d_img;                       // depthwise output [B*Ho*Wo][C] as a RowTiles image (RowTiles::make(C))
   float* partial;                       // [B][tiles_h * tiles_w][C] SE sums per tile, or null
   int B, H, W, Ho, Wo;
 };

@@ -18,11 +18,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "tc_common.cuh"
-#include "tma_host.h"
 
 namespace bnb {
 
@@ -30,21 +31,30 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 576;       // 18 warps: 8 epilogue, MMA issuer, loader, 8 converters (gate layers only)
-constexpr int kEpiWarps = 8, kMmaWarp = 8, kLoadWarp = 9, kConvWarp0 = 10, kConvThreads = 256;
+constexpr int kEpiWarps = 16, kMmaWarp = 16, kLoadWarp = 17, kConvWarp0 = 18, kConvThreads = 256;
+constexpr int kThreads = (kEpiWarps + 2) * 32 + kConvThreads;       // 26 warps: 16 epilogue, MMA issuer, loader, 8 converters (gate layers only)
+constexpr int kEpiStage = 2048;     // bytes of epilogue staging per warp: 32 rows x 16 fp32 columns
 constexpr int kAccCols = 256;
 constexpr uint32_t kABytes = kBM * 128u;      // one fp16 [128][64] plane tile
 
 struct Pw2Args {
-  const uint8_t* Wimg; const float* bias; const float* gate;
-  const __half* rh; const __half* rl; __half* oh; __half* ol; float* out32;
+  const uint8_t* a_img; const uint8_t* Wimg; const float* bias; const float* gate;
+  const uint8_t* r_img; __half* oh; __half* ol; float* out32; uint8_t* o_img;
   int M, N, K, rows_per_chunk, act;
-  int r_pitch, o_pitch;
+  int o_pitch, out_mode;                  // out_mode: 0 fp32, 1 plain planes, 2 PatchTiles image
+  uint32_t a_tile_bytes;
   int n_pad, k_pad, n_tiles, bn, stages, b_res, conv, out_vec;
+  PatchTiles rp, op;                      // residual / output patch layouts
+  long long* trace;                       // debug timeline (BNB_PW2_TRACE): [2 CTAs][8 events][64 slots] clock64 stamps, else null
 };
 
+// events: 0 kernel start, 1 stage load issued, 2 stage data landed (converter / MMA saw it), 3 stage converted, 4 stage MMAs
+// committed, 5 accumulator seen by the epilogue, 6 m-tile stored, 7 kernel end.  Index = stage iteration (1..4) or m-tile count (5, 6).
+#define PW2_TRACE(ev, i) do { if (a.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (i) < 64) \
+    a.trace[((blockIdx.x == 0 ? 0 : 1) * 8 + (ev)) * 64 + (i)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(kThreads, 1)
-pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+pw2_kernel(const __grid_constant__ Pw2Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -53,10 +63,11 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
 
   const uint32_t b_bytes = (uint32_t)a.bn * 128u;
   const uint32_t stage_bytes = 2 * kABytes + (a.b_res ? 0u : 2 * b_bytes);
-  const uint32_t bres_bytes = a.b_res ? 2 * b_bytes : 0u;
+  const int k_stages_all = (a.K + kBK - 1) / kBK;
+  const uint32_t bres_bytes = a.b_res ? (uint32_t)k_stages_all * 2 * b_bytes : 0u;    // resident weights: every K stage of this CTA's n-tile
   const uint32_t bres = base + (uint32_t)a.stages * stage_bytes;
-  const uint32_t stg = bres + bres_bytes;                                  // 8 x 4 KB epilogue staging
-  const uint32_t bars = stg + kEpiWarps * 4096u;
+  const uint32_t stg = bres + bres_bytes;                                  // 16 x 2 KB epilogue staging
+  const uint32_t bars = stg + kEpiWarps * kEpiStage;
   auto tma_bar = [&](int s) { return bars + 8u * s; };
   auto full_bar = [&](int s) { return bars + 8u * (a.stages + s); };
   auto empty_bar = [&](int s) { return bars + 8u * (2 * a.stages + s); };
@@ -64,7 +75,6 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
   auto tempty_bar = [&](int b) { return bars + 8u * (3 * a.stages + 2 + b); };
   const uint32_t bres_bar = bars + 8u * (3 * a.stages + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (3 * a.stages + 5));
-  float* s_bias_all = reinterpret_cast<float*>(base_ptr + (bars - base) + ((8u * (3 * a.stages + 5) + 16 + 15) & ~15u));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(tma_bar(s), 1); mbar_init(full_bar(s), kConvThreads); mbar_init(empty_bar(s), 1); }
@@ -85,6 +95,7 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
   const int m_tiles = (a.M + kBM - 1) / kBM;
   const int nt_fix = blockIdx.x % a.n_tiles, mt_first = blockIdx.x / a.n_tiles, mt_step = gridDim.x / a.n_tiles;
   const int k_stages = (a.K + kBK - 1) / kBK;
+  if (threadIdx.x == 0) PW2_TRACE(0, 0);
 
   if (warp >= kConvWarp0) {
     // ============================== converters (gate layers): A <- split((hi + lo) * gate), in place, thread-private ===
@@ -114,6 +125,7 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
             }
           }
           mbar_wait_relaxed(tma_bar(s), ph);
+          if (pt == 0) PW2_TRACE(2, it);
           if (live) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -134,6 +146,7 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
           }
           fence_proxy_async();
           mbar_arrive(full_bar(s));
+          if (pt == 0) PW2_TRACE(3, it);
         }
       }
     }
@@ -142,22 +155,24 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
     uint32_t it = 0;
     const int n0 = nt_fix * a.bn;
     const uint32_t bn_bytes = (uint32_t)min(a.bn, a.n_pad - n0) * 128u;
-    if (a.b_res && lane == 0) {
-      const uint8_t* wsrc = a.Wimg + (size_t)n0 * 128;
-      mbar_arrive_expect_tx(bres_bar, 2 * bn_bytes);
-      bulk_g2s(bres, wsrc, bn_bytes, bres_bar);
-      bulk_g2s(bres + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, bres_bar);
+    if (a.b_res && lane == 0) {                 // this CTA's weight tile, every K stage, loaded once
+      mbar_arrive_expect_tx(bres_bar, (uint32_t)k_stages * 2 * bn_bytes);
+      for (int ks = 0; ks < k_stages; ++ks) {
+        const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
+        bulk_g2s(bres + (uint32_t)ks * 2 * b_bytes, wsrc, bn_bytes, bres_bar);
+        bulk_g2s(bres + (uint32_t)ks * 2 * b_bytes + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, bres_bar);
+      }
     }
     for (int mt = mt_first; mt < m_tiles; mt += mt_step) {
-      const int m0 = mt * kBM;
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
         const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
         mbar_wait_relaxed(empty_bar(s), ph ^ 1);
         const uint32_t dst = base + (uint32_t)s * stage_bytes;
         if (lane == 0) {
           mbar_arrive_expect_tx(tma_bar(s), 2 * kABytes + (a.b_res ? 0u : 2 * bn_bytes));
-          tma_load_2d(dst, &map_hi, ks * kBK, m0, tma_bar(s));
-          tma_load_2d(dst + kABytes, &map_lo, ks * kBK, m0, tma_bar(s));
+          // the (m-tile, stage) A operand, hi | lo, is one contiguous 32 KB block of the RowTiles image
+          bulk_g2s(dst, a.a_img + (size_t)mt * a.a_tile_bytes + (size_t)ks * (2 * kABytes), 2 * kABytes, tma_bar(s));
+          PW2_TRACE(1, it);
           if (!a.b_res) {
             const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
             bulk_g2s(dst + 2 * kABytes, wsrc, bn_bytes, tma_bar(s));
@@ -183,10 +198,11 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
         for (int ks = 0; ks < k_stages; ++ks, ++it) {
           const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
           mbar_wait(a.conv ? full_bar(s) : tma_bar(s), ph);
+          if (!a.conv) PW2_TRACE(2, it);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + kABytes);
-          const uint32_t sb = a.b_res ? bres : sa + 2 * kABytes;
+          const uint32_t sb = a.b_res ? bres + (uint32_t)ks * 2 * b_bytes : sa + 2 * kABytes;
           const uint64_t d_bhi = make_desc(sb), d_blo = make_desc(sb + b_bytes);
           const int kk_n = min(kBK, a.k_pad - ks * kBK) / 16;
           for (int kk = 0; kk < kk_n; ++kk) {
@@ -196,91 +212,110 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
             umma(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1);
           }
           umma_commit(empty_bar(s));
+          PW2_TRACE(4, it);
         }
         umma_commit(tfull_bar(buf));
       }
     }
   } else {
-    // ============================== epilogue (warps 0-7) ================================================================
-    // warp w owns TMEM lanes 32*(w%4).. (rows) and one half of the tile's columns, 32 columns per tcgen05.ld.  A thread
-    // holds one ROW, so the 32x32 fp32 sub-tile goes through a warp-private XOR-swizzled staging buffer and is read back
-    // row-segment-wise: every global access of the store loop covers whole 64-byte (planes) / 128-byte (fp32) row pieces.
-    const int quarter = warp & 3, half = warp >> 2;
-    float* s_bias = s_bias_all + warp * 128;
-    uint8_t* s_out = base_ptr + (stg - base) + warp * 4096;
+    // ============================== epilogue (warps 0-15) ===============================================================
+    // warp w owns TMEM lanes 32*(w%4).. (rows) and the 16-column chunks c with c % 4 == w / 4.  A thread holds one ROW of the
+    // chunk, so the 32x16 fp32 sub-tile goes through a warp-private XOR-swizzled staging buffer and is read back piece-wise
+    // (8 columns = one 16-byte piece of each fp16 plane per lane): global accesses then cover whole pieces / row segments.
+    // Sixteen warps because one warp per 32x32 sub-tile was latency-bound (profiles/r02 timeline: 4.5 k cycles per m-tile).
+    const int quarter = warp & 3, sub = warp >> 2;
+    uint8_t* s_out = base_ptr + (stg - base) + warp * kEpiStage;
     const int n0 = nt_fix * a.bn;
     const int bn = min(a.bn, a.n_pad - n0);
-    const int c_split = min(bn, ((bn / 2 + 31) / 32) * 32);
-    const int c_begin = half ? c_split : 0, c_end = half ? bn : c_split;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int cc = c_begin + lane + 32 * j;
-      s_bias[lane + 32 * j] = (cc < c_end + 16 && n0 + cc < a.n_pad + 16) ? __ldg(a.bias + n0 + cc) : 0.f;
-    }
-    __syncwarp();
+    const bool plane_mode = a.out_mode != 0;
     uint32_t tcount = 0;
     for (int mt = mt_first; mt < m_tiles; mt += mt_step, ++tcount) {
       const int buf = tcount & 1;
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) PW2_TRACE(5, tcount);
       const int m_w = mt * kBM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kAccCols;
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      for (int c0 = sub * 16; c0 < bn; c0 += 64) {
         const int n = n0 + c0;
-        // residual pieces of this 32-column chunk in the read-back pattern (row = 8*j + lane/4, 8 columns per lane), issued early
-        uint4 rvh[4], rvl[4];
-        const int piece = lane & 3, pcol = n + 8 * piece;
-        const bool plane_mode = a.oh != nullptr;
-        if (plane_mode && a.rh != nullptr) {
+        // read-back pattern of the plane modes: lane -> (row = 16*j + lane/2, 8-column piece = lane & 1), j = 0, 1.
+        // Residual pieces (the block input: pixel m is interior to exactly one patch tile of its image) are requested first.
+        uint4 rvh[2], rvl[2];
+        const int piece = lane & 1, pcol = n + 8 * piece;
+        if (plane_mode && a.r_img != nullptr) {
+          int rs, rchunk;
+          a.rp.stage_of(pcol >> 3, &rs, &rchunk);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int mrow = m_w + 8 * j + (lane >> 2);
-            const bool ok = mrow < a.M && pcol < a.r_pitch;
-            rvh[j] = ok ? __ldg(reinterpret_cast<const uint4*>(a.rh + (size_t)mrow * a.r_pitch + pcol)) : make_uint4(0, 0, 0, 0);
-            rvl[j] = ok ? __ldg(reinterpret_cast<const uint4*>(a.rl + (size_t)mrow * a.r_pitch + pcol)) : make_uint4(0, 0, 0, 0);
+          for (int j = 0; j < 2; ++j) {
+            const int mrow = m_w + 16 * j + (lane >> 1);
+            rvh[j] = make_uint4(0, 0, 0, 0); rvl[j] = rvh[j];
+            if (mrow < a.M && pcol < a.o_pitch) {
+              int b, h, w, ty, tx, pr, pc;
+              a.rp.split_pixel((uint32_t)mrow, &b, &h, &w);
+              a.rp.interior(h, w, &ty, &tx, &pr, &pc);
+              const uint8_t* src = a.r_img + a.rp.tile_base(b, ty, tx) + a.rp.in_tile(pr, pc, rs, rchunk);
+              rvh[j] = __ldg(reinterpret_cast<const uint4*>(src));
+              rvl[j] = __ldg(reinterpret_cast<const uint4*>(src + a.rp.st_plane[rs]));
+            }
           }
         }
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c0, r);
         __syncwarp();                                      // previous chunk's read-back of s_out is complete
         tmem_ld_wait();
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bz = *reinterpret_cast<const float4*>(s_bias + (c0 - c_begin) + 4 * j4);
+        for (int q = 0; q < 4; ++q) {
+          const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4 * q));      // bias is zero-padded past n_pad
           float4 o;
-          o.x = __uint_as_float(r[4 * j4 + 0]) + bz.x; o.y = __uint_as_float(r[4 * j4 + 1]) + bz.y;
-          o.z = __uint_as_float(r[4 * j4 + 2]) + bz.z; o.w = __uint_as_float(r[4 * j4 + 3]) + bz.w;
+          o.x = __uint_as_float(r[4 * q + 0]) + bz.x; o.y = __uint_as_float(r[4 * q + 1]) + bz.y;
+          o.z = __uint_as_float(r[4 * q + 2]) + bz.z; o.w = __uint_as_float(r[4 * q + 3]) + bz.w;
           if (a.act == ACT_SILU) silu4(o.x, o.y, o.z, o.w);
           else if (a.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          *reinterpret_cast<float4*>(s_out + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o;
+          *reinterpret_cast<float4*>(s_out + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;
         }
         __syncwarp();
         if (plane_mode) {
           const bool col_ok = pcol < a.o_pitch;            // pad columns of the pitch receive exact zeros (zero weights, zero bias)
+          int os = 0, ochunk = 0;
+          if (a.out_mode == 2) a.op.stage_of(pcol >> 3, &os, &ochunk);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int row = 8 * j + (lane >> 2), mrow = m_w + row;
+          for (int j = 0; j < 2; ++j) {
+            const int row = 16 * j + (lane >> 1), mrow = m_w + row;
             if (col_ok && mrow < a.M) {
-              const float4 p0 = *reinterpret_cast<const float4*>(s_out + row * 128 + (((2 * piece) ^ (row & 7)) << 4));
-              const float4 p1 = *reinterpret_cast<const float4*>(s_out + row * 128 + (((2 * piece + 1) ^ (row & 7)) << 4));
+              const int key = (row >> 1) & 3;
+              const float4 p0 = *reinterpret_cast<const float4*>(s_out + row * 64 + (((2 * piece) ^ key) << 4));
+              const float4 p1 = *reinterpret_cast<const float4*>(s_out + row * 64 + (((2 * piece + 1) ^ key) << 4));
               float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-              if (a.rh != nullptr) {
+              if (a.r_img != nullptr) {
                 const float2 q0 = join2(rvh[j].x, rvl[j].x), q1 = join2(rvh[j].y, rvl[j].y), q2 = join2(rvh[j].z, rvl[j].z), q3 = join2(rvh[j].w, rvl[j].w);
                 v[0] += q0.x; v[1] += q0.y; v[2] += q1.x; v[3] += q1.y; v[4] += q2.x; v[5] += q2.y; v[6] += q3.x; v[7] += q3.y;
               }
               uint4 ho, lo;
               split2(v[0], v[1], ho.x, lo.x); split2(v[2], v[3], ho.y, lo.y); split2(v[4], v[5], ho.z, lo.z); split2(v[6], v[7], ho.w, lo.w);
-              *reinterpret_cast<uint4*>(a.oh + (size_t)mrow * a.o_pitch + pcol) = ho;
-              *reinterpret_cast<uint4*>(a.ol + (size_t)mrow * a.o_pitch + pcol) = lo;
+              if (a.out_mode == 1) {
+                *reinterpret_cast<uint4*>(a.oh + (size_t)mrow * a.o_pitch + pcol) = ho;
+                *reinterpret_cast<uint4*>(a.ol + (size_t)mrow * a.o_pitch + pcol) = lo;
+              } else {
+                // the next block's PatchTiles image: the pixel goes into every tile whose halo patch contains it (<= 4)
+                int b, h, w;
+                a.op.split_pixel((uint32_t)mrow, &b, &h, &w);
+                const uint32_t lo_off = a.op.st_plane[os];
+                a.op.for_each_tile(h, w, [&](int ty, int tx, int pr, int pc) {
+                  uint8_t* dst = a.o_img + a.op.tile_base(b, ty, tx) + a.op.in_tile(pr, pc, os, ochunk);
+                  *reinterpret_cast<uint4*>(dst) = ho;
+                  *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+                });
+              }
             }
           }
         } else {
-          const int chunk = lane & 7, ncol = n + 4 * chunk;
+          // fp32 output: lane -> (row = 8*j + lane/4, 4 columns = lane & 3): 64-byte row segments per 4 lanes
+          const int chunk = lane & 3, ncol = n + 4 * chunk;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int row = 4 * j + (lane >> 3), mrow = m_w + row;
+          for (int j = 0; j < 4; ++j) {
+            const int row = 8 * j + (lane >> 2), mrow = m_w + row;
             if (mrow < a.M && c0 + 4 * chunk < bn) {
-              const float4 o = *reinterpret_cast<const float4*>(s_out + row * 128 + ((chunk ^ (row & 7)) << 4));
+              const float4 o = *reinterpret_cast<const float4*>(s_out + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
               float* dst = a.out32 + (size_t)mrow * a.N + ncol;
               if (a.out_vec == 4) { if (ncol + 4 <= a.N) *reinterpret_cast<float4*>(dst) = o; }
               else if (a.out_vec == 2) {
@@ -298,11 +333,13 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
+      if (threadIdx.x == 0) PW2_TRACE(6, tcount);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) PW2_TRACE(7, 0);
   if (warp == kMmaWarp) {
     __syncwarp();
     tc_fence_after();
@@ -310,10 +347,11 @@ pw2_kernel(const Pw2Args a, const __grid_constant__ CUtensorMap map_hi, const __
   }
 }
 
-size_t smem_for(int bn, int stages, bool b_res) {
-  const size_t stage = 2 * (size_t)kABytes + (b_res ? 0 : 2 * (size_t)bn * 128);
-  return (size_t)stages * stage + (b_res ? 2 * (size_t)bn * 128 : 0) + 1024 /*alignment*/ + kEpiWarps * 4096 +
-         ((8 * (3 * stages + 5) + 16 + 15) & ~15) + kEpiWarps * 128 * sizeof(float);
+// b_res_stages = number of K stages held resident (0 = weights stream with the A tiles)
+size_t smem_for(int bn, int stages, int b_res_stages) {
+  const size_t stage = 2 * (size_t)kABytes + (b_res_stages ? 0 : 2 * (size_t)bn * 128);
+  return (size_t)stages * stage + (size_t)b_res_stages * 2 * (size_t)bn * 128 + 1024 /*alignment*/ + kEpiWarps * kEpiStage +
+         ((8 * (3 * stages + 5) + 16 + 15) & ~15);
 }
 
 }  // namespace
@@ -321,17 +359,19 @@ size_t smem_for(int bn, int stages, bool b_res) {
 void pw2_tiling(const PwTcLayer& L, int M, bool conv, int* bn_out, int* stages_out, size_t* smem_out, int* b_res_out) {
   const int m_tiles = (M + kBM - 1) / kBM;
   const size_t budget = 227 * 1024;
-  const bool b_res = L.k_stages == 1;
   int n_tiles = (L.n_pad + 255) / 256;
-  auto bn_of = [&](int nt) { return nt == 1 ? L.n_pad : ((L.n_pad + nt - 1) / nt + 31) / 32 * 32; };
+  auto bn_of = [&](int nt) { return nt == 1 ? L.n_pad : ((L.n_pad + nt - 1) / nt + 15) / 16 * 16; };   // 16-column epilogue chunks must not spill into the next n-tile
   int bn = bn_of(n_tiles);
-  while (smem_for(bn, 2, b_res) > budget) { ++n_tiles; bn = bn_of(n_tiles); }
+  while (smem_for(bn, 2, 0) > budget) { ++n_tiles; bn = bn_of(n_tiles); }
   if (L.k_stages >= 3) while (bn > 128) { ++n_tiles; bn = bn_of(n_tiles); }
   while (m_tiles * ((L.n_pad + bn - 1) / bn) < kNumSMs && bn > 64) { ++n_tiles; bn = bn_of(n_tiles); }
+  // weights resident (every K stage of the CTA's n-tile) when that still leaves a 3-deep A ring: N-stationary CTAs then
+  // read them once instead of once per m-tile (profiles/r02: the 288 -> 72 projects moved 100 KB of weights per 160 KB of A)
+  const bool b_res = smem_for(bn, 3, L.k_stages) <= budget && (size_t)L.k_stages * 2 * bn * 128 < (1u << 20);
   int stages = conv ? 6 : 5;
-  while (stages > 2 && smem_for(bn, stages, b_res) > budget) --stages;
+  while (stages > 2 && smem_for(bn, stages, b_res ? L.k_stages : 0) > budget) --stages;
   if (stages > L.k_stages * 3 && stages > 2) stages = L.k_stages * 3 > 2 ? L.k_stages * 3 : 2;   // no point in a ring far deeper than the work
-  *bn_out = bn; *stages_out = stages; *smem_out = smem_for(bn, stages, b_res);
+  *bn_out = bn; *stages_out = stages; *smem_out = smem_for(bn, stages, b_res ? L.k_stages : 0);
   if (b_res_out) *b_res_out = b_res ? 1 : 0;
 }
 
@@ -340,8 +380,11 @@ void pw2_set_attributes() {
 }
 
 void launch_pw2(const PwTcLayer& L, const Pw2Launch& p, cudaStream_t s, LaunchCounter& lc) {
-  if ((p.oh != nullptr) == (p.out32 != nullptr)) throw std::runtime_error("pw2: exactly one of the plane / fp32 outputs must be set");
-  if (p.a_pitch % 8 || (p.oh && (p.o_pitch % 8 || p.o_pitch < p.N)) || (p.rh && p.r_pitch % 8)) throw std::runtime_error("pw2: plane pitches must be multiples of 8");
+  const int n_out = (p.out32 != nullptr) + (p.oh != nullptr) + (p.o_img != nullptr);
+  if (n_out != 1) throw std::runtime_error("pw2: exactly one output (fp32, plain planes, patch image) must be set");
+  if (p.oh && (p.o_pitch % 8 || p.o_pitch < p.N)) throw std::runtime_error("pw2: plane pitch must be a multiple of 8 and >= N");
+  if (p.o_img && p.o_patch.C != p.N) throw std::runtime_error("pw2: output patch layout does not match N");
+  if (p.r_img && (p.r_patch.C != p.N || p.r_patch.S != 1 || p.out32)) throw std::runtime_error("pw2: residual needs a stride-1 patch layout with N channels and a plane output");
   if (p.gate && (p.K % 8 || p.rows_per_chunk <= 0)) throw std::runtime_error("pw2: gated layers need K % 8 == 0");
   int bn = 0, stages = 0, b_res = 0;
   size_t smem_bytes = 0;
@@ -349,21 +392,48 @@ void launch_pw2(const PwTcLayer& L, const Pw2Launch& p, cudaStream_t s, LaunchCo
   if (smem_bytes > 227 * 1024) throw std::runtime_error("pw2: shared memory budget exceeded");
   if (smem_bytes < 116 * 1024) smem_bytes = 116 * 1024;          // one CTA per SM (all 512 TMEM columns)
   Pw2Args a{};
-  a.Wimg = p.Wimg; a.bias = p.bias; a.gate = p.gate; a.rh = p.rh; a.rl = p.rl; a.oh = p.oh; a.ol = p.ol; a.out32 = p.out32;
+  a.a_img = p.a_img; a.Wimg = p.Wimg; a.bias = p.bias; a.gate = p.gate; a.r_img = p.r_img; a.oh = p.oh; a.ol = p.ol; a.out32 = p.out32; a.o_img = p.o_img;
   a.M = p.M; a.N = p.N; a.K = p.K; a.rows_per_chunk = p.rows_per_chunk > 0 ? p.rows_per_chunk : 1; a.act = p.act;
-  a.r_pitch = p.r_pitch; a.o_pitch = p.o_pitch;
+  a.out_mode = p.out32 ? 0 : (p.oh ? 1 : 2);
+  a.o_pitch = p.oh ? p.o_pitch : (p.N + 7) / 8 * 8;
+  a.a_tile_bytes = RowTiles::make(p.K).tile_bytes;
+  a.rp = p.r_patch; a.op = p.o_patch;
   a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.bn = bn; a.n_tiles = (L.n_pad + bn - 1) / bn; a.stages = stages; a.b_res = b_res;
   a.conv = p.gate != nullptr ? 1 : 0;
   a.out_vec = (p.N % 4 == 0) ? 4 : ((p.N % 2 == 0) ? 2 : 1);
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int tiles = m_tiles * a.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : (kNumSMs / a.n_tiles) * a.n_tiles;
-  const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
-  const uint64_t strides[1] = {(uint64_t)p.a_pitch * 2};
-  const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)kBM};
-  const CUtensorMap mh = tma_encode(p.ah, 2, 2, dims, strides, box, 128);
-  const CUtensorMap ml = tma_encode(p.al, 2, 2, dims, strides, box, 128);
-  pw2_kernel<<<grid, kThreads, smem_bytes, s>>>(a, mh, ml);
+  static std::atomic<long long> launch_idx{0};
+  static const char* trace_path = getenv("BNB_PW2_TRACE");
+  static const long long trace_idx = getenv("BNB_PW2_TRACE_IDX") ? atoll(getenv("BNB_PW2_TRACE_IDX")) : 0;
+  const long long my_idx = launch_idx.fetch_add(1);
+  long long* trace = nullptr;
+  if (trace_path && my_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 2 * 8 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 2 * 8 * 64 * sizeof(long long), s)); a.trace = trace; }
+  pw2_kernel<<<grid, kThreads, smem_bytes, s>>>(a);
+  if (trace) {
+    std::vector<long long> h(2 * 8 * 64);
+    BNB_CUDA(cudaStreamSynchronize(s));
+    BNB_CUDA(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "w");
+    if (f) {
+      fprintf(f, "# pw2 M=%d N=%d K=%d conv=%d bn=%d stages=%d b_res=%d grid=%d m_tiles=%d out_mode=%d residual=%d\n", p.M, p.N, p.K, a.conv, bn, stages, b_res, grid, m_tiles, a.out_mode, p.r_img != nullptr);
+      fprintf(f, "# cta idx start load_issue landed converted mma_committed acc_seen tile_stored end   (cycles since the CTA's start)\n");
+      for (int c = 0; c < 2; ++c) {
+        const long long t0 = h[(c * 8 + 0) * 64];
+        for (int i = 0; i < 64; ++i) {
+          bool any = false;
+          for (int e = 0; e < 8; ++e) any = any || h[(c * 8 + e) * 64 + i] != 0;
+          if (!any) continue;
+          fprintf(f, "%d %d", c, i);
+          for (int e = 0; e < 8; ++e) { const long long v = h[(c * 8 + e) * 64 + i]; fprintf(f, " %lld", v ? v - t0 : -1); }
+          fprintf(f, "\n");
+        }
+      }
+      fclose(f);
+    }
+    cudaFree(trace);
+  }
   BNB_LAUNCH_CHECK(lc);
 }
 

@@ -4,20 +4,22 @@
 #include <stdint.h>
 
 #include "kernels.h"
+#include "layouts.h"
 #include "pw_tc.h"
 
 namespace bnb {
 
 struct Pw2Launch {
-  const __half* ah; const __half* al;   // A planes [M][a_pitch] fp16 (x ~= hi + lo), K-major
-  int a_pitch;                          // elements per row in memory (multiple of 8)
+  const uint8_t* a_img;                 // A [M][K] as a RowTiles image (RowTiles::make(K)): fp16 hi | lo planes per (128-row tile, 64-channel stage)
   const uint8_t* Wimg;                  // pw_tc_prepare image of W[N][K]
   const float* bias;                    // [N] padded with zeros to n_pad + 64
   const float* gate;                    // [M / rows_per_chunk][K] SE gate applied to A on the fly, or null
-  const __half* rh; const __half* rl;   // residual planes [M][r_pitch] or null
-  int r_pitch;
-  __half* oh; __half* ol; int o_pitch;  // output planes [M][o_pitch] (o_pitch multiple of 8, >= N), or null
-  float* out32;                         // fp32 output [M][N] (exactly one of oh / out32 is set)
+  const uint8_t* r_img = nullptr;       // residual: the block INPUT, a PatchTiles image (r_patch: stride-1 geometry, pixel m interior), or null
+  PatchTiles r_patch;
+  // exactly one output: fp32 [M][N]; plain hi/lo planes [M][o_pitch]; or the PatchTiles image the NEXT block reads
+  float* out32 = nullptr;
+  __half* oh = nullptr; __half* ol = nullptr; int o_pitch = 0;
+  uint8_t* o_img = nullptr; PatchTiles o_patch;
   int M, N, K, rows_per_chunk, act;
 };
 // tiling decision (host logic, CPU-testable): N-tile width, pipeline stages, shared-memory bytes, resident-weights flag

@@ -132,6 +132,22 @@ BNB_API int bnb_analyze_batch_device(bnb_classifier* h, const void* d_pcm, int f
                              float sensitivity, int k, int32_t* d_idx, float* d_conf,
                              float* d_logits_or_null, void* stream);
 
+/* ---- range filter (the "meta" model: species occurrence by location and week) --------------------------------- */
+
+typedef struct bnb_range_filter bnb_range_filter; /* opaque; owns device weights and a stream */
+
+/* Replaces tflite.NewTFLiteRangeFilter(modelData, errorFunc) (tflite/rangefilter.go:22-58): `tflite` are the bytes of
+ * BirdNET_GLOBAL_6K_V2.4_MData_Model_V2_FP16.tflite (embedded, models_embedded.go); `device` = CUDA ordinal, -1 = current.
+ * A graph of another shape -> BNB_ERR_UNSUPPORTED_MODEL (the caller keeps its TFLite range filter). */
+BNB_API int bnb_range_filter_create(const void* tflite, size_t tflite_len, int device, bnb_range_filter** out);
+BNB_API void bnb_range_filter_destroy(bnb_range_filter* h);
+BNB_API int bnb_range_filter_num_species(const bnb_range_filter* h); /* RangeFilter.NumSpecies() (backend.go:63) */
+/* RangeFilter.Predict(latitude, longitude, week) (backend.go:58-61; tflite/rangefilter.go:64-94): scores[num_species]. */
+BNB_API int bnb_range_filter_predict(bnb_range_filter* h, float latitude, float longitude, float week, float* scores);
+/* BatchRangeFilter.PredictBatch(inputs, batchSize) (backend.go:70-76; used by the heat-map builder,
+ * orchestrator.go:1846-1882): inputs = batch_size x [lat, lon, week]; scores = [batch_size, num_species] row-major. */
+BNB_API int bnb_range_filter_predict_batch(bnb_range_filter* h, const float* inputs, int batch_size, float* scores);
+
 /* ---- introspection / test hooks -------------------------------------------------------------- */
 
 /* Number of kernels of THIS library launched by the handle since creation (bench `gpu_launches`). */
@@ -171,13 +187,16 @@ BNB_API int bnb_debug_keep_intermediates(bnb_classifier* h, int on);
  *   w_dw [9,C] -> d_out [B,Ho,Wo,C] (+ se_sum [B,C] = per-channel sums over pixels, may be NULL); flags bit 0 forbids the
  *   32/64-byte swizzle stage shapes; info10 = {TH, TW, PH, PW, n_mma, k_stages, a_resident, a_slots, b_slots, smem}.
  * bnb_debug_pw2: out [M,N] = act(A' W^T + bias) (+ residual), A' = A (* gate[m / rows_per_chunk] when gate != NULL);
- *   planes_out selects the hi/lo-plane epilogue (joined on the host) or the fp32 one; info4 = {bn, stages, b_res, smem}. */
+ *   out_mode 0 = fp32 epilogue, 1 = plain hi/lo planes, 2 = the pre-tiled patch image of a consuming MBConv block whose
+ *   input map is geom4 = {H, W, stride, C_exp} (decoded on the host); a residual needs geom4 {H, W} too;
+ *   info4 = {bn, stages, b_res, smem}. */
 BNB_API int bnb_debug_tmem_probe(int32_t* out4);
 BNB_API int bnb_debug_mbconv2(const float* x, int B, int H, int W, int Cin, const float* w_exp, const float* b_exp,
                               const float* w_dw, const float* b_dw, int C, int stride, int flags, float* d_out, float* se_sum,
                               int32_t* info10);
 BNB_API int bnb_debug_pw2(const float* A, int M, int K, const float* W, const float* bias, int N, const float* gate,
-                          int rows_per_chunk, const float* residual, int act, int planes_out, float* out, int32_t* info4);
+                          int rows_per_chunk, const float* residual, int act, int out_mode, const int32_t* geom4, float* out,
+                          int32_t* info4);
 
 #ifdef __cplusplus
 }

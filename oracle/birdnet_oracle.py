@@ -166,3 +166,24 @@ class Oracle:
         if with_embeddings:
             return r[T_LOGITS], r[T_EMBEDDING].reshape(len(chunks), -1)
         return r[T_LOGITS]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Range filter ("meta" model): restates what the reference's tfliteRangeFilter does
+# (/root/reference/internal/inference/tflite/rangefilter.go:64-94): write (latitude, longitude, week) into the input
+# tensor, Invoke, read NumSpecies scores.  The arithmetic is the .tflite graph itself, interpreted op by op.
+RANGE_MODEL = os.path.join(ASSETS, "BirdNET_GLOBAL_6K_V2.4_MData_Model_V2_FP16.tflite")
+
+
+class RangeOracle:
+    def __init__(self, path=RANGE_MODEL, dtype=None):
+        import torch
+        from tflite_interp import Interpreter, load
+        self.g = load(path)
+        self.it = Interpreter(self.g, dtype=dtype or torch.float64)
+
+    def predict_batch(self, inputs):
+        """inputs [B,3] (lat, lon, week) -> [B, n_species] float64 scores."""
+        import torch
+        x = torch.as_tensor(np.asarray(inputs, np.float32).reshape(-1, 3))
+        return self.it.run(x)[self.g.outputs[0]].numpy()

@@ -109,6 +109,17 @@ class Interpreter:
             return torch.pow(a[0], a[1])
         if k == "LOGISTIC":
             return torch.sigmoid(a[0])
+        # ---- ops of the range-filter meta-model (BirdNET_GLOBAL_6K_V2.4_MData_Model_V2_FP16.tflite) ----
+        if k == "DEQUANTIZE":                                   # fp16 constants -> float (exact)
+            return a[0].to(self.dtype)
+        if k == "SIN":
+            return torch.sin(a[0])
+        if k == "GREATER":
+            return a[0] > a[1]
+        if k == "LESS":
+            return a[0] < a[1]
+        if k == "SELECT_V2":
+            return torch.where(a[0], a[1], a[2])
         if k in ("REDUCE_MIN", "REDUCE_MAX", "MEAN", "REDUCE_PROD"):
             axes = tuple(self._ints(a[1]))
             x = a[0]

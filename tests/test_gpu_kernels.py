@@ -90,27 +90,32 @@ def test_mbconv2_single_chunk_and_borders(lib_path):
         assert np.abs(se - ref_se).max() <= REL_TOL * np.abs(ref_se).max()
 
 
-# (M, K, N, gate rows_per_chunk or 0, residual, act, planes_out)
+# (name, B, map H x W of the GEMM rows, K, N, gated, residual, act, out_mode, consumer (stride, C_exp) or None)
 GEMMS = [
-    (3000, 72, 36, 0, True, 0, True), (128 * 400 + 5, 72, 36, 0, False, 0, True), (1536, 288, 72, 384, True, 0, True),
-    (96 * 9 + 7, 864, 108, 96, True, 0, True), (24 * 11, 1536, 192, 24, True, 0, True), (24 * 11, 1536, 192, 24, False, 0, True),
-    (37 * 6, 1728, 1024, 0, False, 1, False), (5, 1024, 6522, 0, False, 0, False), (256, 1024, 6522, 0, False, 0, False),
-    (700, 24, 72, 0, False, 2, False),
+    ("b1->b2", 33, 24, 64, 72, 36, False, False, 0, 2, (1, 72)), ("b2->b3", 2, 24, 64, 72, 36, False, True, 0, 2, (1, 72)),
+    ("b3->b4", 3, 24, 64, 72, 36, False, True, 0, 2, (2, 288)), ("b4->b5", 5, 12, 32, 288, 72, True, False, 0, 2, (1, 288)),
+    ("b5->b6", 4, 12, 32, 288, 72, True, True, 0, 2, (1, 288)), ("b7->b8", 4, 12, 32, 288, 72, True, True, 0, 2, (2, 864)),
+    ("b9->b10", 9, 6, 16, 864, 108, True, True, 0, 2, (1, 864)), ("b12->b13", 9, 6, 16, 864, 108, True, True, 0, 2, (2, 1536)),
+    ("b14->b15", 11, 3, 8, 1536, 192, True, True, 0, 2, (1, 1536)), ("b16->post", 11, 3, 8, 1536, 192, True, True, 0, 1, None),
+    ("post", 37, 1, 6, 1728, 1024, False, False, 1, 0, None), ("fc5", 5, 1, 1, 1024, 6522, False, False, 0, 0, None),
+    ("fc256", 256, 1, 1, 1024, 6522, False, False, 0, 0, None), ("silu32", 700, 1, 1, 24, 72, False, False, 2, 0, None),
 ]
 
 
-@pytest.mark.parametrize("M,K,N,rpc,res,act,planes", GEMMS)
-def test_pw2_matches_numpy(lib_path, M, K, N, rpc, res, act, planes):
-    rng = np.random.default_rng(M + K + N)
+@pytest.mark.parametrize("name,B,H,W,K,N,gated,res,act,mode,cons", GEMMS, ids=[g[0] for g in GEMMS])
+def test_pw2_matches_numpy(lib_path, name, B, H, W, K, N, gated, res, act, mode, cons):
+    rng = np.random.default_rng(B + K + N)
+    M, rpc = B * H * W, H * W
     A = (rng.standard_normal((M, K)) * 2).astype(np.float32)
     Wt = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
-    gate = rng.uniform(0.0, 1.0, ((M + rpc - 1) // rpc, K)).astype(np.float32) if rpc else None
+    gate = rng.uniform(0.0, 1.0, (B, K)).astype(np.float32) if gated else None
     resid = (rng.standard_normal((M, N)) * 5).astype(np.float32) if res else None
-    out, info = bb.debug_pw2(A, Wt, bias, gate, rpc, resid, act, planes)
+    geom = (H, W) + (cons if cons else (1, 128)) if (res or mode == 2) else None
+    out, info = bb.debug_pw2(A, Wt, bias, gate, rpc if gated else 0, resid, act, mode, geom)
     A64 = A.astype(np.float64)
-    if rpc:
-        A64 = A64 * np.repeat(gate.astype(np.float64), rpc, axis=0)[:M]
+    if gated:
+        A64 = A64 * np.repeat(gate.astype(np.float64), rpc, axis=0)
     ref = A64 @ Wt.astype(np.float64).T + bias
     if act == 1:
         ref = np.maximum(ref, 0)
@@ -119,5 +124,5 @@ def test_pw2_matches_numpy(lib_path, M, K, N, rpc, res, act, planes):
     if res:
         ref = ref + resid
     err = np.abs(out - ref).max() / np.abs(ref).max()
-    print((M, K, N), info, "rel err %.2e" % err)
+    print(name, (M, K, N), info, "rel err %.2e" % err)
     assert err <= REL_TOL
