@@ -62,6 +62,8 @@ SYMBOLS = {
     "bnb_predict_with_embeddings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "bnb_predict_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bnb_analyze_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnb_analyze_batch_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "bnb_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "bnb_predict_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnb_analyze_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnb_kernel_launches": (C.c_int64, [C.c_void_p]),
@@ -142,6 +144,15 @@ def describe_model(model_bytes: bytes) -> str:
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class _Ticket:
+    def __init__(self, clf, ticket, pcm, idx, conf, logits):
+        self._clf, self._t, self._pcm, self._idx, self._conf, self._logits = clf, ticket, pcm, idx, conf, logits
+
+    def wait(self):
+        _check(self._clf._lib.bnb_wait(self._clf._h, self._t))
+        return (self._idx, self._conf, self._logits) if self._logits is not None else (self._idx, self._conf)
 
 
 class B200Classifier:
@@ -237,6 +248,19 @@ class B200Classifier:
         _check(self._lib.bnb_analyze_batch(self._h, _ptr(pcm), self._fmt(pcm), B, float(sensitivity), k, _ptr(idx), _ptr(conf),
                                            _ptr(logits) if logits is not None else None))
         return (idx, conf, logits) if want_logits else (idx, conf)
+
+    def analyze_batch_submit(self, pcm, sensitivity=1.0, k=DEFAULT_TOP_K, want_logits=False):
+        """Asynchronous analyze_batch: returns a ticket object; call .wait() for (idx, conf[, logits]).  At most two tickets may be
+        outstanding.  `pcm` must stay alive and unchanged until wait() (it is referenced by the ticket)."""
+        pcm = self._check_batch(pcm, k)
+        B = pcm.shape[0]
+        idx = np.empty((B, k), np.int32)
+        conf = np.empty((B, k), np.float32)
+        logits = np.empty((B, self.n_species), np.float32) if want_logits else None
+        t = C.c_int32()
+        _check(self._lib.bnb_analyze_batch_submit(self._h, _ptr(pcm), self._fmt(pcm), B, float(sensitivity), k, _ptr(idx), _ptr(conf),
+                                                  _ptr(logits) if logits is not None else None, C.byref(t)))
+        return _Ticket(self, t.value, pcm, idx, conf, logits)
 
     # raw-pointer variants (device memory owned by the caller, e.g. torch tensors' data_ptr())
     def predict_batch_device(self, d_pcm, fmt, B, d_logits, d_emb=0, stream=0):
@@ -415,6 +439,35 @@ class BirdNET:
     def predict_batch(self, chunks, k=DEFAULT_TOP_K):
         idx, conf = self.classifier.analyze_batch(chunks, self.sensitivity, k)
         return [[Result(self.labels[i], float(c)) for i, c in zip(ri, rc)] for ri, rc in zip(idx, conf)]
+
+    def analyze_file(self, pcm_int16, overlap_s=0.0, threshold=0.1, batch=None, sample_rate=48000):
+        """Batched offline file analysis (BASELINE config 2; doc/wiki/file-analysis.md:1-13): slide a 3 s window with `overlap_s`
+        seconds of overlap over mono int16 PCM, run ALL windows through the batched int16 entry point (device-side /32768,
+        sigmoid(sensitivity * logit), top-10) and keep, per window, the results at or above `threshold`
+        (the reference's file mode keeps what passes --threshold).  Returns [(begin_s, end_s, species, confidence)], window order,
+        descending confidence inside a window.  The trailing partial window is zero-padded when it holds >= 1.5 s."""
+        pcm = np.ascontiguousarray(pcm_int16, np.int16).reshape(-1)
+        n = self.classifier.n_samples
+        step = n - int(round(overlap_s * sample_rate))
+        if step <= 0:
+            raise ValueError("overlap must be shorter than the 3 s window")
+        starts = list(range(0, max(len(pcm) - n, 0) + 1, step)) if len(pcm) >= n else []
+        tail = starts[-1] + step if starts else 0
+        if len(pcm) - tail >= n // 2:                         # last partial window, padded with silence
+            starts.append(tail)
+        B = batch or self.classifier.max_batch
+        out = []
+        for i in range(0, len(starts), B):
+            win = np.zeros((len(starts[i:i + B]), n), np.int16)
+            for j, s0 in enumerate(starts[i:i + B]):
+                seg = pcm[s0:s0 + n]
+                win[j, :len(seg)] = seg
+            idx, conf = self.classifier.analyze_batch(win, self.sensitivity, DEFAULT_TOP_K)
+            for j, s0 in enumerate(starts[i:i + B]):
+                for ii, cc in zip(idx[j], conf[j]):
+                    if cc >= threshold:
+                        out.append((s0 / sample_rate, (s0 + n) / sample_rate, self.labels[ii], float(cc)))
+        return out
 
     def close(self):
         if self.classifier is not None:

@@ -16,25 +16,44 @@ def shard_range(n_chunks: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def pack_topk(idx: torch.Tensor, conf: torch.Tensor, out: torch.Tensor | None = None):
+    """[n, k] int32 indices + [n, k] float32 confidences -> one [n, 2k] int32 buffer (confidences bit-cast), so the gather is
+    ONE collective per step instead of two."""
+    n, k = idx.shape
+    if out is None:
+        out = torch.empty((n, 2 * k), dtype=torch.int32, device=idx.device)
+    out[:, :k] = idx
+    out[:, k:] = conf.view(torch.int32)
+    return out
+
+
+def unpack_topk(packed: torch.Tensor):
+    k = packed.shape[1] // 2
+    return packed[:, :k], packed[:, k:].view(torch.float32)
+
+
+def gather_topk_packed(packed: torch.Tensor, out: torch.Tensor, group=None):
+    """Equal shards: all-gather [n, 2k] packed rows of every rank into out [world * n, 2k] (rank order = chunk order)."""
+    dist.all_gather_into_tensor(out, packed, group=group)
+    return out
+
+
 def gather_topk(idx: torch.Tensor, conf: torch.Tensor, n_chunks: int, group=None):
-    """All-gather ragged per-rank [n_r, k] results into chunk order [n_chunks, k] on every rank.
+    """All-gather ragged per-rank [n_r, k] results into chunk order [n_chunks, k] on every rank — ONE packed collective.
 
     Ranks own contiguous ranges (shard_range), so concatenating in rank order restores the global order.
     Shards are padded to the largest shard for the fixed-size collective and trimmed afterwards."""
     world = dist.get_world_size(group)
     k = idx.shape[1]
     per = (n_chunks + world - 1) // world
-    pad_i = torch.zeros((per, k), dtype=idx.dtype, device=idx.device)
-    pad_c = torch.zeros((per, k), dtype=conf.dtype, device=conf.device)
-    pad_i[: idx.shape[0]] = idx
-    pad_c[: conf.shape[0]] = conf
-    all_i = torch.empty((world * per, k), dtype=idx.dtype, device=idx.device)
-    all_c = torch.empty((world * per, k), dtype=conf.dtype, device=conf.device)
-    dist.all_gather_into_tensor(all_i, pad_i, group=group)
-    dist.all_gather_into_tensor(all_c, pad_c, group=group)
-    out_i, out_c = [], []
+    pad = torch.zeros((per, 2 * k), dtype=torch.int32, device=idx.device)
+    pack_topk(idx, conf, pad[: idx.shape[0]])
+    allp = torch.empty((world * per, 2 * k), dtype=torch.int32, device=idx.device)
+    gather_topk_packed(pad, allp, group=group)
+    rows = []
     for r in range(world):
         lo, hi = shard_range(n_chunks, r, world)
-        out_i.append(all_i[r * per: r * per + (hi - lo)])
-        out_c.append(all_c[r * per: r * per + (hi - lo)])
-    return torch.cat(out_i), torch.cat(out_c)
+        rows.append(allp[r * per: r * per + (hi - lo)])
+    out = torch.cat(rows)
+    oi, oc = unpack_topk(out)
+    return oi.contiguous(), oc.contiguous()

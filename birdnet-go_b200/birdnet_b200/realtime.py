@@ -88,11 +88,46 @@ class Results:
         self.source_id, self.start_time, self.pcm, self.results, self.elapsed = source_id, start_time, pcm, results, elapsed
 
 
+BUFFER_OVERRUN_REPORT_COOLDOWN_S = 3600.0     # process.go:36  bufferOverrunReportCooldown
+BUFFER_OVERRUN_MIN_COUNT = 10                 # process.go:39  bufferOverrunMinCount
+DEFAULT_BUFFER_INTERVAL_S = 1.5               # process.go:353 fallback: BirdNET v2.4 (3 s window, 50 % overlap)
+
+
+class BufferOverrunTracker:
+    """bufferOverrunTracker + recordBufferOverrun (process.go:44-215): tumbling window per (source, model); when the window
+    expires with >= BUFFER_OVERRUN_MIN_COUNT overruns ONE report is emitted (the reference sends a Sentry event)."""
+
+    def __init__(self, source, model_id, report=None):
+        self.source, self.model_id = source, model_id
+        self.overrun_count = 0
+        self.window_start = None
+        self.max_elapsed = 0.0
+        self.buffer_length = 0.0
+        self.reports = []
+        self._report = report
+
+    def record(self, elapsed, buffer_len, now):
+        if self.window_start is None:
+            self.window_start = now
+        if now - self.window_start >= BUFFER_OVERRUN_REPORT_COOLDOWN_S:
+            if self.overrun_count >= BUFFER_OVERRUN_MIN_COUNT:
+                rep = {"source": self.source, "model_id": self.model_id, "overrun_count": self.overrun_count,
+                       "max_elapsed_ms": int(self.max_elapsed * 1e3), "buffer_length_ms": int(self.buffer_length * 1e3),
+                       "reporting_window_minutes": int((now - self.window_start) / 60.0)}
+                self.reports.append(rep)
+                if self._report:
+                    self._report(rep)
+            self.overrun_count, self.max_elapsed, self.window_start = 0, 0.0, now
+        self.overrun_count += 1
+        if elapsed > self.max_elapsed:
+            self.max_elapsed, self.buffer_length = elapsed, buffer_len
+
+
 class RealtimeCoalescer:
     """One AnalysisBuffer per source; `tick()` plays analysisBufferMonitor for all of them and issues ONE batched call."""
 
     def __init__(self, analyze_batch, labels, sources, overlap_bytes=144000, read_bytes=144000, capacity_bytes=3 * WINDOW_BYTES,
-                 sensitivity=1.0, top_k=10, queue_size=DEFAULT_QUEUE_SIZE):
+                 sensitivity=1.0, top_k=10, queue_size=DEFAULT_QUEUE_SIZE, model_id="BirdNET_V2.4"):
         # analyze_batch(pcm_int16 [B,144000], sensitivity, k) -> (idx [B,k], conf [B,k]); e.g. B200Classifier.analyze_batch
         self.analyze_batch, self.labels = analyze_batch, labels
         self.sensitivity, self.top_k = sensitivity, top_k
@@ -105,6 +140,10 @@ class RealtimeCoalescer:
         self.batches = 0
         self.windows = 0
         self.first_window = {s: True for s in sources}
+        self.buffer_interval = DEFAULT_BUFFER_INTERVAL_S * (read_bytes / 144000.0)   # spec.BufferInterval(): the fresh part of a window
+        self.model_id = model_id
+        self.overruns = {}                                    # "source:modelID" -> BufferOverrunTracker (getOverrunTracker, process.go:66-76)
+        self.overrun_total = 0
 
     def write(self, source_id, frame: bytes):
         """BufferConsumer.Write for one source: frame = int16 LE mono PCM at the model rate."""
@@ -127,6 +166,17 @@ class RealtimeCoalescer:
         dt = time.perf_counter() - t0
         self.batches += 1
         self.windows += len(ready)
+        # process.go:351-370: inference slower than the buffer interval means the pipeline falls behind real time; every window of
+        # the batch waited for the same call, so the overrun is recorded per source
+        if dt > self.buffer_interval:
+            t_now = time.monotonic() if now is None else now
+            for s, _ in ready:
+                key = s + ":" + self.model_id
+                tr = self.overruns.get(key)
+                if tr is None:
+                    tr = self.overruns[key] = BufferOverrunTracker(s, self.model_id)
+                tr.record(dt, self.buffer_interval, t_now)
+                self.overrun_total += 1
         for (s, w), ri, rc in zip(ready, idx, conf):
             res = [(self.labels[i], float(c)) for i, c in zip(ri, rc)]
             if len(self.queue) >= self.queue_size:           # process.go:405-420: non-blocking send, count the drop

@@ -182,6 +182,21 @@ int bnb_analyze_batch(bnb_classifier* h, const void* pcm, int format, int B, flo
   return guarded([&] { h->eng->analyze_host(pcm, format, B, sensitivity, k, idx, conf, logits_or_null); });
 }
 
+int bnb_analyze_batch_submit(bnb_classifier* h, const void* pcm, int format, int B, float sensitivity, int k, int32_t* idx, float* conf,
+                             float* logits_or_null, int32_t* ticket) {
+  if (int rc = check_batch(h, pcm, format, B)) return rc;
+  if (!idx || !conf || k <= 0 || !ticket) return fail(BNB_ERR_INVALID_ARGUMENT, "idx/conf/ticket NULL or k <= 0");
+  if (B <= 0 || B > h->eng->max_batch()) return fail(BNB_ERR_INVALID_ARGUMENT, "batch must be in 1..max_batch");
+  DeviceRestore dr;
+  return guarded([&] { *ticket = h->eng->submit_host(pcm, format, B, sensitivity, k, idx, conf, logits_or_null, nullptr); });
+}
+
+int bnb_wait(bnb_classifier* h, int32_t ticket) {
+  if (int rc = check_handle(h)) return rc;
+  DeviceRestore dr;
+  return guarded([&] { h->eng->wait_host(ticket); });
+}
+
 int bnb_predict_batch_device(bnb_classifier* h, const void* d_pcm, int format, int B, float* d_logits, float* d_embeddings, void* stream) {
   if (int rc = check_batch(h, d_pcm, format, B)) return rc;
   if (!d_logits) return fail(BNB_ERR_INVALID_ARGUMENT, "logits pointer is NULL");

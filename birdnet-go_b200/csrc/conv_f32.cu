@@ -117,17 +117,20 @@ stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restr
     uint32_t hw[kStemCo / 2], lw[kStemCo / 2];
 #pragma unroll
     for (int c = 0; c < kStemCo / 2; ++c) tc::split2(mix[c].x, mix[c].y, hw[c], lw[c]);
-    op.for_each_tile(h, tid, [&](int ty, int tx, int pr, int pc) {
-      uint8_t* tile = out_img + op.tile_base(b, ty, tx);
+    const uint4 ent = __ldg(op.dst_tbl + (size_t)h * op.W + tid);
+    const uint32_t e4[4] = {ent.x, ent.y, ent.z, ent.w};
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      if (e4[d] == 0xffffffffu) continue;
 #pragma unroll
       for (int q = 0; q < kStemCo / 8; ++q) {
         int st, chunk;
         op.stage_of(q, &st, &chunk);
-        uint8_t* dst = tile + op.in_tile(pr, pc, st, chunk);
+        uint8_t* dst = out_img + op.entry_piece(b, e4[d], st, chunk);
         *reinterpret_cast<uint4*>(dst) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
         *reinterpret_cast<uint4*>(dst + op.st_plane[st]) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
       }
-    });
+    }
     return;
   }
   float* o = out + opos;
@@ -492,7 +495,7 @@ void launch_row_mean2(const float* in, float* out, uint8_t* o_img, int B, int ro
 void launch_stem_mix(const StemMixDev& p, const float* in, float* stem_out_or_null, float* out, int B,
                      cudaStream_t s, LaunchCounter& lc, uint8_t* out_img, const PatchTiles* out_patch) {
   dim3 grid(p.out_h, B);
-  if (out_img && (!out_patch || out_patch->C != kStemCo || out_patch->H != p.out_h || out_patch->W != p.out_w / 2)) throw std::runtime_error("stem_mix: patch layout does not match the pooled stem output");
+  if (out_img && (!out_patch || !out_patch->dst_tbl || out_patch->C != kStemCo || out_patch->H != p.out_h || out_patch->W != p.out_w / 2)) throw std::runtime_error("stem_mix: patch layout does not match the pooled stem output");
   stem_mix_kernel<<<grid, kStemThreads, 0, s>>>(p, in, stem_out_or_null, out, out_img, out_patch ? *out_patch : PatchTiles());
   BNB_LAUNCH_CHECK(lc);
 }

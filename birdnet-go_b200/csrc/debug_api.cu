@@ -228,6 +228,16 @@ int bnb_debug_pw2(const float* A, int M, int K, const float* W, const float* bia
       op = mb2_patch_layout(Po, geom4[0], geom4[1]); Bimg = M / (geom4[0] * geom4[1]);
     }
     const int o_pitch = (N + 7) / 8 * 8;
+    const PatchTables Tr = residual ? patch_build_tables(rp) : PatchTables(), To = out_mode == 2 ? patch_build_tables(op) : PatchTables();
+    DevBuf dtr(Tr.dst.size() * 4), dtrr(Tr.res.size() * 4), dto(To.dst.size() * 4), dtor(To.res.size() * 4);
+    if (residual) {
+      BNB_CUDA(cudaMemcpy(dtr.p, Tr.dst.data(), Tr.dst.size() * 4, cudaMemcpyHostToDevice)); BNB_CUDA(cudaMemcpy(dtrr.p, Tr.res.data(), Tr.res.size() * 4, cudaMemcpyHostToDevice));
+      rp.dst_tbl = dtr.as<uint4>(); rp.res_tbl = dtrr.as<uint32_t>();
+    }
+    if (out_mode == 2) {
+      BNB_CUDA(cudaMemcpy(dto.p, To.dst.data(), To.dst.size() * 4, cudaMemcpyHostToDevice)); BNB_CUDA(cudaMemcpy(dtor.p, To.res.data(), To.res.size() * 4, cudaMemcpyHostToDevice));
+      op.dst_tbl = dto.as<uint4>(); op.res_tbl = dtor.as<uint32_t>();
+    }
     DevBuf da(aimg.size()), dimg(img.size()), db(bz.size() * 4), dg(gate ? (size_t)chunks * K * 4 : 16), dr(rimg.size()),
         doh((size_t)M * o_pitch * 2), dol((size_t)M * o_pitch * 2), d32((size_t)M * N * 4), dop(out_mode == 2 ? op.bytes(Bimg) : 16);
     BNB_CUDA(cudaMemcpy(da.p, aimg.data(), aimg.size(), cudaMemcpyHostToDevice));

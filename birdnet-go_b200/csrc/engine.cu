@@ -77,6 +77,7 @@ void Engine::init(const void* tflite, size_t len, const bnb_options& opts) {
   max_batch_ = opts.max_batch > 0 ? opts.max_batch : 256;
   micro_ = opts.micro_batch > 0 ? opts.micro_batch : 32;
   n_lanes_ = opts.lanes > 0 ? std::min<int>(opts.lanes, kMaxLanes) : 2;
+  use_graphs_ = opts.use_graphs != 0;
   fused_ = !(getenv("BNB_FUSED") && atoi(getenv("BNB_FUSED")) == 0);
   fused_force_ = getenv("BNB_FUSED") && atoi(getenv("BNB_FUSED")) == 2;   // also in keep-intermediates mode (debug)
   if (micro_ > max_batch_) micro_ = max_batch_;
@@ -112,8 +113,7 @@ void Engine::init(const void* tflite, size_t len, const bnb_options& opts) {
     BNB_CUDA(cudaEventCreateWithFlags(&lanes_[i].done, cudaEventDisableTiming));
   }
   BNB_CUDA(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
-  BNB_CUDA(cudaEventCreate(&ev_start_));
-  BNB_CUDA(cudaEventCreate(&ev_stop_));
+  BNB_CUDA(cudaEventCreateWithFlags(&ev_small_, cudaEventDisableTiming));
   upload_weights(P);
   alloc_workspace();
 }
@@ -125,15 +125,19 @@ void Engine::release() noexcept {
   cudaDeviceSynchronize();
   for (int i = 0; i < n_lanes_; ++i) { if (lanes_[i].stream) cudaStreamDestroy(lanes_[i].stream); if (lanes_[i].done) cudaEventDestroy(lanes_[i].done); }
   if (ev_in_) cudaEventDestroy(ev_in_);
+  if (ev_small_) cudaEventDestroy(ev_small_);
   for (void* p : allocs_) cudaFree(p);
   for (auto& kv : keep_bufs_) cudaFree(kv.second.first);
   for (auto& kv : keep_imgs_) cudaFree(kv.second.first);
-  if (h_in_) cudaFreeHost(h_in_);
-  if (h_out_) cudaFreeHost(h_out_);
-  for (cudaEvent_t e : ev_h2d_) cudaEventDestroy(e);
+  for (Slot& S : slots_) {
+    if (S.h_in) cudaFreeHost(S.h_in);
+    if (S.h_out) cudaFreeHost(S.h_out);
+    for (cudaEvent_t e : S.ev_h2d) cudaEventDestroy(e);
+    if (S.start) cudaEventDestroy(S.start);
+    if (S.done) cudaEventDestroy(S.done);
+  }
+  for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second.exec);
   for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
-  if (ev_start_) cudaEventDestroy(ev_start_);
-  if (ev_stop_) cudaEventDestroy(ev_stop_);
   if (compute_) cudaStreamDestroy(compute_);
   if (copy_) cudaStreamDestroy(copy_);
 }
@@ -258,6 +262,9 @@ void Engine::upload_weights(const NetPlan& P) {
       if (b.expand.b) memcpy(be.data(), b.expand.b, (size_t)b.cexp * sizeof(float));
       d.mb2_bias = up(be.data(), be.size());
       d.in_patch = mb2_patch_layout(d.mb2, b.in_h, b.in_w);
+      const PatchTables T = patch_build_tables(d.in_patch);                   // pixel -> (tile, row) lookup tables for the producers' epilogues
+      d.in_patch.dst_tbl = reinterpret_cast<const uint4*>(up_t<uint32_t>(T.dst.data(), T.dst.size()));
+      d.in_patch.res_tbl = up_t<uint32_t>(T.res.data(), T.res.size());
     }
     blocks_.push_back(d);
   }
@@ -324,7 +331,7 @@ void Engine::alloc_workspace() {
     alloc_work2(work2_back_, bb, split_, (int)blocks_.size());
     if (split_ >= (int)blocks_.size()) throw unsupported_model("the network has no small-map blocks for the whole-batch phase");
     mid2_bytes_ = blocks_[split_].in_patch.bytes(1);                      // the split-point tensor = input image of block `split_`
-    mid2_ = alloc_img(bb * mid2_bytes_);
+    mid2_ = alloc_img(bb * mid2_bytes_); mid2_base_ = mid2_;
     const BlockPlan& gl = blocks_.back().g;
     last2_ = alloc_planes(bb * gl.out_h * gl.out_w * plane_pitch(gl.cout));   // the last block's output: plain planes for the im2col kernel
     im2col2_ = alloc_img(RowTiles::make((int)im2col_sz).bytes((long long)bb * post_g_.out_w));
@@ -332,7 +339,7 @@ void Engine::alloc_workspace() {
   } else {
     alloc_work(work_back_, bb, split_, (int)blocks_.size(), 0);
     mid_sz_ = (size_t)gs.out_h * gs.out_w * gs.cout;
-    ws_mid_ = dmalloc(bb * mid_sz_);
+    ws_mid_ = dmalloc(bb * mid_sz_); ws_mid_base_ = ws_mid_;
     ws_im2col_ = dmalloc(bb * im2col_sz);
   }
 }
@@ -574,6 +581,8 @@ void Engine::run_back(const float* mid, int n, float* d_logits, float* d_emb, cu
 void Engine::predict_device(const void* d_pcm, int fmt, int B, float* d_logits, float* d_emb, cudaStream_t s) {
   BNB_CUDA(cudaSetDevice(device_));
   if (!s) s = compute_;
+  ws_mid_ = ws_mid_base_; mid2_ = mid2_base_;
+  BNB_CUDA(cudaStreamWaitEvent(s, ev_small_, 0));
   views_.clear();
   const size_t cb = (size_t)n_samples_ * fmt_bytes(fmt);
   const int lanes = keep_ ? 1 : n_lanes_;
@@ -598,29 +607,40 @@ void Engine::analyze_device(const void* d_pcm, int fmt, int B, float sensitivity
   BNB_CUDA(cudaSetDevice(device_));
   if (!s) s = compute_;
   float* lg = d_logits_or_null;
-  if (!lg) { ensure_host_staging(); lg = d_logits_; }
+  if (!lg) { ensure_host_staging(); lg = slots_[0].d_logits; }
   predict_device(d_pcm, fmt, B, lg, nullptr, s);
   { ProfScope ps(this, C_TOPK, s); launch_sigmoid_topk(lg, B, n_species_, sensitivity, k, d_idx, d_conf, s, lc_); }
 }
 
 // ------------------------------------------------------------------------------------------------
+// Host-buffer entry points.  Two submission slots (device input, device outputs, pinned staging, split-point buffer each) so
+// that ONE caller can keep two batches in flight: the host-to-device copy of batch i+1 (copy stream) and its front phase
+// (lane streams) overlap the back phase of batch i (compute stream).  The synchronous calls are submit + wait.
 void Engine::ensure_host_staging() {
-  if (d_in_) return;
+  if (slots_[0].d_in) return;
   const size_t mbs = (size_t)max_batch_;
   auto dm = [&](size_t bytes) { void* p = nullptr; BNB_CUDA(cudaMalloc(&p, bytes)); allocs_.push_back(p); return p; };
-  d_in_ = dm(mbs * n_samples_ * 4);
-  d_logits_ = static_cast<float*>(dm(mbs * n_species_ * 4));
-  d_emb_ = static_cast<float*>(dm(mbs * emb_dim_ * 4));
   topk_cap_ = 64;
-  d_idx_ = static_cast<int32_t*>(dm(mbs * topk_cap_ * 4));
-  d_conf_ = static_cast<float*>(dm(mbs * topk_cap_ * 4));
-  h_in_bytes_ = mbs * n_samples_ * 4;
-  h_out_bytes_ = mbs * ((size_t)n_species_ + emb_dim_ + 2 * topk_cap_) * 4;
-  BNB_CUDA(cudaHostAlloc(&h_in_, h_in_bytes_, cudaHostAllocDefault));
-  BNB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_out_), h_out_bytes_, cudaHostAllocDefault));
   const int n_micro = ceil_div(max_batch_, micro_);
-  ev_h2d_.resize(n_micro + 4);      // + the ramp of small micro-batches at the head of a host call
-  for (auto& e : ev_h2d_) BNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    Slot& S = slots_[i];
+    S.d_in = dm(mbs * n_samples_ * 4);
+    S.d_logits = static_cast<float*>(dm(mbs * n_species_ * 4));
+    S.d_emb = static_cast<float*>(dm(mbs * emb_dim_ * 4));
+    S.d_idx = static_cast<int32_t*>(dm(mbs * topk_cap_ * 4));
+    S.d_conf = static_cast<float*>(dm(mbs * topk_cap_ * 4));
+    S.h_in_bytes = mbs * n_samples_ * 4;
+    S.off_emb = mbs * (size_t)n_species_ * 4; S.off_idx = S.off_emb + mbs * (size_t)emb_dim_ * 4; S.off_conf = S.off_idx + mbs * topk_cap_ * 4;
+    BNB_CUDA(cudaHostAlloc(&S.h_in, S.h_in_bytes, cudaHostAllocDefault));
+    BNB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&S.h_out), S.off_conf + mbs * topk_cap_ * 4, cudaHostAllocDefault));
+    S.ev_h2d.resize(n_micro + 4);      // + the ramp of small micro-batches at the head of a host call
+    for (auto& e : S.ev_h2d) BNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    BNB_CUDA(cudaEventCreate(&S.start));
+    BNB_CUDA(cudaEventCreate(&S.done));
+    if (i == 0) { S.mid = ws_mid_base_; S.mid2 = mid2_base_; }             // slot 0 shares the split-point buffer with the device entry points
+    else if (v2_) S.mid2 = alloc_img(mbs * mid2_bytes_);
+    else { void* p = dm(mbs * mid_sz_ * sizeof(float)); S.mid = static_cast<float*>(p); }
+  }
 }
 
 namespace {
@@ -631,61 +651,124 @@ bool is_pinned(const void* p) {
 }
 }  // namespace
 
-// Shared body of the two host entry points.  k == 0 -> logits (+emb) only.
 void Engine::predict_host(const void* pcm, int fmt, int B, float* logits, float* emb) {
-  analyze_host(pcm, fmt, B, 0.f, 0, nullptr, nullptr, logits);
-  if (emb) {
-    BNB_CUDA(cudaMemcpyAsync(emb, d_emb_, (size_t)B * emb_dim_ * 4, cudaMemcpyDeviceToHost, compute_));
-    BNB_CUDA(cudaStreamSynchronize(compute_));
-  }
+  wait_host(submit_host(pcm, fmt, B, 0.f, 0, nullptr, nullptr, logits, emb));
 }
 
 void Engine::analyze_host(const void* pcm, int fmt, int B, float sensitivity, int k, int32_t* idx, float* conf, float* logits) {
+  wait_host(submit_host(pcm, fmt, B, sensitivity, k, idx, conf, logits, nullptr));
+}
+
+// the kernel chain of one small batch (B <= micro batch) on ONE stream: what a CUDA graph captures
+void Engine::small_batch_chain(Slot& S, int fmt, int B, float sensitivity, int k, cudaStream_t s) {
+  ws_mid_ = S.mid; mid2_ = S.mid2;
+  run_front(S.d_in, fmt, B, 0, lanes_[0], s);
+  run_back(ws_mid_, B, S.d_logits, S.d_emb, s);
+  if (k > 0) { ProfScope ps(this, C_TOPK, s); launch_sigmoid_topk(S.d_logits, B, n_species_, sensitivity, k, S.d_idx, S.d_conf, s, lc_); }
+}
+
+int Engine::submit_host(const void* pcm, int fmt, int B, float sensitivity, int k, int32_t* idx, float* conf, float* logits, float* emb) {
   BNB_CUDA(cudaSetDevice(device_));
   ensure_host_staging();
   if (k > topk_cap_) throw std::invalid_argument("k exceeds the top-k capacity (64)");
+  const int si = next_slot_;
+  Slot& S = slots_[si];
+  if (S.busy) throw std::invalid_argument("two submissions are already outstanding: wait for the older ticket first");
   const size_t cb = (size_t)n_samples_ * fmt_bytes(fmt);
   const bool src_pinned = is_pinned(pcm);
   views_.clear();
+  ws_mid_ = S.mid; mid2_ = S.mid2;
+  S.B = B; S.k = k; S.u_idx = idx; S.u_conf = conf; S.u_logits = logits; S.u_emb = emb;
   const int lanes = keep_ ? 1 : n_lanes_;
-  BNB_CUDA(cudaEventRecord(ev_start_, compute_));
-  for (int l = 0; l < lanes; ++l) BNB_CUDA(cudaStreamWaitEvent(lanes_[l].stream, ev_start_, 0));   // previous call's back phase is done (stream order)
-  // H2D per micro-batch on the copy stream; compute waits per micro-batch
-  // The first micro-batch's copy cannot overlap any compute of this call, so the head of the batch ramps up:
-  // micro/4, micro/4, micro/2, then full micro-batches (chunks are independent: any split gives the same bits).
-  int mi = 0;
-  for (int i = 0; i < B; ++mi) {
-    int n = micro_;
-    static const int ramp = getenv("BNB_RAMP") ? atoi(getenv("BNB_RAMP")) : 1;     // 0 = none, 1 = /4 /4 /2, 2 = /2 (tuning knob)
-    if (micro_ >= 16 && B > micro_) {
-      if (ramp == 1) n = mi < 2 ? micro_ / 4 : (mi == 2 ? micro_ / 2 : micro_);
-      else if (ramp == 2) n = mi == 0 ? micro_ / 2 : micro_;
+  const bool small = B <= micro_ && !keep_;
+  if (small) {
+    // ---- one micro-batch: everything on the compute stream, replayed from a CUDA graph when enabled (batch-1 latency) ----
+    const char* src = static_cast<const char*>(pcm);
+    if (!src_pinned) { memcpy(S.h_in, src, (size_t)B * cb); src = static_cast<const char*>(S.h_in); }
+    BNB_CUDA(cudaEventRecord(S.start, compute_));
+    for (int l = 0; l < lanes; ++l) BNB_CUDA(cudaStreamWaitEvent(compute_, lanes_[l].done, 0));        // lane 0's workspaces are free
+    BNB_CUDA(cudaMemcpyAsync(S.d_in, src, (size_t)B * cb, cudaMemcpyHostToDevice, compute_));
+    if (use_graphs_ && !profiling_) {
+      uint32_t sbits; memcpy(&sbits, &sensitivity, 4);
+      const GraphKey key{si, fmt, B, k, sbits};
+      auto it = graphs_.find(key);
+      if (it == graphs_.end()) {
+        const long long l0 = lc_.n;
+        cudaGraph_t g = nullptr;
+        BNB_CUDA(cudaStreamBeginCapture(compute_, cudaStreamCaptureModeThreadLocal));
+        try { small_batch_chain(S, fmt, B, sensitivity, k, compute_); }
+        catch (...) { cudaStreamEndCapture(compute_, &g); if (g) cudaGraphDestroy(g); throw; }
+        BNB_CUDA(cudaStreamEndCapture(compute_, &g));
+        GraphEntry ge; ge.kernels = lc_.n - l0;
+        cudaError_t ie = cudaGraphInstantiate(&ge.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) throw cuda_error(ie, "cudaGraphInstantiate", __FILE__, __LINE__);
+        lc_.n = l0;
+        if (graphs_.size() > 64) { for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second.exec); graphs_.clear(); }
+        it = graphs_.emplace(key, ge).first;
+      }
+      BNB_CUDA(cudaGraphLaunch(it->second.exec, compute_));
+      lc_.n += it->second.kernels;
+    } else {
+      small_batch_chain(S, fmt, B, sensitivity, k, compute_);
     }
-    n = std::min(n, B - i);
-    const char* src = static_cast<const char*>(pcm) + (size_t)i * cb;
-    if (!src_pinned) {   // callee copies (process.go:280-291): stage through our pinned buffer
-      memcpy(static_cast<char*>(h_in_) + (size_t)i * cb, src, (size_t)n * cb);
-      src = static_cast<const char*>(h_in_) + (size_t)i * cb;
+    BNB_CUDA(cudaEventRecord(ev_small_, compute_));                      // lane 0's workspaces were used on the compute stream
+  } else {
+    BNB_CUDA(cudaEventRecord(S.start, compute_));
+    for (int l = 0; l < lanes; ++l) BNB_CUDA(cudaStreamWaitEvent(lanes_[l].stream, ev_small_, 0));
+    // H2D per micro-batch on the copy stream; a lane starts a micro-batch as soon as its samples have landed.
+    // The first copy cannot overlap compute of THIS batch, so the head ramps up: micro/4, micro/4, micro/2, then full
+    // micro-batches (chunks are independent: any split gives the same bits).
+    int mi = 0;
+    for (int i = 0; i < B; ++mi) {
+      int n = micro_;
+      static const int ramp = getenv("BNB_RAMP") ? atoi(getenv("BNB_RAMP")) : 1;     // 0 = none, 1 = /4 /4 /2, 2 = /2 (tuning knob)
+      if (micro_ >= 16 && B > micro_) {
+        if (ramp == 1) n = mi < 2 ? micro_ / 4 : (mi == 2 ? micro_ / 2 : micro_);
+        else if (ramp == 2) n = mi == 0 ? micro_ / 2 : micro_;
+      }
+      n = std::min(n, B - i);
+      const char* src = static_cast<const char*>(pcm) + (size_t)i * cb;
+      if (!src_pinned) {   // callee copies (process.go:280-291): stage through our pinned buffer
+        memcpy(static_cast<char*>(S.h_in) + (size_t)i * cb, src, (size_t)n * cb);
+        src = static_cast<const char*>(S.h_in) + (size_t)i * cb;
+      }
+      BNB_CUDA(cudaMemcpyAsync(static_cast<char*>(S.d_in) + (size_t)i * cb, src, (size_t)n * cb, cudaMemcpyHostToDevice, copy_));
+      BNB_CUDA(cudaEventRecord(S.ev_h2d[mi], copy_));
+      Lane& L = lanes_[mi % lanes];
+      BNB_CUDA(cudaStreamWaitEvent(L.stream, S.ev_h2d[mi], 0));
+      run_front(static_cast<const char*>(S.d_in) + (size_t)i * cb, fmt, n, i, L, L.stream);
+      i += n;
     }
-    BNB_CUDA(cudaMemcpyAsync(static_cast<char*>(d_in_) + (size_t)i * cb, src, (size_t)n * cb, cudaMemcpyHostToDevice, copy_));
-    BNB_CUDA(cudaEventRecord(ev_h2d_[mi], copy_));
-    Lane& L = lanes_[mi % lanes];
-    BNB_CUDA(cudaStreamWaitEvent(L.stream, ev_h2d_[mi], 0));
-    run_front(static_cast<const char*>(d_in_) + (size_t)i * cb, fmt, n, i, L, L.stream);
-    i += n;
+    for (int l = 0; l < lanes; ++l) { BNB_CUDA(cudaEventRecord(lanes_[l].done, lanes_[l].stream)); BNB_CUDA(cudaStreamWaitEvent(compute_, lanes_[l].done, 0)); }
+    run_back(ws_mid_, B, S.d_logits, S.d_emb, compute_);
+    if (k > 0) { ProfScope ps(this, C_TOPK, compute_); launch_sigmoid_topk(S.d_logits, B, n_species_, sensitivity, k, S.d_idx, S.d_conf, compute_, lc_); }
   }
-  for (int l = 0; l < lanes; ++l) { BNB_CUDA(cudaEventRecord(lanes_[l].done, lanes_[l].stream)); BNB_CUDA(cudaStreamWaitEvent(compute_, lanes_[l].done, 0)); }
-  run_back(ws_mid_, B, d_logits_, d_emb_, compute_);
+  // results -> pinned staging (asynchronous); wait_host hands them to the caller's buffers
   if (k > 0) {
-    { ProfScope ps(this, C_TOPK, compute_); launch_sigmoid_topk(d_logits_, B, n_species_, sensitivity, k, d_idx_, d_conf_, compute_, lc_); }
-    BNB_CUDA(cudaMemcpyAsync(idx, d_idx_, (size_t)B * k * 4, cudaMemcpyDeviceToHost, compute_));
-    BNB_CUDA(cudaMemcpyAsync(conf, d_conf_, (size_t)B * k * 4, cudaMemcpyDeviceToHost, compute_));
+    BNB_CUDA(cudaMemcpyAsync(S.h_out + S.off_idx, S.d_idx, (size_t)B * k * 4, cudaMemcpyDeviceToHost, compute_));
+    BNB_CUDA(cudaMemcpyAsync(S.h_out + S.off_conf, S.d_conf, (size_t)B * k * 4, cudaMemcpyDeviceToHost, compute_));
   }
-  if (logits) BNB_CUDA(cudaMemcpyAsync(logits, d_logits_, (size_t)B * n_species_ * 4, cudaMemcpyDeviceToHost, compute_));
-  BNB_CUDA(cudaEventRecord(ev_stop_, compute_));
-  BNB_CUDA(cudaStreamSynchronize(compute_));
-  BNB_CUDA(cudaStreamSynchronize(copy_));
-  BNB_CUDA(cudaEventElapsedTime(&last_ms_, ev_start_, ev_stop_));
+  if (logits) BNB_CUDA(cudaMemcpyAsync(S.h_out, S.d_logits, (size_t)B * n_species_ * 4, cudaMemcpyDeviceToHost, compute_));
+  if (emb) BNB_CUDA(cudaMemcpyAsync(S.h_out + S.off_emb, S.d_emb, (size_t)B * emb_dim_ * 4, cudaMemcpyDeviceToHost, compute_));
+  BNB_CUDA(cudaEventRecord(S.done, compute_));
+  S.busy = true; S.ticket = ++tickets_;
+  next_slot_ ^= 1;
+  return (int)(S.ticket & 0x7fffffff);
+}
+
+void Engine::wait_host(int ticket) {
+  BNB_CUDA(cudaSetDevice(device_));
+  Slot* S = nullptr;
+  for (Slot& c : slots_) if (c.busy && (int)(c.ticket & 0x7fffffff) == ticket) S = &c;
+  if (!S) throw std::invalid_argument("unknown or already completed ticket");
+  BNB_CUDA(cudaEventSynchronize(S->done));
+  S->busy = false;
+  BNB_CUDA(cudaEventElapsedTime(&last_ms_, S->start, S->done));
+  const size_t B = (size_t)S->B, k = (size_t)S->k;
+  if (S->k > 0) { memcpy(S->u_idx, S->h_out + S->off_idx, B * k * 4); memcpy(S->u_conf, S->h_out + S->off_conf, B * k * 4); }
+  if (S->u_logits) memcpy(S->u_logits, S->h_out, B * n_species_ * 4);
+  if (S->u_emb) memcpy(S->u_emb, S->h_out + S->off_emb, B * emb_dim_ * 4);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <tuple>
 #include <memory>
 #include <string>
 #include <vector>
@@ -65,6 +66,10 @@ class Engine {
   // host buffers: pinned staging, H2D/compute overlap per micro-batch, D2H, synchronous
   void predict_host(const void* pcm, int fmt, int B, float* logits, float* emb);
   void analyze_host(const void* pcm, int fmt, int B, float sensitivity, int k, int32_t* idx, float* conf, float* logits);
+  // asynchronous form: returns a ticket once the work is enqueued; the outputs are valid after wait_host(ticket).  At most two
+  // tickets may be outstanding.  k == 0 -> no top-k; logits / emb may be null.
+  int submit_host(const void* pcm, int fmt, int B, float sensitivity, int k, int32_t* idx, float* conf, float* logits, float* emb);
+  void wait_host(int ticket);
 
   void keep_intermediates(bool on) { keep_ = on; }
   // per-category device timing (CUDA events around every launch); see bnb_profile_* in the C ABI
@@ -153,12 +158,27 @@ class Engine {
   std::map<int, TensorView> views_;
 
   // full-batch device buffers for the host path
-  void* d_in_ = nullptr; float* d_logits_ = nullptr; float* d_emb_ = nullptr; int32_t* d_idx_ = nullptr; float* d_conf_ = nullptr;
-  void* h_in_ = nullptr; float* h_out_ = nullptr; size_t h_in_bytes_ = 0, h_out_bytes_ = 0;
+  // host-path submission slots (two batches in flight: copy + front of i+1 overlap the back phase of i)
+  struct Slot {
+    void* d_in = nullptr; float* d_logits = nullptr; float* d_emb = nullptr; int32_t* d_idx = nullptr; float* d_conf = nullptr;
+    void* h_in = nullptr; uint8_t* h_out = nullptr; size_t h_in_bytes = 0, off_emb = 0, off_idx = 0, off_conf = 0;
+    std::vector<cudaEvent_t> ev_h2d; cudaEvent_t start = nullptr, done = nullptr;
+    float* mid = nullptr; uint8_t* mid2 = nullptr;          // split-point buffer of this slot (fp32 chain / plane images)
+    bool busy = false; long long ticket = 0; int B = 0, k = 0;
+    int32_t* u_idx = nullptr; float *u_conf = nullptr, *u_logits = nullptr, *u_emb = nullptr;   // the caller's output buffers
+  };
+  Slot slots_[2]; int next_slot_ = 0; long long tickets_ = 0;
+  void small_batch_chain(Slot& S, int fmt, int B, float sensitivity, int k, cudaStream_t s);
+  // CUDA graphs of the single-micro-batch chain, keyed by (slot, format, batch, k, sensitivity bits)
+  struct GraphKey { int slot, fmt, B, k; uint32_t sens; bool operator<(const GraphKey& o) const { return std::tie(slot, fmt, B, k, sens) < std::tie(o.slot, o.fmt, o.B, o.k, o.sens); } };
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; long long kernels = 0; };
+  std::map<GraphKey, GraphEntry> graphs_;
+  bool use_graphs_ = false;
+  cudaEvent_t ev_small_ = nullptr;                       // end of the last single-stream (small batch) chain: lane streams order after it
+  float* ws_mid_base_ = nullptr; uint8_t* mid2_base_ = nullptr;
   int topk_cap_ = 0;
   cudaStream_t compute_ = nullptr, copy_ = nullptr;
-  std::vector<cudaEvent_t> ev_h2d_;
-  cudaEvent_t ev_start_ = nullptr, ev_stop_ = nullptr;
+
 };
 
 }  // namespace bnb

@@ -19,6 +19,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <vector>
+
 #ifndef __host__
 #define __host__
 #define __device__
@@ -58,6 +60,11 @@ struct PatchTiles {
   uint32_t tile_bytes = 0;
   uint32_t magic_t = 0;                            // ceil(65536 / (TH*S)): u / (TH*S) == (u * magic_t) >> 16 for u < 65536 / (TH*S)
   uint32_t hw = 0, magic_hw = 0;                   // H*W and floor(2^32 / (H*W))
+  // Device lookup tables (null on the host side): where pixel p = h*W + w of a chunk goes.  dst_tbl[p] = up to four entries
+  // (tile index inside the chunk << 8 | patch row n), 0xffffffff = unused; res_tbl[p] = the entry of the tile in which the
+  // pixel is interior.  They replace for_each_tile / interior in the kernels' epilogues (scalar address arithmetic was the
+  // critical path of the project GEMM's epilogue: profiles/r02 timelines).
+  const uint4* dst_tbl = nullptr; const uint32_t* res_tbl = nullptr;
 
   __host__ __device__ size_t bytes(long long B) const { return (size_t)B * tiles_h * tiles_w * tile_bytes; }
   __host__ __device__ void split_pixel(uint32_t m, int* b, int* h, int* w) const {      // m = (b*H + h)*W + w
@@ -74,6 +81,16 @@ struct PatchTiles {
   // offset of the piece inside ONE tile image (hi plane; lo = + st_plane[s]) for patch position (prow, pcol)
   __host__ __device__ uint32_t in_tile(int prow, int pcol, int s, int chunk) const {
     return st_off[s] + lay_swz((uint32_t)(prow * PW + pcol), (uint32_t)chunk, (uint32_t)st_rb[s]);
+  }
+  // offset of the hi-plane piece for a table entry (tile << 8 | n) of chunk b; the lo plane is + st_plane[s]
+  __host__ __device__ size_t entry_piece(int b, uint32_t entry, int s, int chunk) const {
+    return ((size_t)b * (size_t)(tiles_h * tiles_w) + (entry >> 8)) * tile_bytes + st_off[s] + lay_swz(entry & 255u, (uint32_t)chunk, (uint32_t)st_rb[s]);
+  }
+  __host__ __device__ void split_chunk(uint32_t m, int* b, uint32_t* pix) const {          // m = b*H*W + pix
+    uint32_t q = (uint32_t)(((uint64_t)m * magic_hw) >> 32);
+    uint32_t r = m - q * hw;
+    if (r >= hw) { ++q; r -= hw; }
+    *b = (int)q; *pix = r;
   }
   __host__ __device__ size_t tile_base(int b, int ty, int tx) const { return ((size_t)((size_t)b * tiles_h + ty) * tiles_w + tx) * tile_bytes; }
   // every tile that holds pixel (h, w): calls f(tile_y, tile_x, prow, pcol); at most 4 tiles
@@ -100,5 +117,24 @@ struct PatchTiles {
     *ty = t; *prow = h - t * TH + 1; *tx = w >> log2TW; *pcol = (w & (TW - 1)) + 1;
   }
 };
+
+// host: the two lookup tables of a layout (upload them and point dst_tbl / res_tbl at the device copies)
+struct PatchTables { std::vector<uint32_t> dst /* 4 per pixel */, res /* 1 per pixel */; };
+inline PatchTables patch_build_tables(const PatchTiles& t) {
+  PatchTables T;
+  T.dst.assign((size_t)t.H * t.W * 4, 0xffffffffu);
+  T.res.assign((size_t)t.H * t.W, 0xffffffffu);
+  for (int h = 0; h < t.H; ++h)
+    for (int w = 0; w < t.W; ++w) {
+      int k = 0;
+      const size_t p = (size_t)h * t.W + w;
+      t.for_each_tile(h, w, [&](int ty, int tx, int pr, int pc) {
+        const uint32_t e = ((uint32_t)(ty * t.tiles_w + tx) << 8) | (uint32_t)(pr * t.PW + pc);
+        T.dst[p * 4 + k++] = e;
+        if (t.S == 1 && pr >= 1 && pr <= t.TH && pc >= 1 && pc <= t.TW) T.res[p] = e;
+      });
+    }
+  return T;
+}
 
 }  // namespace bnb

@@ -52,6 +52,8 @@ struct Mb2Args {
   int TH, PH, n_mma, tiles_h, tiles_w;
   int n_units, k_stages, rot_mode;       // rot_mode: 0 none, 1 last unit replicated over the four lane quarters, 2 four rotated versions of the only unit
   int a_slots, b_slots, a_resident, n_img_units;
+  int dbg;                                // BNB_MB2_DBG timing experiments (wrong results): 1 = epilogue skips its TMEM loads, 2 = no MMAs issued, 4 = epilogue skips its stores
+  int mma_batch, mma_cross;               // units whose MMAs the issuer interleaves (<= kGroups); may a round span two tiles
   uint32_t a_slot_bytes, a_region_bytes, b_slot_bytes, img_unit_bytes;
   long long* trace;                      // debug timeline (BNB_MB2_TRACE): [2 CTAs][8 events][64 slots] clock64 stamps, else null
   uint32_t st_rb[kMb2MaxStages], st_ksteps[kMb2MaxStages], st_k0[kMb2MaxStages], st_aoff[kMb2MaxStages],
@@ -65,15 +67,18 @@ struct Mb2Args {
     a.trace[((blockIdx.x == 0 ? 0 : 1) * 8 + (ev)) * 64 + (i)] = clock64(); } while (0)
 
 template <int PW>
-__device__ __forceinline__ void load_row(float (&dst)[PW], uint32_t taddr, bool row_in, bool left_oob, bool right_oob, float be) {
+__device__ __forceinline__ void load_row(float (&dst)[PW], uint32_t taddr, bool row_in, bool left_oob, bool right_oob, float be, int dbg = 0) {
   if (!row_in) {                                  // warp-uniform: the whole patch row lies outside the image
 #pragma unroll
     for (int i = 0; i < PW; ++i) dst[i] = 0.f;
     return;
   }
   uint32_t raw[PW];
-  tmem_ld_n<PW>(taddr, raw);
-  tmem_ld_wait();
+  if (!(dbg & 1)) { tmem_ld_n<PW>(taddr, raw); tmem_ld_wait(); }
+  else {
+#pragma unroll
+    for (int i = 0; i < PW; ++i) raw[i] = 0x3f000000u + (uint32_t)i;
+  }
 #pragma unroll
   for (int i = 0; i < PW; ++i) dst[i] = __uint_as_float(raw[i]) + be;
   // zero padding lives in the EXPANDED domain.  The columns outside the image hold whatever the patch image held before
@@ -203,14 +208,21 @@ mbconv2_kernel(const Mb2Args a) {
     }
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ======================================================================
-    if (lane == 0) {
+    // The WHOLE warp runs this loop with warp-uniform values (barrier waits, descriptor arithmetic), and only the tcgen05
+    // instructions themselves are predicated on one lane: ptxas then keeps descriptors / addresses in uniform registers.  With
+    // the loop inside `if (lane == 0)` every operand was computed in vector registers and moved with R2UR, and the single
+    // issuing thread spent ~230 cycles of dependent scalar work per MMA (profiles/r02 timeline: 15 MMAs = 3.7 k cycles per unit,
+    // the kernel's critical path).  Descriptors are built once per (unit, stage); a k-step only adds a constant.
+    {
+      const bool leader = lane == 0;
       const uint32_t idesc = make_idesc_mn(128u, (uint32_t)a.n_mma);
       uint32_t it = 0, q = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int bs = it % a.b_slots;
         mbar_wait(b_full(bs), (it / a.b_slots) & 1);
-        MB2_TRACE(2, it);
+        if (leader) MB2_TRACE(2, it);
         const int rot = it & 3;
+        const uint32_t sb0 = b_ring + (uint32_t)bs * a.b_slot_bytes;
         for (int u = 0; u < a.n_units; ++u) {
           const uint32_t seq = it * a.n_units + u;
           const int buf = seq % kGroups;
@@ -223,22 +235,28 @@ mbconv2_kernel(const Mb2Args a) {
             else { slot = q % a.a_slots; ph = (q / a.a_slots) & 1; }
             mbar_wait(a_full(slot), ph);
             tc_fence_after();
-            const uint32_t sa = a_addr(slot);
-            const uint32_t sb = b_ring + (uint32_t)bs * a.b_slot_bytes + a.st_boff[s];
-            const uint64_t d_whi = make_desc_rb(sa, a.st_rb[s]), d_wlo = make_desc_rb(sa + a.st_aplane[s], a.st_rb[s]);
-            const uint64_t d_xhi = make_desc_rb(sb, a.st_rb[s]), d_xlo = make_desc_rb(sb + a.st_bplane[s], a.st_rb[s]);
-            for (uint32_t kk = 0; kk < a.st_ksteps[s]; ++kk) {
-              const uint64_t adv = (uint64_t)(kk * 2);           // +32 bytes (>> 4) inside the swizzle row
-              umma(d_tmem, d_whi + adv, d_xhi + adv, idesc, (s | kk) != 0);
-              umma(d_tmem, d_wlo + adv, d_xhi + adv, idesc, 1);
-              umma(d_tmem, d_whi + adv, d_xlo + adv, idesc, 1);
+            const uint32_t sa = a_addr(slot), sb = sb0 + a.st_boff[s], rb = a.st_rb[s];
+            const uint64_t d_whi = make_desc_rb(sa, rb), d_wlo = make_desc_rb(sa + a.st_aplane[s], rb);
+            const uint64_t d_xhi = make_desc_rb(sb, rb), d_xlo = make_desc_rb(sb + a.st_bplane[s], rb);
+            const uint32_t nk = a.st_ksteps[s];
+            if (leader && !(a.dbg & 2)) {
+#pragma unroll
+              for (uint32_t kk = 0; kk < 4; ++kk) {
+                if (kk < nk) {
+                  const uint64_t adv = (uint64_t)(kk * 2);           // +32 bytes (>> 4) inside the swizzle row
+                  umma(d_tmem, d_whi + adv, d_xhi + adv, idesc, (s | (int)kk) != 0);
+                  umma(d_tmem, d_wlo + adv, d_xhi + adv, idesc, 1);
+                  umma(d_tmem, d_whi + adv, d_xlo + adv, idesc, 1);
+                }
+              }
             }
-            if (!a.a_resident) umma_commit(a_empty(slot));
+            __syncwarp();
+            if (leader && !a.a_resident) umma_commit(a_empty(slot));
           }
-          umma_commit(t_full(buf));
-          MB2_TRACE(3, seq);
+          if (leader) { umma_commit(t_full(buf)); MB2_TRACE(3, seq); }
         }
-        umma_commit(b_empty(bs));
+        if (leader) umma_commit(b_empty(bs));
+        __syncwarp();
       }
     }
   } else {
@@ -282,7 +300,7 @@ mbconv2_kernel(const Mb2Args a) {
         float rA[PW], rB[PW], rC[PW];
         auto ld = [&](float (&dst)[PW], int r) {
           const int hi = hi0 + r;
-          load_row<PW>(dst, tbuf + (uint32_t)(r * PW), hi >= 0 && hi < a.H, left_oob, right_oob, be);
+          load_row<PW>(dst, tbuf + (uint32_t)(r * PW), hi >= 0 && hi < a.H, left_oob, right_oob, be, a.dbg);
           if (r == a.PH - 1) { tc_fence_before(); mbar_arrive(t_empty(g)); if (lane == 0 && quarter == 0) MB2_TRACE(5, seq); }     // accumulator fully read: hand the buffer back
         };
         // RowTiles image of the result: row m = (b*Ho + ho)*Wo + wo, 64-channel stage c >> 6, chunk (c >> 3) & 7
@@ -291,7 +309,7 @@ mbconv2_kernel(const Mb2Args a) {
         const uint32_t chunk16 = (uint32_t)((c >> 3) & 7) << 4;
         auto out = [&](const float (&r0)[PW], const float (&r1)[PW], const float (&r2)[PW], int oh) {
           const uint32_t m = m_tile0 + (uint32_t)oh * a.Wo;
-          out_row<S, TW, PW>(r0, r1, r2, wd, bd, out_c + (size_t)(m >> 7) * a.d_tile_bytes + (m & 127u) * 128u, chunk16, m & 7u, active, lsum);
+          out_row<S, TW, PW>(r0, r1, r2, wd, bd, out_c + (size_t)(m >> 7) * a.d_tile_bytes + (m & 127u) * 128u, chunk16, m & 7u, active && !(a.dbg & 4), lsum);
         };
         if (S == 1) {
           ld(rA, 0); ld(rB, 1);
@@ -468,6 +486,10 @@ void launch_mbconv2(const Mb2Plan& P, const Mb2Launch& L, cudaStream_t s, Launch
   a.TH = P.TH; a.PH = P.PH; a.n_mma = P.n_mma; a.tiles_h = P.tiles_h; a.tiles_w = P.tiles_w;
   a.n_units = P.n_units; a.k_stages = P.k_stages; a.rot_mode = rot_mode_of(P);
   a.a_slots = P.a_slots; a.b_slots = P.b_slots; a.a_resident = P.a_resident; a.n_img_units = a.rot_mode == 2 ? 4 : P.n_units;
+  a.mma_batch = P.a_resident ? kGroups : std::max(1, std::min(kGroups, P.a_slots / P.k_stages));
+  a.mma_cross = P.b_slots >= 2 ? 1 : 0;
+  { static const int dbg = getenv("BNB_MB2_DBG") ? atoi(getenv("BNB_MB2_DBG")) : 0; a.dbg = dbg; }
+  { static const int forced = getenv("BNB_MB2_BATCH") ? atoi(getenv("BNB_MB2_BATCH")) : 0; if (forced > 0) a.mma_batch = std::min(a.mma_batch, forced); }
   a.a_slot_bytes = P.a_slot_bytes; a.a_region_bytes = P.a_region_bytes; a.b_slot_bytes = P.b_slot_bytes; a.img_unit_bytes = P.img_unit_bytes;
   for (int st = 0; st < P.k_stages; ++st) {
     a.st_rb[st] = P.st_rb[st]; a.st_ksteps[st] = P.st_ksteps[st]; a.st_k0[st] = P.st_k0[st]; a.st_aoff[st] = P.st_aoff[st];

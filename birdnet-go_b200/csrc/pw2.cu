@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <stdexcept>
 #include <string>
@@ -44,6 +45,7 @@ struct Pw2Args {
   int o_pitch, out_mode;                  // out_mode: 0 fp32, 1 plain planes, 2 PatchTiles image
   uint32_t a_tile_bytes;
   int n_pad, k_pad, n_tiles, bn, stages, b_res, conv, out_vec;
+  int n_acc;                              // independent accumulators per tile (column ranges of bn): MMA i goes to accumulator i % n_acc
   PatchTiles rp, op;                      // residual / output patch layouts
   long long* trace;                       // debug timeline (BNB_PW2_TRACE): [2 CTAs][8 events][64 slots] clock64 stamps, else null
 };
@@ -184,7 +186,11 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
     }
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ===========================================================================
-    if (lane == 0) {
+    // Whole warp, warp-uniform values, only the tcgen05 instructions predicated on one lane (descriptors stay in uniform
+    // registers; see mbconv2.cu).  The products of a tile are dealt round-robin to n_acc column ranges of the accumulator
+    // buffer (their sum is the result; the epilogue adds the ranges in a fixed order).
+    {
+      const bool leader = lane == 0;
       uint32_t it = 0, tcount = 0;
       if (a.b_res) mbar_wait(bres_bar, 0);
       const int n0 = nt_fix * a.bn;
@@ -195,26 +201,35 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
         mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccCols;
+        uint32_t acc = 0, started = 0;                     // next accumulator; how many accumulators have received their first product
         for (int ks = 0; ks < k_stages; ++ks, ++it) {
           const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
           mbar_wait(a.conv ? full_bar(s) : tma_bar(s), ph);
-          if (!a.conv) PW2_TRACE(2, it);
+          if (leader && !a.conv) PW2_TRACE(2, it);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + kABytes);
           const uint32_t sb = a.b_res ? bres + (uint32_t)ks * 2 * b_bytes : sa + 2 * kABytes;
           const uint64_t d_bhi = make_desc(sb), d_blo = make_desc(sb + b_bytes);
           const int kk_n = min(kBK, a.k_pad - ks * kBK) / 16;
-          for (int kk = 0; kk < kk_n; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 2);
-            umma(d_tmem, d_ahi + adv, d_bhi + adv, idesc, (ks | kk) != 0);
-            umma(d_tmem, d_alo + adv, d_bhi + adv, idesc, 1);
-            umma(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kk < kk_n) {
+              const uint64_t adv = (uint64_t)(kk * 2);
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {                // hi*hi, lo*hi, hi*lo
+                const uint32_t d = d_tmem + acc * (uint32_t)bn;
+                if (leader) umma(d, (t == 1 ? d_alo : d_ahi) + adv, (t == 2 ? d_blo : d_bhi) + adv, idesc, started >= (uint32_t)a.n_acc);
+                acc = (acc + 1 == (uint32_t)a.n_acc) ? 0u : acc + 1;
+                ++started;
+              }
+            }
           }
-          umma_commit(empty_bar(s));
-          PW2_TRACE(4, it);
+          __syncwarp();
+          if (leader) { umma_commit(empty_bar(s)); PW2_TRACE(4, it); }
         }
-        umma_commit(tfull_bar(buf));
+        if (leader) umma_commit(tfull_bar(buf));
+        __syncwarp();
       }
     }
   } else {
@@ -250,10 +265,9 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
             const int mrow = m_w + 16 * j + (lane >> 1);
             rvh[j] = make_uint4(0, 0, 0, 0); rvl[j] = rvh[j];
             if (mrow < a.M && pcol < a.o_pitch) {
-              int b, h, w, ty, tx, pr, pc;
-              a.rp.split_pixel((uint32_t)mrow, &b, &h, &w);
-              a.rp.interior(h, w, &ty, &tx, &pr, &pc);
-              const uint8_t* src = a.r_img + a.rp.tile_base(b, ty, tx) + a.rp.in_tile(pr, pc, rs, rchunk);
+              int b; uint32_t pix;
+              a.rp.split_chunk((uint32_t)mrow, &b, &pix);
+              const uint8_t* src = a.r_img + a.rp.entry_piece(b, __ldg(a.rp.res_tbl + pix), rs, rchunk);
               rvh[j] = __ldg(reinterpret_cast<const uint4*>(src));
               rvl[j] = __ldg(reinterpret_cast<const uint4*>(src + a.rp.st_plane[rs]));
             }
@@ -263,6 +277,13 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
         tmem_ld16(taddr + (uint32_t)c0, r);
         __syncwarp();                                      // previous chunk's read-back of s_out is complete
         tmem_ld_wait();
+        for (int ac = 1; ac < a.n_acc; ++ac) {             // add the other accumulators of the tile (fixed order)
+          uint32_t r2[16];
+          tmem_ld16(taddr + (uint32_t)(ac * bn + c0), r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4 * q));      // bias is zero-padded past n_pad
@@ -296,15 +317,20 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
                 *reinterpret_cast<uint4*>(a.oh + (size_t)mrow * a.o_pitch + pcol) = ho;
                 *reinterpret_cast<uint4*>(a.ol + (size_t)mrow * a.o_pitch + pcol) = lo;
               } else {
-                // the next block's PatchTiles image: the pixel goes into every tile whose halo patch contains it (<= 4)
-                int b, h, w;
-                a.op.split_pixel((uint32_t)mrow, &b, &h, &w);
+                // the next block's PatchTiles image: the pixel goes into every tile whose halo patch contains it (<= 4, from the table)
+                int b; uint32_t pix;
+                a.op.split_chunk((uint32_t)mrow, &b, &pix);
                 const uint32_t lo_off = a.op.st_plane[os];
-                a.op.for_each_tile(h, w, [&](int ty, int tx, int pr, int pc) {
-                  uint8_t* dst = a.o_img + a.op.tile_base(b, ty, tx) + a.op.in_tile(pr, pc, os, ochunk);
-                  *reinterpret_cast<uint4*>(dst) = ho;
-                  *reinterpret_cast<uint4*>(dst + lo_off) = lo;
-                });
+                const uint4 ent = __ldg(a.op.dst_tbl + pix);
+                const uint32_t e4[4] = {ent.x, ent.y, ent.z, ent.w};
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                  if (e4[d] != 0xffffffffu) {
+                    uint8_t* dst = a.o_img + a.op.entry_piece(b, e4[d], os, ochunk);
+                    *reinterpret_cast<uint4*>(dst) = ho;
+                    *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+                  }
+                }
               }
             }
           }
@@ -383,7 +409,8 @@ void launch_pw2(const PwTcLayer& L, const Pw2Launch& p, cudaStream_t s, LaunchCo
   const int n_out = (p.out32 != nullptr) + (p.oh != nullptr) + (p.o_img != nullptr);
   if (n_out != 1) throw std::runtime_error("pw2: exactly one output (fp32, plain planes, patch image) must be set");
   if (p.oh && (p.o_pitch % 8 || p.o_pitch < p.N)) throw std::runtime_error("pw2: plane pitch must be a multiple of 8 and >= N");
-  if (p.o_img && p.o_patch.C != p.N) throw std::runtime_error("pw2: output patch layout does not match N");
+  if (p.o_img && (p.o_patch.C != p.N || !p.o_patch.dst_tbl)) throw std::runtime_error("pw2: output patch layout does not match N or has no device tables");
+  if (p.r_img && !p.r_patch.res_tbl) throw std::runtime_error("pw2: residual patch layout has no device table");
   if (p.r_img && (p.r_patch.C != p.N || p.r_patch.S != 1 || p.out32)) throw std::runtime_error("pw2: residual needs a stride-1 patch layout with N channels and a plane output");
   if (p.gate && (p.K % 8 || p.rows_per_chunk <= 0)) throw std::runtime_error("pw2: gated layers need K % 8 == 0");
   int bn = 0, stages = 0, b_res = 0;
@@ -400,6 +427,8 @@ void launch_pw2(const PwTcLayer& L, const Pw2Launch& p, cudaStream_t s, LaunchCo
   a.rp = p.r_patch; a.op = p.o_patch;
   a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.bn = bn; a.n_tiles = (L.n_pad + bn - 1) / bn; a.stages = stages; a.b_res = b_res;
   a.conv = p.gate != nullptr ? 1 : 0;
+  a.n_acc = 3 * bn <= kAccCols ? 3 : (2 * bn <= kAccCols ? 2 : 1);
+  { static const int forced = getenv("BNB_PW2_NACC") ? atoi(getenv("BNB_PW2_NACC")) : 0; if (forced > 0) a.n_acc = std::min(a.n_acc, forced); }
   a.out_vec = (p.N % 4 == 0) ? 4 : ((p.N % 2 == 0) ? 2 : 1);
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int tiles = m_tiles * a.n_tiles;

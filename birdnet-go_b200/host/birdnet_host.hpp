@@ -10,6 +10,8 @@
 //   convert16BitToFloat32                        /root/reference/internal/analysis/process.go:479-497
 //   AnalysisBuffer (overwrite ring + overlap)    /root/reference/internal/audiocore/buffer/analysis.go:30-251
 //   Results / ResultsQueue message               /root/reference/internal/classifier/queue.go:10-28
+//   bufferOverrunTracker / recordBufferOverrun   /root/reference/internal/analysis/process.go:44-215, 351-370
+//   AnalyzeFileBatched (config-2 driver)         doc/wiki/file-analysis.md:1-13 semantics through the batched int16 entry point
 //
 // Header-only; link with -lbirdnet_b200.
 #pragma once
@@ -17,6 +19,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -177,6 +180,101 @@ class BirdNET {
   double sensitivity_;
   std::mutex mu_;
 };
+
+// Tumbling-window overrun accounting per (source, model): process.go:44-215.  `now` is a monotonic clock in seconds supplied by
+// the caller (the reference uses time.Now()); a report is produced when a window of bufferOverrunReportCooldown expires with at
+// least bufferOverrunMinCount overruns (the reference sends it to Sentry).
+constexpr double bufferOverrunReportCooldown = 3600.0;   // process.go:36
+constexpr long long bufferOverrunMinCount = 10;          // process.go:39
+struct OverrunReport { std::string source, modelID; long long overrunCount = 0; double maxElapsed = 0, bufferLength = 0, window = 0; };
+class BufferOverrunTracker {
+ public:
+  BufferOverrunTracker(std::string source, std::string modelID) : source_(std::move(source)), model_(std::move(modelID)) {}
+  // recordBufferOverrun (process.go:177-215); returns true and fills *rep when the expired window is reported
+  bool Record(double elapsed, double bufferLen, double now, OverrunReport* rep = nullptr) {
+    std::lock_guard<std::mutex> lk(mu_);
+    bool reported = false;
+    if (!started_) { windowStart_ = now; started_ = true; }
+    if (now - windowStart_ >= bufferOverrunReportCooldown) {
+      if (count_ >= bufferOverrunMinCount) {
+        if (rep) { rep->source = source_; rep->modelID = model_; rep->overrunCount = count_; rep->maxElapsed = maxElapsed_; rep->bufferLength = bufferLength_; rep->window = now - windowStart_; }
+        reported = true;
+      }
+      count_ = 0; maxElapsed_ = 0; windowStart_ = now;
+    }
+    ++count_;
+    if (elapsed > maxElapsed_) { maxElapsed_ = elapsed; bufferLength_ = bufferLen; }
+    return reported;
+  }
+  long long Count() const { return count_; }
+  double MaxElapsed() const { return maxElapsed_; }
+ private:
+  std::string source_, model_;
+  long long count_ = 0; bool started_ = false; double windowStart_ = 0, maxElapsed_ = 0, bufferLength_ = 0;
+  std::mutex mu_;
+};
+// getOverrunTracker (process.go:66-76): one tracker per "source:modelID"
+class OverrunTrackers {
+ public:
+  BufferOverrunTracker& Get(const std::string& source, const std::string& modelID) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto& p = map_[source + ":" + modelID];
+    if (!p) p.reset(new BufferOverrunTracker(source, modelID));
+    return *p;
+  }
+  size_t Size() const { return map_.size(); }
+ private:
+  std::map<std::string, std::unique_ptr<BufferOverrunTracker>> map_;
+  std::mutex mu_;
+};
+// the check of ProcessData (process.go:351-370): elapsed > BufferInterval -> record an overrun for that source
+inline bool checkProcessingOverrun(OverrunTrackers& trackers, const std::string& source, const std::string& modelID, double elapsed,
+                                   double bufferInterval, double now, OverrunReport* rep = nullptr) {
+  if (elapsed <= bufferInterval) return false;
+  trackers.Get(source, modelID).Record(elapsed, bufferInterval, now, rep);
+  return true;
+}
+
+// One detection row of the offline file analysis
+struct Detection { double Begin = 0, End = 0; std::string Species; float Confidence = 0.f; };
+
+// Batched offline file analysis (BASELINE config 2): slide the 3 s window with `overlapSeconds` of overlap over mono int16 PCM, run
+// ALL windows through bnb_analyze_batch(BNB_PCM_S16) in batches of <= maxBatch (device-side /32768, sigmoid(sensitivity * logit),
+// top-10) and keep the results >= threshold, window order, descending confidence inside a window.  A trailing partial window of
+// >= half the window length is zero-padded.
+inline std::vector<Detection> AnalyzeFileBatched(inference::B200Classifier& clf, const std::vector<std::string>& labels, const int16_t* pcm,
+                                                 size_t nSamples, double overlapSeconds, double sensitivity, double threshold, int maxBatch = 256,
+                                                 int sampleRate = 48000) {
+  const size_t n = (size_t)clf.NumSamples();
+  const long long step = (long long)n - (long long)std::llround(overlapSeconds * sampleRate);
+  if (step <= 0) throw std::invalid_argument("overlap must be shorter than the analysis window");
+  std::vector<size_t> starts;
+  for (size_t s0 = 0; s0 + n <= nSamples; s0 += (size_t)step) starts.push_back(s0);
+  const size_t tail = starts.empty() ? 0 : starts.back() + (size_t)step;
+  if (nSamples > tail && nSamples - tail >= n / 2) starts.push_back(tail);
+  std::vector<Detection> out;
+  std::vector<int16_t> win;
+  std::vector<int32_t> idx; std::vector<float> conf;
+  for (size_t i = 0; i < starts.size(); i += (size_t)maxBatch) {
+    const int B = (int)std::min((size_t)maxBatch, starts.size() - i);
+    win.assign((size_t)B * n, 0);
+    for (int j = 0; j < B; ++j) {
+      const size_t s0 = starts[i + j], len = std::min(n, nSamples - s0);
+      std::memcpy(&win[(size_t)j * n], pcm + s0, len * sizeof(int16_t));
+    }
+    clf.AnalyzeBatch(win.data(), BNB_PCM_S16, B, (float)sensitivity, defaultTopKResults, &idx, &conf);
+    for (int j = 0; j < B; ++j)
+      for (int r = 0; r < defaultTopKResults; ++r) {
+        const float c = conf[(size_t)j * defaultTopKResults + r];
+        if (c >= (float)threshold) {
+          Detection d; d.Begin = (double)starts[i + j] / sampleRate; d.End = d.Begin + (double)n / sampleRate;
+          d.Species = labels[(size_t)idx[(size_t)j * defaultTopKResults + r]]; d.Confidence = c;
+          out.push_back(d);
+        }
+      }
+  }
+  return out;
+}
 
 // Overwrite-mode byte ring + overlap prefix: consecutive reads share `overlapSize` bytes (analysis.go:30-251).
 class AnalysisBuffer {

@@ -76,6 +76,23 @@ static void test_postprocessing() {
   CHECK(f.size() == 5 && f[0] == 0.f && f[1] == 1.f / 32768.f && f[2] == -1.f / 32768.f && f[3] == 32767.f / 32768.f && f[4] == -1.f);
 }
 
+static void test_overrun_tracker() {
+  OverrunTrackers tr;
+  OverrunReport rep;
+  CHECK(!checkProcessingOverrun(tr, "rtsp_1", "BirdNET_V2.4", 0.4, 1.5, 0.0));          // faster than the buffer interval: nothing recorded
+  CHECK(tr.Size() == 0);
+  double now = 1.0;
+  for (int i = 0; i < 12; ++i, now += 1.5) CHECK(checkProcessingOverrun(tr, "rtsp_1", "BirdNET_V2.4", 2.0 + i, 1.5, now, &rep));
+  BufferOverrunTracker& t = tr.Get("rtsp_1", "BirdNET_V2.4");
+  CHECK(t.Count() == 12 && t.MaxElapsed() == 13.0 && tr.Size() == 1);
+  CHECK(t.Record(3.0, 1.5, 1.0 + bufferOverrunReportCooldown + 1.0, &rep));               // window expired with >= 10 overruns: one report
+  CHECK(rep.overrunCount == 12 && rep.maxElapsed == 13.0 && rep.bufferLength == 1.5 && rep.source == "rtsp_1");
+  CHECK(t.Count() == 1);
+  BufferOverrunTracker few("a", "m");
+  for (int i = 0; i < 3; ++i) few.Record(2.0, 1.5, (double)i);
+  CHECK(!few.Record(2.0, 1.5, bufferOverrunReportCooldown + 10.0, &rep) && few.Count() == 1);   // below the minimum count: reset silently
+}
+
 static std::vector<uint8_t> slurp(const char* p) {
   std::ifstream f(p, std::ios::binary);
   if (!f) throw std::runtime_error(std::string("cannot open ") + p);
@@ -101,6 +118,13 @@ static int analyze(int argc, char** argv) {
   std::unique_ptr<inference::Classifier> backend;
   try { backend.reset(new inference::B200Classifier(model)); }
   catch (const ErrB200Unavailable& e) { std::printf("UNAVAILABLE %s\n", e.what()); return 3; }   // caller would fall back to TFLite
+  {
+    // the batched offline driver (config 2): every window of the file through ONE bnb_analyze_batch(int16) call
+    inference::B200Classifier& b200 = static_cast<inference::B200Classifier&>(*backend);
+    const auto det = AnalyzeFileBatched(b200, labels, reinterpret_cast<const int16_t*>(&wav[data_off]), data_len / 2, 0.0, sensitivity, threshold, 64);
+    double last = -1.0;
+    for (const Detection& d : det) if (d.Begin != last) { std::printf("batched\t%.1f\t%s\t%.4f\n", d.Begin, d.Species.c_str(), d.Confidence); last = d.Begin; }
+  }
   BirdNET bn(std::move(backend), labels, sensitivity);
   const size_t win = 144000 * 2;
   for (size_t off = 0, i = 0; off + win <= data_len; off += win, ++i) {
@@ -122,6 +146,7 @@ int main(int argc, char** argv) {
     if (argc > 4 && std::string(argv[1]) == "analyze") return analyze(argc, argv);
     test_analysis_buffer();
     test_postprocessing();
+    test_overrun_tracker();
     std::printf(g_fail ? "FAILED %d\n" : "OK\n", g_fail);
     return g_fail ? 1 : 0;
   } catch (const std::exception& e) { std::printf("EXCEPTION %s\n", e.what()); return 2; }

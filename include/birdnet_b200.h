@@ -122,6 +122,17 @@ BNB_API int bnb_predict_batch(bnb_classifier* h, const void* pcm, int format, in
 BNB_API int bnb_analyze_batch(bnb_classifier* h, const void* pcm, int format, int B, float sensitivity,
                       int k, int32_t* idx, float* conf, float* logits_or_null);
 
+/* Asynchronous form of bnb_analyze_batch for ONE caller that wants the host-to-device copy of batch i+1 to overlap the
+ * kernels of batch i (the handle stays single-caller: submit and wait come from the same serialized caller).
+ * `submit` returns once the work is enqueued and writes a ticket; idx / conf (/ logits) are valid after bnb_wait(ticket).
+ * At most TWO tickets may be outstanding (a third submit fails with BNB_ERR_INVALID_ARGUMENT).  Pageable `pcm` is copied
+ * during the call (callee-copies, process.go:280-291); PINNED host memory is read by the copy engine asynchronously and
+ * must stay unchanged until bnb_wait returns.  Batches of at most micro_batch chunks replay from a CUDA graph when
+ * bnb_options.use_graphs is set. */
+BNB_API int bnb_analyze_batch_submit(bnb_classifier* h, const void* pcm, int format, int B, float sensitivity, int k,
+                                     int32_t* idx, float* conf, float* logits_or_null, int32_t* ticket);
+BNB_API int bnb_wait(bnb_classifier* h, int32_t ticket);
+
 /* ---- device-buffer entry points (batched offline driver, bench, multi-GPU harness) ----------- */
 
 /* Same computation with inputs/outputs already resident in device memory of the handle's device;

@@ -252,3 +252,108 @@ def test_fused_and_unfused_chains_agree(lib_path, golden, audio, monkeypatch):
         assert err <= 1e-3, (mode, err)
         assert (outs[mode].argmax(1) == ref.argmax(1)).all()
     assert np.abs(outs["0"] - outs["2"]).max() < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: the benched geometry, the async / graph entry points, hostile inputs, several devices in one process
+def test_benched_geometry_matches_golden(lib_path, golden):
+    """bench.py's exact classifier (max_batch 256, micro-batch 64, 2 lanes): all 79 golden soundscape rows, wherever they sit in
+    the tiled batch of 256, against the float64 oracle (VERDICT r1 weak #1: the benched configuration had no oracle test)."""
+    from bench import soundscape_batch
+    c = bb.B200Classifier(max_batch=256, micro_batch=64, lanes=2)
+    x = soundscape_batch(256)
+    y = c.predict_batch(x)
+    ref = golden["soundscape_logits"].astype(np.float64)
+    for k in range(256):
+        r = ref[k % 79]
+        assert np.abs(_sig(y[k]) - _sig(r)).max() <= SIG_TOL, k
+        assert int(y[k].argmax()) == int(r.argmax()), k
+    print("benched geometry: max|dsigmoid| = %.3e" % np.abs(_sig(y[:79]) - _sig(ref)).max())
+    idx, conf = c.analyze_batch(x, 1.0, 10)
+    assert (idx[:, 0] == ref.argmax(1)[np.arange(256) % 79]).all()
+    c.close()
+
+
+def test_config3_shape_max_batch_1024(lib_path):
+    """BASELINE config 3 shape: batch 1024 of synthetic pink noise + chirp through one call; a fixed 512-chunk subset is compared
+    with the committed oracle vectors (tests/golden/make_synth_golden.py), the rest through batch-position invariance."""
+    from bench import synth_chunks
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "synth512_golden.npz"))
+    x = synth_chunks(512, seed0=1234)
+    c = bb.B200Classifier(max_batch=1024, micro_batch=64, lanes=2)
+    big = np.concatenate([x, x[::-1]])
+    idx, conf, logits = c.analyze_batch(big, 1.0, 10, want_logits=True)
+    assert np.array_equal(logits[:512], logits[1023:511:-1])                 # same chunk, another slot of the batch: same bits
+    sig = bo.sigmoid_sensitivity(logits[:512], 1.0).astype(np.float64)
+    top_ref, conf_ref = g["top10_idx"], g["top10_conf"].astype(np.float64)
+    got_at_ref = np.take_along_axis(sig, top_ref.astype(np.int64), axis=1)
+    assert np.abs(got_at_ref - conf_ref).max() <= SIG_TOL                     # the oracle's ten best per chunk
+    assert np.abs(sig.max(1) - conf_ref[:, 0]).max() <= SIG_TOL
+    clear = (conf_ref[:, 0] - conf_ref[:, 1]) > 2e-3
+    assert (idx[:512, 0] == top_ref[:, 0])[clear].all()
+    c.close()
+
+
+def test_async_submit_wait_and_graphs_give_the_same_bits(lib_path, audio):
+    chunks = bo.slice_chunks(audio["soundscape"], 72000)
+    c = bb.B200Classifier(max_batch=79, micro_batch=16, use_graphs=1)
+    idx0, conf0, lg0 = c.analyze_batch(chunks, 1.5, 10, want_logits=True)
+    # two batches in flight, different sizes, results must equal the synchronous call bit for bit
+    t1 = c.analyze_batch_submit(chunks[:40], 1.5, 10, want_logits=True)
+    t2 = c.analyze_batch_submit(chunks[40:], 1.5, 10, want_logits=True)
+    with pytest.raises(bb.B200Error):
+        c.analyze_batch_submit(chunks[:1], 1.5, 10)                          # a third outstanding ticket is refused
+    i1, c1, l1 = t1.wait()
+    i2, c2, l2 = t2.wait()
+    assert np.array_equal(np.concatenate([l1, l2]), lg0) and np.array_equal(np.concatenate([i1, i2]), idx0)
+    assert np.array_equal(np.concatenate([c1, c2]), conf0)
+    with pytest.raises(bb.B200Error):
+        t1.wait()                                                             # a ticket completes once
+    # small batches replay from a CUDA graph (B <= micro-batch): first call captures, later calls replay
+    for n in (1, 3, 16, 1, 3):
+        i3, c3, l3 = c.analyze_batch(chunks[:n], 1.5, 10, want_logits=True)
+        assert np.array_equal(l3, lg0[:n]) and np.array_equal(i3, idx0[:n])
+    one = c.predict(chunks[5])
+    assert np.array_equal(one, lg0[5])
+    n0 = c.kernel_launches()
+    c.predict(chunks[5])
+    assert c.kernel_launches() > n0                                           # graph replays still count their kernels
+    c.close()
+
+
+def test_nan_and_inf_samples_do_not_poison_the_process(lib_path, audio):
+    """A NaN / Inf PCM sample must not fault the top-k kernel (ADVICE r1: an all-NaN chunk indexed shared memory out of bounds)
+    nor touch the other chunks of the batch."""
+    chunks = bo.slice_chunks(audio["soundscape"], 144000)[:4].copy()
+    good = chunks.copy()
+    chunks[1, 1000] = np.nan
+    chunks[2, 77] = np.inf
+    c = bb.B200Classifier(max_batch=4)
+    idx, conf, logits = c.analyze_batch(chunks, 1.0, 10, want_logits=True)
+    ref_idx, ref_conf, ref_logits = c.analyze_batch(good, 1.0, 10, want_logits=True)
+    assert np.array_equal(logits[[0, 3]], ref_logits[[0, 3]]) and np.array_equal(idx[[0, 3]], ref_idx[[0, 3]])
+    # what a NaN sample does to ITS chunk is implementation-defined (the stem's ReLU is max(x, 0), which drops NaN on most
+    # hardware, XNNPACK included): all that is required is a well-formed answer — indices in range, confidences NaN or in [0, 1]
+    for r in (1, 2):
+        assert ((idx[r] >= 0) & (idx[r] < 6522)).all()
+        assert (np.isnan(conf[r]) | ((conf[r] >= 0) & (conf[r] <= 1))).all()
+    assert c.predict(good[0]).shape == (6522,)                                # the handle is still healthy
+    c.close()
+
+
+def test_two_devices_in_one_process(lib_path, audio):
+    """A Go process drives every GPU of the box from one address space (stream_id mod R, SURVEY §8e): handles on different
+    devices must not share per-device kernel attributes or scratch state (VERDICT r1 weak #10)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    chunks = bo.slice_chunks(audio["soundscape"], 144000)[:6]
+    a = bb.B200Classifier(device=0, max_batch=8)
+    b = bb.B200Classifier(device=1, max_batch=8)
+    ya, yb = a.predict_batch(chunks), b.predict_batch(chunks)
+    assert np.array_equal(ya, yb)
+    import threading
+    out = {}
+    ths = [threading.Thread(target=lambda k, c: out.__setitem__(k, c.predict_batch(chunks)), args=(k, c)) for k, c in (("a", a), ("b", b))]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    assert np.array_equal(out["a"], ya) and np.array_equal(out["b"], ya)
+    a.close(); b.close()

@@ -6,6 +6,7 @@ import subprocess
 
 import pytest
 
+import birdnet_b200 as bb
 import birdnet_oracle as bo
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -46,3 +47,24 @@ def test_dropin_predict_reproduces_published_table(host_test):
     for (t, name, c), (gt, gname, gc) in zip(got, bo.GOLDEN_TABLE):
         assert t == gt and name == gname and abs(c - gc) <= 1e-3
     assert "size-mismatch-error ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_batched_offline_file_analysis_reproduces_the_published_table(lib_path):
+    """BASELINE config 2 driver (doc/wiki/file-analysis.md:1-13): soundscape.wav, no overlap, threshold 0.1, sensitivity 1.5 through
+    ONE batched int16 call must list exactly the reference's 25 detections (species and confidence to the table's 4 decimals)."""
+    import bench
+    pcm = bench.read_wav_int16(os.path.join(bo.ASSETS, "soundscape.wav"))
+    bn = bb.BirdNET(sensitivity=bo.GOLDEN_SENSITIVITY, max_batch=64)
+    rows = bn.analyze_file(pcm, overlap_s=0.0, threshold=0.1)
+    top = {}
+    for b0, e0, sp, cf in rows:
+        top.setdefault(b0, (sp, cf))                       # first row of a window = its best result
+    assert len(top) == len(bo.GOLDEN_TABLE)
+    for t0, name, c in bo.GOLDEN_TABLE:
+        sp, cf = top[float(t0)]
+        assert sp.split("_", 1)[1] == name and abs(cf - c) <= 1e-3, (t0, sp, cf)
+    # overlap 1.5 s: 79 windows, every window's rows are sorted and above the threshold
+    rows = bn.analyze_file(pcm, overlap_s=1.5, threshold=0.1)
+    assert all(r[3] >= 0.1 for r in rows) and len({r[0] for r in rows}) <= 79
+    bn.close()

@@ -80,3 +80,39 @@ def test_eight_streams_through_the_gpu(lib_path):
     assert [labels[i] for i in idx[0]] == [s for s, _ in last.results]
     assert np.allclose([c for _, c in last.results], conf[0], atol=1e-6)
     clf.close()
+
+
+def test_buffer_overrun_tracking_tumbling_window():
+    """process.go:351-370 + :177-215: an inference slower than the buffer interval counts as an overrun per source; a report is
+    emitted once per expired window when at least 10 overruns accumulated."""
+    import numpy as np
+    from birdnet_b200 import realtime as rt
+
+    slow = {"dt": 0.0}
+
+    def analyze(pcm, sens, k):
+        return np.zeros((len(pcm), k), np.int32), np.zeros((len(pcm), k), np.float32)
+
+    co = rt.RealtimeCoalescer(analyze, ["x"] * 6522, ["a", "b"])
+    # fast inference: no overrun
+    for s in ("a", "b"):
+        co.write(s, b"\0" * 144000)
+    co.tick(now=0.0)
+    assert co.overrun_total == 0 and not co.overruns
+    # force the measured inference time above the interval by patching the clock the coalescer uses
+    real = rt.time.perf_counter
+    ticks = iter([0.0, 10.0] * 1000)
+    rt.time.perf_counter = lambda: next(ticks)
+    try:
+        t = 1.0
+        for _ in range(12):
+            co.write("a", b"\0" * 144000)
+            co.tick(now=t); t += 1.5
+        tr = co.overruns["a:BirdNET_V2.4"]
+        assert tr.overrun_count == 12 and not tr.reports and abs(tr.max_elapsed - 10.0) < 1e-9 and abs(tr.buffer_length - 1.5) < 1e-9
+        co.write("a", b"\0" * 144000)
+        co.tick(now=1.0 + rt.BUFFER_OVERRUN_REPORT_COOLDOWN_S + 1)         # window expired with >= 10 overruns: one report, counters reset
+        assert len(tr.reports) == 1 and tr.reports[0]["overrun_count"] == 12 and tr.overrun_count == 1
+        assert "b:BirdNET_V2.4" not in co.overruns
+    finally:
+        rt.time.perf_counter = real
