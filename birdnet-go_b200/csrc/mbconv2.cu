@@ -64,7 +64,7 @@ struct Mb2Args {
 // the epilogue group, 5 accumulator released (all rows read), 6 unit done (stores issued), 7 kernel end.  Index = tile
 // iteration (events 1, 2) or unit sequence number (3..6).  CTA 0 and the last CTA are recorded.
 #define MB2_TRACE(ev, i) do { if (a.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (i) < 64) \
-    a.trace[((blockIdx.x == 0 ? 0 : 1) * 8 + (ev)) * 64 + (i)] = clock64(); } while (0)
+    a.trace[((blockIdx.x == 0 ? 0 : 1) * 10 + (ev)) * 64 + (i)] = clock64(); } while (0)
 
 template <int PW>
 __device__ __forceinline__ void load_row(float (&dst)[PW], uint32_t taddr, bool row_in, bool left_oob, bool right_oob, float be, int dbg = 0) {
@@ -229,6 +229,7 @@ mbconv2_kernel(const Mb2Args a) {
           mbar_wait(t_empty(buf), ((seq / kGroups) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)buf * kMb2BufCols;
+          if (leader) MB2_TRACE(8, seq);
           for (int s = 0; s < a.k_stages; ++s, ++q) {
             int slot; uint32_t ph;
             if (a.a_resident) { slot = (a.rot_mode == 2 ? rot : u) * a.k_stages + s; ph = 0; }
@@ -253,7 +254,7 @@ mbconv2_kernel(const Mb2Args a) {
             __syncwarp();
             if (leader && !a.a_resident) umma_commit(a_empty(slot));
           }
-          if (leader) { umma_commit(t_full(buf)); MB2_TRACE(3, seq); }
+          if (leader) { MB2_TRACE(9, seq); umma_commit(t_full(buf)); MB2_TRACE(3, seq); }
         }
         if (leader) umma_commit(b_empty(bs));
         __syncwarp();
@@ -503,27 +504,27 @@ void launch_mbconv2(const Mb2Plan& P, const Mb2Launch& L, cudaStream_t s, Launch
   static const long long trace_idx = getenv("BNB_MB2_TRACE_IDX") ? atoll(getenv("BNB_MB2_TRACE_IDX")) : 0;
   const long long my_idx = launch_idx.fetch_add(1);
   long long* trace = nullptr;
-  if (trace_path && my_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 2 * 8 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 2 * 8 * 64 * sizeof(long long), s)); a.trace = trace; }
+  if (trace_path && my_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 2 * 10 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 2 * 10 * 64 * sizeof(long long), s)); a.trace = trace; }
   if (P.S == 1 && P.TW == 8) mbconv2_kernel<1, 8><<<grid, kThreads, P.smem_bytes, s>>>(a);
   else if (P.S == 2 && P.TW == 4) mbconv2_kernel<2, 4><<<grid, kThreads, P.smem_bytes, s>>>(a);
   else throw std::runtime_error("mbconv2: unsupported tile shape");
   if (trace) {
-    std::vector<long long> h(2 * 8 * 64);
+    std::vector<long long> h(2 * 10 * 64);
     BNB_CUDA(cudaStreamSynchronize(s));
     BNB_CUDA(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     FILE* f = fopen(trace_path, "w");
     if (f) {
       fprintf(f, "# mbconv2 B=%d H=%d W=%d Cin=%d C=%d S=%d tile=%dx%d patch=%dx%d n_mma=%d units=%d k_stages=%d resident=%d a_slots=%d b_slots=%d grid=%d tiles=%lld\n",
               L.B, L.H, L.W, P.Cin, P.C, P.S, P.TH, P.TW, P.PH, P.PW, P.n_mma, P.n_units, P.k_stages, P.a_resident, P.a_slots, P.b_slots, grid, tiles);
-      fprintf(f, "# cta idx start patch_issue patch_landed mma_committed acc_seen acc_released unit_done end   (cycles since the CTA's start)\n");
+      fprintf(f, "# cta idx start patch_issue patch_landed mma_committed acc_seen acc_released unit_done end mma_first_issue mma_last_issue   (cycles since the CTA's start)\n");
       for (int c = 0; c < 2; ++c) {
-        const long long t0 = h[(c * 8 + 0) * 64];
+        const long long t0 = h[(c * 10 + 0) * 64];
         for (int i = 0; i < 64; ++i) {
           bool any = false;
-          for (int e = 0; e < 8; ++e) any = any || h[(c * 8 + e) * 64 + i] != 0;
+          for (int e = 0; e < 10; ++e) any = any || h[(c * 10 + e) * 64 + i] != 0;
           if (!any) continue;
           fprintf(f, "%d %d", c, i);
-          for (int e = 0; e < 8; ++e) { const long long v = h[(c * 8 + e) * 64 + i]; fprintf(f, " %lld", v ? v - t0 : -1); }
+          for (int e = 0; e < 10; ++e) { const long long v = h[(c * 10 + e) * 64 + i]; fprintf(f, " %lld", v ? v - t0 : -1); }
           fprintf(f, "\n");
         }
       }
