@@ -39,13 +39,15 @@ stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restr
     s_wm[c * kStemCo + co] = __ldg(p.w_mix + i);
   }
   if (tid < kStemCo) { s_b[tid] = __ldg(p.b_stem + tid); s_bm[tid] = __ldg(p.b_mix + tid); }
+  pdl_trigger();
+  pdl_wait();                // weights above are constants; everything below reads the frontend's output / writes activations
   // stage input rows; padded column index pc = col + pad_l  (pc in [0, kStemCols))
   const float* inb = in + (size_t)b * p.in_h * p.in_w * 2;
   for (int i = tid; i < kStemKh * kStemCols; i += kStemThreads) {
     const int r = i / kStemCols, pc = i - r * kStemCols;
     const int row = 2 * h - p.pad_t + r, col = pc - p.pad_l;
     float2 v = make_float2(0.f, 0.f);
-    if (row >= 0 && row < p.in_h && col >= 0 && col < p.in_w) v = __ldg(reinterpret_cast<const float2*>(inb + ((size_t)row * p.in_w + col) * 2));
+    if (row >= 0 && row < p.in_h && col >= 0 && col < p.in_w) v = __ldcg(reinterpret_cast<const float2*>(inb + ((size_t)row * p.in_w + col) * 2));   // previous kernel's output: coherent load (PDL)
     *reinterpret_cast<float2*>(&s_in[r][pc & 3][pc >> 2][0]) = v;
   }
   __syncthreads();
@@ -335,6 +337,8 @@ se_gate_kernel(const SeArgs a) {
   const int b0 = blockIdx.x * kSeChunks, tid = threadIdx.x;
   const int nb = min(kSeChunks, a.B - b0);
   const float inv = 1.0f / (float)a.HW;
+  pdl_trigger();
+  pdl_wait();
   for (int i = tid; i < kSeChunks * a.C; i += kSeThreads) {
     const int g = i / a.C, c = i - g * a.C;
     // four independent partial accumulators: the loads of a round are in flight together (the serial version paid one L2
@@ -344,10 +348,10 @@ se_gate_kernel(const SeArgs a) {
       const float* pp = a.partial + (size_t)(b0 + g) * a.parts * a.C + c;
       int p = 0;
       for (; p + 4 <= a.parts; p += 4) {
-        s0 += __ldg(pp + (size_t)p * a.C); s1 += __ldg(pp + (size_t)(p + 1) * a.C);
-        s2 += __ldg(pp + (size_t)(p + 2) * a.C); s3 += __ldg(pp + (size_t)(p + 3) * a.C);
+        s0 += __ldcg(pp + (size_t)p * a.C); s1 += __ldcg(pp + (size_t)(p + 1) * a.C);       // coherent loads (PDL)
+        s2 += __ldcg(pp + (size_t)(p + 2) * a.C); s3 += __ldcg(pp + (size_t)(p + 3) * a.C);
       }
-      for (; p < a.parts; ++p) s0 += __ldg(pp + (size_t)p * a.C);
+      for (; p < a.parts; ++p) s0 += __ldcg(pp + (size_t)p * a.C);
     }
     s_mean[g][c] = ((s0 + s1) + (s2 + s3)) * inv;
   }
@@ -373,18 +377,24 @@ se_gate_kernel(const SeArgs a) {
     }
   }
   __syncthreads();
-  for (int c = tid; c < a.C; c += kSeThreads) {
+  // FC2: six weight loads in flight per thread.  (blockIdx.y could own a slice of the output channels; measured slower with
+  // 2-4 slices — the kernel is bound by the latency of its three dependent phases, not by FC2's weight traffic: gridDim.y = 1)
+  const int per = (((a.C + (int)gridDim.y - 1) / (int)gridDim.y) + 31) & ~31;
+  const int c_lo = (int)blockIdx.y * per, c_hi = min(a.C, c_lo + per);
+  for (int c = c_lo + tid; c < c_hi; c += kSeThreads) {
     float acc[kSeChunks];
     const float bz = __ldg(a.b2 + c);
 #pragma unroll
     for (int g = 0; g < kSeChunks; ++g) acc[g] = bz;
     int j = 0;
-    for (; j + 4 <= a.Cse; j += 4) {                               // w2t: [Cse][C] (transposed at load) -> coalesced; 4 loads in flight
-      const float w0 = __ldg(a.w2t + (size_t)j * a.C + c), w1 = __ldg(a.w2t + (size_t)(j + 1) * a.C + c);
-      const float w2 = __ldg(a.w2t + (size_t)(j + 2) * a.C + c), w3 = __ldg(a.w2t + (size_t)(j + 3) * a.C + c);
+    for (; j + 6 <= a.Cse; j += 6) {                               // w2t: [Cse][C] (transposed at load) -> coalesced
+      float wv[6];
 #pragma unroll
-      for (int g = 0; g < kSeChunks; ++g)
-        acc[g] = fmaf(s_hidden[g][j + 3], w3, fmaf(s_hidden[g][j + 2], w2, fmaf(s_hidden[g][j + 1], w1, fmaf(s_hidden[g][j], w0, acc[g]))));
+      for (int t = 0; t < 6; ++t) wv[t] = __ldg(a.w2t + (size_t)(j + t) * a.C + c);
+#pragma unroll
+      for (int t = 0; t < 6; ++t)
+#pragma unroll
+        for (int g = 0; g < kSeChunks; ++g) acc[g] = fmaf(s_hidden[g][j + t], wv[t], acc[g]);
     }
     for (; j < a.Cse; ++j) {
       const float wv = __ldg(a.w2t + (size_t)j * a.C + c);
@@ -433,13 +443,15 @@ post_prep2_kernel(const __half* __restrict__ ih, const __half* __restrict__ il, 
                   uint8_t* __restrict__ o_img, const RowTiles ot, int B, int kh, int kw, int in_w, int out_w, int cin) {
   const int c8n = cin / 8, K8 = kh * kw * c8n;
   const long long total = (long long)B * out_w * K8;
+  pdl_trigger();
+  pdl_wait();
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int k8 = (int)(idx % K8);
     const long long row = idx / K8;
     const int wo = (int)(row % out_w), b = (int)(row / out_w);
     const int c8 = k8 % c8n, t = k8 / c8n, x = t % kw, y = t / kw;
     const size_t src = ((((size_t)b * kh + y) * in_w + wo + x) * cin) + 8 * c8;
-    const uint4 h = __ldg(reinterpret_cast<const uint4*>(ih + src)), l = __ldg(reinterpret_cast<const uint4*>(il + src));
+    const uint4 h = __ldcg(reinterpret_cast<const uint4*>(ih + src)), l = __ldcg(reinterpret_cast<const uint4*>(il + src));   // coherent (PDL)
     const float4 m0 = __ldg(reinterpret_cast<const float4*>(mul + 8 * c8)), m1 = __ldg(reinterpret_cast<const float4*>(mul + 8 * c8 + 4));
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(add + 8 * c8)), a1 = __ldg(reinterpret_cast<const float4*>(add + 8 * c8 + 4));
     const float2 v0 = tc::join2(h.x, l.x), v1 = tc::join2(h.y, l.y), v2 = tc::join2(h.z, l.z), v3 = tc::join2(h.w, l.w);
@@ -458,11 +470,13 @@ post_prep2_kernel(const __half* __restrict__ ih, const __half* __restrict__ il, 
 __global__ void __launch_bounds__(256)
 row_mean2_kernel(const float* __restrict__ in, float* __restrict__ out, uint8_t* __restrict__ o_img, const RowTiles ot, int B, int rows, int C) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // one thread = two adjacent channels
+  pdl_trigger();
+  pdl_wait();
   if (idx >= B * (C / 2)) return;
   const int b = idx / (C / 2), c = 2 * (idx - b * (C / 2));
   float s0 = 0.f, s1 = 0.f;
   for (int r = 0; r < rows; ++r) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(in + ((size_t)b * rows + r) * C + c));
+    const float2 v = __ldcg(reinterpret_cast<const float2*>(in + ((size_t)b * rows + r) * C + c));   // coherent (PDL)
     s0 += v.x; s1 += v.y;
   }
   s0 /= (float)rows; s1 /= (float)rows;
@@ -482,22 +496,27 @@ void launch_post_prep2(const __half* ih, const __half* il, const float* mul, con
   const long long total = (long long)B * out_w * kh * kw * (cin / 8);
   long long blocks = ceil_div_ll(total, 256);
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-  post_prep2_kernel<<<(unsigned)blocks, 256, 0, s>>>(ih, il, mul, add, o_img, RowTiles::make(kh * kw * cin), B, kh, kw, in_w, out_w, cin);
-  BNB_LAUNCH_CHECK(lc);
+  launch_k(post_prep2_kernel, dim3((unsigned)blocks), dim3(256), 0, s, ih, il, mul, add, o_img, RowTiles::make(kh * kw * cin), B, kh, kw, in_w, out_w, cin);
+  lc.n++;
 }
 
 void launch_row_mean2(const float* in, float* out, uint8_t* o_img, int B, int rows, int C, cudaStream_t s, LaunchCounter& lc) {
   if (C % 2) throw std::runtime_error("row_mean2: channel count must be even");
-  row_mean2_kernel<<<ceil_div(B * (C / 2), 256), 256, 0, s>>>(in, out, o_img, RowTiles::make(C), B, rows, C);
-  BNB_LAUNCH_CHECK(lc);
+  launch_k(row_mean2_kernel, dim3(ceil_div(B * (C / 2), 256)), dim3(256), 0, s, in, out, o_img, RowTiles::make(C), B, rows, C);
+  lc.n++;
 }
 
 void launch_stem_mix(const StemMixDev& p, const float* in, float* stem_out_or_null, float* out, int B,
                      cudaStream_t s, LaunchCounter& lc, uint8_t* out_img, const PatchTiles* out_patch) {
   dim3 grid(p.out_h, B);
   if (out_img && (!out_patch || !out_patch->dst_tbl || out_patch->C != kStemCo || out_patch->H != p.out_h || out_patch->W != p.out_w / 2)) throw std::runtime_error("stem_mix: patch layout does not match the pooled stem output");
-  stem_mix_kernel<<<grid, kStemThreads, 0, s>>>(p, in, stem_out_or_null, out, out_img, out_patch ? *out_patch : PatchTiles());
-  BNB_LAUNCH_CHECK(lc);
+  launch_k(stem_mix_kernel, grid, dim3(kStemThreads), 0, s, p, in, stem_out_or_null, out, out_img, out_patch ? *out_patch : PatchTiles());
+  lc.n++;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("BNB_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 void launch_pw_conv(const PwArgs& a, cudaStream_t s, LaunchCounter& lc) {
@@ -525,8 +544,8 @@ void launch_dw_conv(const DwArgs& a0, cudaStream_t s, LaunchCounter& lc) {
 
 void launch_se_gate(const SeArgs& a, cudaStream_t s, LaunchCounter& lc) {
   if (a.C > kSeMaxC || a.Cse > kSeMaxS) throw std::runtime_error("se_gate: channel count exceeds kernel limits");
-  se_gate_kernel<<<(a.B + kSeChunks - 1) / kSeChunks, kSeThreads, 0, s>>>(a);
-  BNB_LAUNCH_CHECK(lc);
+  launch_k(se_gate_kernel, dim3((a.B + kSeChunks - 1) / kSeChunks, 1), dim3(kSeThreads), 0, s, a);
+  lc.n++;
 }
 
 void launch_post_prep(const float* in, const float* mul, const float* add, float* out, int B, int kh, int kw, int in_w, int out_w,

@@ -257,12 +257,25 @@ frontend_kernel(const FrontendDev P, const void* __restrict__ pcm, const float* 
   const int b = blockIdx.y, t0 = blockIdx.x * kFeFramesPerCta;
   const int nfr = min(kFeFramesPerCta, P.n_frames - t0);
 
+  // tables (constants: loaded before the dependency wait so they overlap the previous kernel's tail)
+  for (int i = tid; i < 2048; i += blockDim.x) S.win1[i] = __ldg(P.win[0] + i);
+  for (int i = tid; i < 1024; i += blockDim.x) S.win2[i] = __ldg(P.win[1] + i);
+  for (int i = tid; i < 1024; i += blockDim.x) S.tw1[i] = __ldg(P.tw[0] + i);
+  for (int i = tid; i < 512; i += blockDim.x) S.tw2[i] = __ldg(P.tw[1] + i);
+  for (int i = tid; i < kPost1; i += blockDim.x) S.post1[i] = __ldg(P.post[0] + i);
+  for (int i = tid; i < kPost2; i += blockDim.x) S.post2[i] = __ldg(P.post[1] + i);
+  for (int i = tid; i < kPost1; i += blockDim.x) S.dc1[i] = __ldg(P.win_dft[0] + i);
+  for (int i = tid; i < kPost2; i += blockDim.x) S.dc2[i] = __ldg(P.win_dft[1] + i);
+  pdl_trigger();
+  pdl_wait();
   // chunk min / max from the partials
-  float mn = partial[(b * kMinMaxParts) * 2], mx = partial[(b * kMinMaxParts) * 2 + 1];
+  // (coherent loads: the partials were written by the previous kernel, which may still have been running when this CTA
+  // started — PDL, common.cuh)
+  float mn = __ldcg(partial + (b * kMinMaxParts) * 2), mx = __ldcg(partial + (b * kMinMaxParts) * 2 + 1);
 #pragma unroll
   for (int i = 1; i < kMinMaxParts; ++i) {
-    mn = fminf(mn, partial[(b * kMinMaxParts + i) * 2]);
-    mx = fmaxf(mx, partial[(b * kMinMaxParts + i) * 2 + 1]);
+    mn = fminf(mn, __ldcg(partial + (b * kMinMaxParts + i) * 2));
+    mx = fmaxf(mx, __ldcg(partial + (b * kMinMaxParts + i) * 2 + 1));
   }
   const float den = (mx - mn) + P.eps;                  // max(x - min) + eps, as the graph computes it
 
@@ -289,15 +302,6 @@ frontend_kernel(const FrontendDev P, const void* __restrict__ pcm, const float* 
     }
   }
   for (int i = span_len + tid; i < kSpanMax; i += blockDim.x) S.span[i] = 0.f;
-  // tables
-  for (int i = tid; i < 2048; i += blockDim.x) S.win1[i] = __ldg(P.win[0] + i);
-  for (int i = tid; i < 1024; i += blockDim.x) S.win2[i] = __ldg(P.win[1] + i);
-  for (int i = tid; i < 1024; i += blockDim.x) S.tw1[i] = __ldg(P.tw[0] + i);
-  for (int i = tid; i < 512; i += blockDim.x) S.tw2[i] = __ldg(P.tw[1] + i);
-  for (int i = tid; i < kPost1; i += blockDim.x) S.post1[i] = __ldg(P.post[0] + i);
-  for (int i = tid; i < kPost2; i += blockDim.x) S.post2[i] = __ldg(P.post[1] + i);
-  for (int i = tid; i < kPost1; i += blockDim.x) S.dc1[i] = __ldg(P.win_dft[0] + i);
-  for (int i = tid; i < kPost2; i += blockDim.x) S.dc2[i] = __ldg(P.win_dft[1] + i);
   __syncthreads();
 
   // spectrogram 0: frames warp and warp+16; spectrogram 1: frames (2 warp, 2 warp + 1)
@@ -328,6 +332,8 @@ minmax_partial_kernel(const void* __restrict__ pcm, int n_samples, float* __rest
   const int b = blockIdx.y, part = blockIdx.x;
   const int per = n_samples / kMinMaxParts;            // 18000, multiple of 8
   float mn = INFINITY, mx = -INFINITY;
+  pdl_trigger();
+  pdl_wait();
   if (FMT == 0) {
     const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(pcm) + (size_t)b * n_samples + (size_t)part * per);
     for (int i = threadIdx.x; i < per / 4; i += blockDim.x) {
@@ -373,8 +379,8 @@ void frontend_set_attributes() {
 
 void launch_minmax(const void* pcm, int fmt, int B, int n_samples, float* partial, cudaStream_t s, LaunchCounter& lc) {
   dim3 grid(kMinMaxParts, B);
-  if (fmt == 0) minmax_partial_kernel<0><<<grid, 256, 0, s>>>(pcm, n_samples, partial);
-  else minmax_partial_kernel<1><<<grid, 256, 0, s>>>(pcm, n_samples, partial);
+  if (fmt == 0) launch_k(minmax_partial_kernel<0>, grid, dim3(256), 0, s, pcm, n_samples, partial);
+  else launch_k(minmax_partial_kernel<1>, grid, dim3(256), 0, s, pcm, n_samples, partial);
   BNB_LAUNCH_CHECK(lc);
 }
 
@@ -382,8 +388,8 @@ void launch_frontend(const FrontendDev& fe, const void* pcm, int fmt, int B, con
                      cudaStream_t s, LaunchCounter& lc) {
   const size_t smem = frontend_smem_bytes();
   dim3 grid(ceil_div(fe.n_frames, kFeFramesPerCta), B);
-  if (fmt == 0) frontend_kernel<0><<<grid, kWarps * 32, smem, s>>>(fe, pcm, partial, out);
-  else frontend_kernel<1><<<grid, kWarps * 32, smem, s>>>(fe, pcm, partial, out);
+  if (fmt == 0) launch_k(frontend_kernel<0>, grid, dim3(kWarps * 32), smem, s, fe, pcm, partial, out);
+  else launch_k(frontend_kernel<1>, grid, dim3(kWarps * 32), smem, s, fe, pcm, partial, out);
   BNB_LAUNCH_CHECK(lc);
 }
 

@@ -138,10 +138,7 @@ mbconv2_kernel(const Mb2Args a) {
   const uint32_t b_ring = a_ring + a.a_region_bytes;
   // weight slab address: resident slabs are packed exactly like the image (unit-major, stages inside); the streaming ring has
   // one max-sized slot per slab in flight
-  auto a_addr = [&](int slot) {
-    return a.a_resident ? a_ring + (uint32_t)(slot / a.k_stages) * a.img_unit_bytes + a.st_aoff[slot % a.k_stages]
-                        : a_ring + (uint32_t)slot * a.a_slot_bytes;
-  };
+  auto a_res_addr = [&](int iu, int s) { return a_ring + (uint32_t)iu * a.img_unit_bytes + a.st_aoff[s]; };
   const uint32_t bars = b_ring + (uint32_t)a.b_slots * a.b_slot_bytes;
   auto a_full = [&](int s) { return bars + 8u * s; };
   auto a_empty = [&](int s) { return bars + 8u * (a.a_slots + s); };
@@ -171,93 +168,104 @@ mbconv2_kernel(const Mb2Args a) {
   const int tiles_per_chunk = a.tiles_h * a.tiles_w;
   const int total_tiles = a.B * tiles_per_chunk;
   if (threadIdx.x == 0) MB2_TRACE(0, 0);
+  // PDL (common.cuh): everything above is independent of the previous kernel.  The weight loader never touches activations, so
+  // it alone skips the wait: resident weights stream in while the previous kernel's last tiles drain.
+  pdl_trigger();
+  if (warp != kLoadAWarp) pdl_wait();
 
   if (warp == kLoadBWarp) {
     // ============================== patch loader: the tile's whole shared-memory slot is ONE contiguous image in memory ===
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int bs = it % a.b_slots; const uint32_t ph = (it / a.b_slots) & 1;
-        mbar_wait_relaxed(b_empty(bs), ph ^ 1);
+    // (whole warp walks the loop; one elected lane issues: see elect_one())
+    uint32_t it = 0, ph = 0; int bs = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      mbar_wait_relaxed(b_empty(bs), ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(b_full(bs), a.b_slot_bytes);
         bulk_g2s(b_ring + (uint32_t)bs * a.b_slot_bytes, a.x_img + (size_t)tile * a.b_slot_bytes, a.b_slot_bytes, b_full(bs));
         MB2_TRACE(1, it);
       }
+      __syncwarp();
+      if (++bs == a.b_slots) { bs = 0; ph ^= 1; }
     }
   } else if (warp == kLoadAWarp) {
     // ============================== weight loader: pre-swizzled (unit, stage) slabs, hi | lo ========================
-    if (lane == 0) {
-      if (a.a_resident) {
-        for (int iu = 0; iu < a.n_img_units; ++iu)
-          for (int s = 0; s < a.k_stages; ++s) {
-            const int slot = iu * a.k_stages + s;
+    if (a.a_resident) {
+      for (int iu = 0; iu < a.n_img_units; ++iu)
+        for (int s = 0; s < a.k_stages; ++s) {
+          const int slot = iu * a.k_stages + s;
+          if (elect_one()) {
             mbar_arrive_expect_tx(a_full(slot), 2u * a.st_aplane[s]);
-            bulk_g2s(a_addr(slot), a.Wimg + (size_t)iu * a.img_unit_bytes + a.st_aoff[s], 2u * a.st_aplane[s], a_full(slot));
+            bulk_g2s(a_res_addr(iu, s), a.Wimg + (size_t)iu * a.img_unit_bytes + a.st_aoff[s], 2u * a.st_aplane[s], a_full(slot));
           }
-      } else {
-        uint32_t q = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
-          for (int u = 0; u < a.n_units; ++u)
-            for (int s = 0; s < a.k_stages; ++s, ++q) {
-              const int slot = q % a.a_slots; const uint32_t ph = (q / a.a_slots) & 1;
-              mbar_wait_relaxed(a_empty(slot), ph ^ 1);
+          __syncwarp();
+        }
+    } else {
+      int slot = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+        for (int u = 0; u < a.n_units; ++u)
+          for (int s = 0; s < a.k_stages; ++s) {
+            mbar_wait_relaxed(a_empty(slot), ph ^ 1);
+            if (elect_one()) {
               mbar_arrive_expect_tx(a_full(slot), 2u * a.st_aplane[s]);
-              bulk_g2s(a_addr(slot), a.Wimg + (size_t)u * a.img_unit_bytes + a.st_aoff[s], 2u * a.st_aplane[s], a_full(slot));
+              bulk_g2s(a_ring + (uint32_t)slot * a.a_slot_bytes, a.Wimg + (size_t)u * a.img_unit_bytes + a.st_aoff[s], 2u * a.st_aplane[s], a_full(slot));
             }
-      }
+            __syncwarp();
+            if (++slot == a.a_slots) { slot = 0; ph ^= 1; }
+          }
     }
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ======================================================================
-    // The WHOLE warp runs this loop with warp-uniform values (barrier waits, descriptor arithmetic), and only the tcgen05
-    // instructions themselves are predicated on one lane: ptxas then keeps descriptors / addresses in uniform registers.  With
-    // the loop inside `if (lane == 0)` every operand was computed in vector registers and moved with R2UR, and the single
-    // issuing thread spent ~230 cycles of dependent scalar work per MMA (profiles/r02 timeline: 15 MMAs = 3.7 k cycles per unit,
-    // the kernel's critical path).  Descriptors are built once per (unit, stage); a k-step only adds a constant.
+    // The WHOLE warp runs this loop with warp-uniform values (barrier waits, descriptor arithmetic: counters instead of runtime
+    // divisions so that ptxas keeps them on the uniform datapath), and the tcgen05 instructions are issued by one ELECTED lane:
+    // a stage's MMAs are then consecutive UTCHMMA instructions.  Guarded by `lane == 0` each of them sat in a waterfall loop and
+    // the issuer needed ~200 cycles per MMA (profiles/r02 timeline: 15 MMAs = 3 k cycles per unit, the kernel's critical path).
     {
-      const bool leader = lane == 0;
       const uint32_t idesc = make_idesc_mn(128u, (uint32_t)a.n_mma);
-      uint32_t it = 0, q = 0;
+      uint32_t it = 0, seq = 0, bph = 0, aph = 0; int bs = 0, aslot = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int bs = it % a.b_slots;
-        mbar_wait(b_full(bs), (it / a.b_slots) & 1);
-        if (leader) MB2_TRACE(2, it);
+        mbar_wait(b_full(bs), bph);
+        if (elect_one()) MB2_TRACE(2, it);
         const int rot = it & 3;
         const uint32_t sb0 = b_ring + (uint32_t)bs * a.b_slot_bytes;
-        for (int u = 0; u < a.n_units; ++u) {
-          const uint32_t seq = it * a.n_units + u;
+        for (int u = 0; u < a.n_units; ++u, ++seq) {
           const int buf = seq % kGroups;
           mbar_wait(t_empty(buf), ((seq / kGroups) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)buf * kMb2BufCols;
-          if (leader) MB2_TRACE(8, seq);
-          for (int s = 0; s < a.k_stages; ++s, ++q) {
-            int slot; uint32_t ph;
-            if (a.a_resident) { slot = (a.rot_mode == 2 ? rot : u) * a.k_stages + s; ph = 0; }
-            else { slot = q % a.a_slots; ph = (q / a.a_slots) & 1; }
-            mbar_wait(a_full(slot), ph);
+          if (elect_one()) MB2_TRACE(8, seq);
+          const int iu = a.rot_mode == 2 ? rot : u;
+          for (int s = 0; s < a.k_stages; ++s) {
+            uint32_t sa;
+            if (a.a_resident) { mbar_wait(a_full(iu * a.k_stages + s), 0); sa = a_res_addr(iu, s); }
+            else { mbar_wait(a_full(aslot), aph); sa = a_ring + (uint32_t)aslot * a.a_slot_bytes; }
             tc_fence_after();
-            const uint32_t sa = a_addr(slot), sb = sb0 + a.st_boff[s], rb = a.st_rb[s];
+            const uint32_t sb = sb0 + a.st_boff[s], rb = a.st_rb[s];
             const uint64_t d_whi = make_desc_rb(sa, rb), d_wlo = make_desc_rb(sa + a.st_aplane[s], rb);
             const uint64_t d_xhi = make_desc_rb(sb, rb), d_xlo = make_desc_rb(sb + a.st_bplane[s], rb);
             const uint32_t nk = a.st_ksteps[s];
-            if (leader && !(a.dbg & 2)) {
+            if (elect_one()) {
+              if (!(a.dbg & 2)) {
 #pragma unroll
-              for (uint32_t kk = 0; kk < 4; ++kk) {
-                if (kk < nk) {
-                  const uint64_t adv = (uint64_t)(kk * 2);           // +32 bytes (>> 4) inside the swizzle row
-                  umma(d_tmem, d_whi + adv, d_xhi + adv, idesc, (s | (int)kk) != 0);
-                  umma(d_tmem, d_wlo + adv, d_xhi + adv, idesc, 1);
-                  umma(d_tmem, d_whi + adv, d_xlo + adv, idesc, 1);
+                for (uint32_t kk = 0; kk < 4; ++kk) {
+                  if (kk < nk) {
+                    const uint64_t adv = (uint64_t)(kk * 2);           // +32 bytes (>> 4) inside the swizzle row
+                    umma(d_tmem, d_whi + adv, d_xhi + adv, idesc, (s | (int)kk) != 0);
+                    umma(d_tmem, d_wlo + adv, d_xhi + adv, idesc, 1);
+                    umma(d_tmem, d_whi + adv, d_xlo + adv, idesc, 1);
+                  }
                 }
               }
+              if (!a.a_resident) umma_commit(a_empty(aslot));
             }
             __syncwarp();
-            if (leader && !a.a_resident) umma_commit(a_empty(slot));
+            if (!a.a_resident && ++aslot == a.a_slots) { aslot = 0; aph ^= 1; }
           }
-          if (leader) { MB2_TRACE(9, seq); umma_commit(t_full(buf)); MB2_TRACE(3, seq); }
+          if (elect_one()) { MB2_TRACE(9, seq); umma_commit(t_full(buf)); MB2_TRACE(3, seq); }
+          __syncwarp();
         }
-        if (leader) umma_commit(b_empty(bs));
+        if (elect_one()) umma_commit(b_empty(bs));
         __syncwarp();
+        if (++bs == a.b_slots) { bs = 0; bph ^= 1; }
       }
     }
   } else {
@@ -485,6 +493,7 @@ void launch_mbconv2(const Mb2Plan& P, const Mb2Launch& L, cudaStream_t s, Launch
   a.d_tile_bytes = RowTiles::make(P.C).tile_bytes; a.partial = L.partial;
   a.B = L.B; a.H = L.H; a.W = L.W; a.C = P.C; a.Ho = L.Ho; a.Wo = L.Wo;
   a.TH = P.TH; a.PH = P.PH; a.n_mma = P.n_mma; a.tiles_h = P.tiles_h; a.tiles_w = P.tiles_w;
+  { static const int n_forced = getenv("BNB_MB2_NMMA") ? atoi(getenv("BNB_MB2_NMMA")) : 0; if (n_forced > 0) a.n_mma = n_forced; }   // timing experiment (wrong results)
   a.n_units = P.n_units; a.k_stages = P.k_stages; a.rot_mode = rot_mode_of(P);
   a.a_slots = P.a_slots; a.b_slots = P.b_slots; a.a_resident = P.a_resident; a.n_img_units = a.rot_mode == 2 ? 4 : P.n_units;
   a.mma_batch = P.a_resident ? kGroups : std::max(1, std::min(kGroups, P.a_slots / P.k_stages));
@@ -505,8 +514,8 @@ void launch_mbconv2(const Mb2Plan& P, const Mb2Launch& L, cudaStream_t s, Launch
   const long long my_idx = launch_idx.fetch_add(1);
   long long* trace = nullptr;
   if (trace_path && my_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 2 * 10 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 2 * 10 * 64 * sizeof(long long), s)); a.trace = trace; }
-  if (P.S == 1 && P.TW == 8) mbconv2_kernel<1, 8><<<grid, kThreads, P.smem_bytes, s>>>(a);
-  else if (P.S == 2 && P.TW == 4) mbconv2_kernel<2, 4><<<grid, kThreads, P.smem_bytes, s>>>(a);
+  if (P.S == 1 && P.TW == 8) launch_k(mbconv2_kernel<1, 8>, dim3(grid), dim3(kThreads), P.smem_bytes, s, a);
+  else if (P.S == 2 && P.TW == 4) launch_k(mbconv2_kernel<2, 4>, dim3(grid), dim3(kThreads), P.smem_bytes, s, a);
   else throw std::runtime_error("mbconv2: unsupported tile shape");
   if (trace) {
     std::vector<long long> h(2 * 10 * 64);

@@ -25,10 +25,12 @@ sigmoid_topk_kernel(const float* __restrict__ logits, int n, float sensitivity, 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* x = logits + (size_t)b * n;
   const double sens = (double)sensitivity;
+  pdl_trigger();
+  pdl_wait();
   // NaN logits (a NaN/Inf PCM sample propagates to every logit) become confidence NaN in the reference too; here they
   // rank below every real confidence (-1 sentinel) so the arg-max rounds below always find an in-range index
   for (int i = tid; i < n; i += kTopkThreads) {
-    const float c = (float)(1.0 / (1.0 + exp(-sens * (double)__ldg(x + i))));
+    const float c = (float)(1.0 / (1.0 + exp(-sens * (double)__ldcg(x + i))));
     s_conf[i] = (c == c) ? c : -1.f;
   }
   __syncthreads();
@@ -58,7 +60,7 @@ sigmoid_topk_kernel(const float* __restrict__ logits, int n, float sensitivity, 
 
 void launch_sigmoid_topk(const float* logits, int B, int n, float sensitivity, int k, int32_t* idx, float* conf,
                          cudaStream_t s, LaunchCounter& lc) {
-  sigmoid_topk_kernel<<<B, kTopkThreads, (size_t)n * sizeof(float), s>>>(logits, n, sensitivity, k, idx, conf);
+  launch_k(sigmoid_topk_kernel, dim3(B), dim3(kTopkThreads), (size_t)n * sizeof(float), s, logits, n, sensitivity, k, idx, conf);
   BNB_LAUNCH_CHECK(lc);
 }
 

@@ -98,6 +98,9 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
   const int nt_fix = blockIdx.x % a.n_tiles, mt_first = blockIdx.x / a.n_tiles, mt_step = gridDim.x / a.n_tiles;
   const int k_stages = (a.K + kBK - 1) / kBK;
   if (threadIdx.x == 0) PW2_TRACE(0, 0);
+  // PDL (common.cuh): the loader first issues the resident weight tile (a constant), then joins the wait
+  pdl_trigger();
+  if (warp != kLoadWarp) pdl_wait();
 
   if (warp >= kConvWarp0) {
     // ============================== converters (gate layers): A <- split((hi + lo) * gate), in place, thread-private ===
@@ -121,8 +124,8 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
               g0[q] = make_float4(1.f, 1.f, 1.f, 1.f); g1[q] = g0[q];
               if (m < a.M) {
                 const float* gp = a.gate + (size_t)(m / a.rows_per_chunk) * a.K + k;
-                g0[q] = __ldg(reinterpret_cast<const float4*>(gp));
-                g1[q] = __ldg(reinterpret_cast<const float4*>(gp + 4));
+                g0[q] = __ldcg(reinterpret_cast<const float4*>(gp));          // written by the previous kernel: coherent load (PDL, common.cuh)
+                g1[q] = __ldcg(reinterpret_cast<const float4*>(gp + 4));
               }
             }
           }
@@ -153,24 +156,28 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
       }
     }
   } else if (warp == kLoadWarp) {
-    // ============================== loader: A hi / lo tiles by TMA, weight slabs by bulk copies ========================
-    uint32_t it = 0;
+    // ============================== loader: one bulk copy per (m-tile, K stage) A block, weight slabs by bulk copies ========
+    // (whole warp walks the loop, one elected lane issues: see elect_one())
+    uint32_t it = 0, ph = 0; int s = 0;
     const int n0 = nt_fix * a.bn;
     const uint32_t bn_bytes = (uint32_t)min(a.bn, a.n_pad - n0) * 128u;
-    if (a.b_res && lane == 0) {                 // this CTA's weight tile, every K stage, loaded once
-      mbar_arrive_expect_tx(bres_bar, (uint32_t)k_stages * 2 * bn_bytes);
-      for (int ks = 0; ks < k_stages; ++ks) {
-        const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
-        bulk_g2s(bres + (uint32_t)ks * 2 * b_bytes, wsrc, bn_bytes, bres_bar);
-        bulk_g2s(bres + (uint32_t)ks * 2 * b_bytes + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, bres_bar);
+    if (a.b_res) {                              // this CTA's weight tile, every K stage, loaded once
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)k_stages * 2 * bn_bytes);
+        for (int ks = 0; ks < k_stages; ++ks) {
+          const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
+          bulk_g2s(bres + (uint32_t)ks * 2 * b_bytes, wsrc, bn_bytes, bres_bar);
+          bulk_g2s(bres + (uint32_t)ks * 2 * b_bytes + b_bytes, wsrc + (size_t)a.n_pad * 128, bn_bytes, bres_bar);
+        }
       }
+      __syncwarp();
     }
+    pdl_wait();
     for (int mt = mt_first; mt < m_tiles; mt += mt_step) {
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
-        const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
         mbar_wait_relaxed(empty_bar(s), ph ^ 1);
         const uint32_t dst = base + (uint32_t)s * stage_bytes;
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_arrive_expect_tx(tma_bar(s), 2 * kABytes + (a.b_res ? 0u : 2 * bn_bytes));
           // the (m-tile, stage) A operand, hi | lo, is one contiguous 32 KB block of the RowTiles image
           bulk_g2s(dst, a.a_img + (size_t)mt * a.a_tile_bytes + (size_t)ks * (2 * kABytes), 2 * kABytes, tma_bar(s));
@@ -182,16 +189,17 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
           }
         }
         __syncwarp();
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ===========================================================================
-    // Whole warp, warp-uniform values, only the tcgen05 instructions predicated on one lane (descriptors stay in uniform
-    // registers; see mbconv2.cu).  The products of a tile are dealt round-robin to n_acc column ranges of the accumulator
-    // buffer (their sum is the result; the epilogue adds the ranges in a fixed order).
+    // Whole warp, warp-uniform values (counters, no runtime divisions), the tcgen05 instructions issued by one ELECTED lane: a
+    // stage's 12 MMAs are consecutive UTCHMMA instructions (see elect_one() and mbconv2.cu).  The products of a tile are dealt
+    // round-robin to n_acc column ranges of the accumulator buffer (their sum is the result; the epilogue adds the ranges in a
+    // fixed order).
     {
-      const bool leader = lane == 0;
-      uint32_t it = 0, tcount = 0;
+      uint32_t it = 0, tcount = 0, ph = 0; int s = 0;
       if (a.b_res) mbar_wait(bres_bar, 0);
       const int n0 = nt_fix * a.bn;
       const int bn = min(a.bn, a.n_pad - n0);
@@ -203,32 +211,52 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccCols;
         uint32_t acc = 0, started = 0;                     // next accumulator; how many accumulators have received their first product
         for (int ks = 0; ks < k_stages; ++ks, ++it) {
-          const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
           mbar_wait(a.conv ? full_bar(s) : tma_bar(s), ph);
-          if (leader && !a.conv) PW2_TRACE(2, it);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + kABytes);
           const uint32_t sb = a.b_res ? bres + (uint32_t)ks * 2 * b_bytes : sa + 2 * kABytes;
           const uint64_t d_bhi = make_desc(sb), d_blo = make_desc(sb + b_bytes);
-          const int kk_n = min(kBK, a.k_pad - ks * kBK) / 16;
+          const int kk_n = min(kBK, a.k_pad - ks * kBK) >> 4;
+          if (elect_one()) {
+            if (!a.conv) PW2_TRACE(2, it);
+            if (a.n_acc == 1 || a.n_acc == 3) {            // term t -> accumulator t (n_acc == 3) or the single accumulator
+              const uint32_t step = a.n_acc == 3 ? (uint32_t)bn : 0u;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            if (kk < kk_n) {
-              const uint64_t adv = (uint64_t)(kk * 2);
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kk < kk_n) {
+                  const uint64_t adv = (uint64_t)(kk * 2);
+                  const uint32_t first = (uint32_t)((ks | kk) != 0);
+                  umma(d_tmem, d_ahi + adv, d_bhi + adv, idesc, first);
+                  umma(d_tmem + step, d_alo + adv, d_bhi + adv, idesc, a.n_acc == 3 ? first : 1u);
+                  umma(d_tmem + 2 * step, d_ahi + adv, d_blo + adv, idesc, a.n_acc == 3 ? first : 1u);
+                }
+              }
+            } else {
+              uint32_t acc_l = acc, started_l = started;
 #pragma unroll
-              for (int t = 0; t < 3; ++t) {                // hi*hi, lo*hi, hi*lo
-                const uint32_t d = d_tmem + acc * (uint32_t)bn;
-                if (leader) umma(d, (t == 1 ? d_alo : d_ahi) + adv, (t == 2 ? d_blo : d_bhi) + adv, idesc, started >= (uint32_t)a.n_acc);
-                acc = (acc + 1 == (uint32_t)a.n_acc) ? 0u : acc + 1;
-                ++started;
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kk < kk_n) {
+                  const uint64_t adv = (uint64_t)(kk * 2);
+#pragma unroll
+                  for (int t = 0; t < 3; ++t) {                // hi*hi, lo*hi, hi*lo
+                    const uint32_t d = d_tmem + acc_l * (uint32_t)bn;
+                    umma(d, (t == 1 ? d_alo : d_ahi) + adv, (t == 2 ? d_blo : d_bhi) + adv, idesc, started_l >= (uint32_t)a.n_acc);
+                    acc_l = (acc_l + 1 == (uint32_t)a.n_acc) ? 0u : acc_l + 1;
+                    ++started_l;
+                  }
+                }
               }
             }
+            umma_commit(empty_bar(s));
+            PW2_TRACE(4, it);
           }
           __syncwarp();
-          if (leader) { umma_commit(empty_bar(s)); PW2_TRACE(4, it); }
+          // every lane tracks the accumulator rotation the elected lane just walked through
+          { const uint32_t n = 3u * (uint32_t)kk_n; started += n; if (a.n_acc > 1) { acc += n; while (acc >= (uint32_t)a.n_acc) acc -= (uint32_t)a.n_acc; } }
+          if (++s == a.stages) { s = 0; ph ^= 1; }
         }
-        if (leader) umma_commit(tfull_bar(buf));
+        if (elect_one()) umma_commit(tfull_bar(buf));
         __syncwarp();
       }
     }
@@ -268,8 +296,8 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
               int b; uint32_t pix;
               a.rp.split_chunk((uint32_t)mrow, &b, &pix);
               const uint8_t* src = a.r_img + a.rp.entry_piece(b, __ldg(a.rp.res_tbl + pix), rs, rchunk);
-              rvh[j] = __ldg(reinterpret_cast<const uint4*>(src));
-              rvl[j] = __ldg(reinterpret_cast<const uint4*>(src + a.rp.st_plane[rs]));
+              rvh[j] = __ldcg(reinterpret_cast<const uint4*>(src));
+              rvl[j] = __ldcg(reinterpret_cast<const uint4*>(src + a.rp.st_plane[rs]));
             }
           }
         }
@@ -427,8 +455,10 @@ void launch_pw2(const PwTcLayer& L, const Pw2Launch& p, cudaStream_t s, LaunchCo
   a.rp = p.r_patch; a.op = p.o_patch;
   a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.bn = bn; a.n_tiles = (L.n_pad + bn - 1) / bn; a.stages = stages; a.b_res = b_res;
   a.conv = p.gate != nullptr ? 1 : 0;
-  a.n_acc = 3 * bn <= kAccCols ? 3 : (2 * bn <= kAccCols ? 2 : 1);
-  { static const int forced = getenv("BNB_PW2_NACC") ? atoi(getenv("BNB_PW2_NACC")) : 0; if (forced > 0) a.n_acc = std::min(a.n_acc, forced); }
+  // one accumulator by default; BNB_PW2_NACC=2|3 deals the products to independent accumulators (experiment knob: no gain measured)
+  a.n_acc = 1;
+  { static const int forced = getenv("BNB_PW2_NACC") ? atoi(getenv("BNB_PW2_NACC")) : 0;
+    if (forced > 1) a.n_acc = std::min(forced, 3 * bn <= kAccCols ? 3 : (2 * bn <= kAccCols ? 2 : 1)); }
   a.out_vec = (p.N % 4 == 0) ? 4 : ((p.N % 2 == 0) ? 2 : 1);
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int tiles = m_tiles * a.n_tiles;
@@ -439,7 +469,7 @@ void launch_pw2(const PwTcLayer& L, const Pw2Launch& p, cudaStream_t s, LaunchCo
   const long long my_idx = launch_idx.fetch_add(1);
   long long* trace = nullptr;
   if (trace_path && my_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 2 * 8 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 2 * 8 * 64 * sizeof(long long), s)); a.trace = trace; }
-  pw2_kernel<<<grid, kThreads, smem_bytes, s>>>(a);
+  launch_k(pw2_kernel, dim3(grid), dim3(kThreads), smem_bytes, s, a);
   if (trace) {
     std::vector<long long> h(2 * 8 * 64);
     BNB_CUDA(cudaStreamSynchronize(s));

@@ -49,6 +49,15 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     if (spin > (kSpinLimit >> 4)) __trap();
   }
 }
+// One lane of a CONVERGED warp.  Guarding the tcgen05 / bulk-copy issue with this (and not with `lane == 0`) matters: ptxas
+// knows an elect.sync branch holds exactly one thread and emits the UTCHMMA / UBLKCP with its uniform-register operands
+// directly; behind `lane == 0` every such instruction was wrapped in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop
+// (~10 dependent instructions per MMA on an SMSP shared with the epilogue warps: 200 cycles per MMA, profiles/r02 SASS notes).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
