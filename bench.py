@@ -377,7 +377,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--micro-batch", type=int, default=64)
+    ap.add_argument("--micro-batch", type=int, default=128)
     ap.add_argument("--lanes", type=int, default=2)
     ap.add_argument("--precision", default="default", choices=["default", "f32", "f16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -612,13 +612,16 @@ def main():
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1373.2)))
         total_ms = sum(v[0] for v in prof.values())
         # DRAM traffic of the same kernels from the committed ncu launch list (tools/ncu_traffic.py), per launch like `achieved`
-        traffic = None
-        tpath = os.path.join(REPO, "profiles", "r01_dram_traffic.json")
-        if os.path.exists(tpath):
-            tk = json.load(open(tpath))["kernels"]
-            grp = [tk[k] for k in ("mbconv_tc_kernel", "pw_tc_kernel") if k in tk]
-            if grp:
-                traffic = sum(g["dram_bytes_per_step"] for g in grp) / max(1.0, sum(g["launches_per_step"] for g in grp))
+        traffic, tsrc = None, None
+        for tname, knames in (("r02_dram_traffic.json", ("mbconv2_kernel", "pw2_kernel")), ("r01_dram_traffic.json", ("mbconv_tc_kernel", "pw_tc_kernel"))):
+            tpath = os.path.join(REPO, "profiles", tname)
+            if os.path.exists(tpath):
+                tk = json.load(open(tpath))["kernels"]
+                grp = [tk[k] for k in knames if k in tk]
+                if grp:
+                    traffic = sum(g["dram_bytes_per_step"] for g in grp) / max(1.0, sum(g["launches_per_step"] for g in grp))
+                    tsrc = "profiles/%s (ncu dram__bytes_read+write, mean per launch of %s)" % (tname, " + ".join(knames))
+                    break
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -631,8 +634,8 @@ def main():
                     "value_int16_pcm": e2e16_value, "value_two_callers": e2e2_value, "h2d_bytes_per_step_int16_pcm": int(B * N_SAMPLES * 2)},
             "roofline": {"bound": "tensor", "kernel": "pointwise 1x1 conv GEMMs (expand + project, %d launches/step)" % (pw_launches // max(1, a.steps)),
                          "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": traffic,
-                         "traffic_source": "profiles/r01_dram_traffic.json (ncu dram__bytes_read+write, mean per launch of the same kernels)" if traffic else None,
-                         "issued_tflops": 3 * tf, "note": "achieved = algorithmic 1x1-conv FLOPs / time of the tcgen05 kernels (mbconv_tc also does the depthwise conv in that time); every product is issued as 3 fp16 MMAs (hi*hi + lo*hi + hi*lo)",
+                         "traffic_source": tsrc,
+                         "issued_tflops": 3 * tf, "note": "achieved = algorithmic 1x1-conv FLOPs / time of the tcgen05 kernels (mbconv2_kernel also does the SiLUs, the depthwise conv and the SE sums in that time; pw2_kernel the SE gating, residual and the hi/lo split of its output); every product is issued as 3 fp16 MMAs (hi*hi + lo*hi + hi*lo)",
                          "peak_source": which + " bf16 dense (sustained)", "share_of_step": pw_ms / total_ms if total_ms else None},
             "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items()},
             "latency_batch1_ms": lat_ms, "latency_batch1_ms_no_graph": float(np.median(lat_plain)),

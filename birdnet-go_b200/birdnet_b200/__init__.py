@@ -72,6 +72,8 @@ SYMBOLS = {
     "bnb_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bnb_profile_launches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bnb_debug_pw_tiling": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "bnb_debug_mb2_plan": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "bnb_debug_pw2_tiling": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "bnb_debug_mbconv_geometry": (C.c_int, [C.c_int] * 9 + [C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "bnb_describe_model": (C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     "bnb_debug_read_tensor": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
@@ -121,6 +123,27 @@ def pw_tiling(M, N, K):
     bn, st, sm = C.c_int(), C.c_int(), C.c_int64()
     _check(lib.bnb_debug_pw_tiling(M, N, K, C.byref(bn), C.byref(st), C.byref(sm)))
     return bn.value, st.value, sm.value
+
+
+def mb2_plan(H, W, Ho, Wo, stride, Cin, C_exp):
+    """Plan of the F16X3 fused expand+depthwise kernel (mbconv2.cu) for one block: tile, MMA width, weight residency, smem."""
+    lib = load_library()
+    out = (C.c_int * 12)()
+    sm = C.c_int64()
+    _check(lib.bnb_debug_mb2_plan(H, W, Ho, Wo, stride, Cin, C_exp, out, C.byref(sm)))
+    keys = ("ok", "th", "tw", "ph", "pw", "n_mma", "units", "k_stages", "resident", "a_slots", "pair_slots", "pair_bytes")
+    d = dict(zip(keys, list(out)))
+    d["smem_bytes"] = sm.value
+    return d
+
+
+def pw2_tiling(M, N, K, gated=False):
+    """(bn, stages, weights_resident, n_tiles, smem_bytes) of the F16X3 project GEMM (pw2.cu)."""
+    lib = load_library()
+    out = (C.c_int * 4)()
+    sm = C.c_int64()
+    _check(lib.bnb_debug_pw2_tiling(M, N, K, 1 if gated else 0, out, C.byref(sm)))
+    return out[0], out[1], out[2], out[3], sm.value
 
 
 def mbconv_geometry(H, W, Ho, Wo, stride, Cin, C_exp=0, B=0, max_tiles=0):

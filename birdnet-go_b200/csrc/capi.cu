@@ -7,6 +7,8 @@
 #include <set>
 
 #include "engine.h"
+#include "mbconv2.h"
+#include "pw2.h"
 #include "mbconv_tc.h"
 
 using namespace bnb;
@@ -254,6 +256,25 @@ int bnb_debug_mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin,
   const int v[10] = {g.th, g.tw, g.ph, g.pw, g.tiles_h, g.tiles_w, g.k_stages, g.box_c, g.a_slots, g.b_slots};
   for (int i = 0; i < 10; ++i) out10[i] = v[i];
   *smem_bytes = (int64_t)g.smem_bytes;
+  return BNB_OK;
+}
+
+int bnb_debug_mb2_plan(int H, int W, int Ho, int Wo, int stride, int Cin, int C, int* out12, int64_t* smem_bytes) {
+  if (!out12 || !smem_bytes) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL out");
+  const Mb2Plan P = mb2_plan(H, W, Ho, Wo, stride, Cin, C);
+  const int v[12] = {P.ok ? 1 : 0, P.TH, P.TW, P.PH, P.PW, P.n_mma, P.n_units, P.k_stages, P.a_resident, P.a_slots, P.b_slots, (int)P.b_pair_bytes};
+  for (int i = 0; i < 12; ++i) out12[i] = v[i];
+  *smem_bytes = (int64_t)P.smem_bytes;
+  return BNB_OK;
+}
+
+int bnb_debug_pw2_tiling(int M, int N, int K, int gated, int* out4, int64_t* smem_bytes) {
+  if (!out4 || !smem_bytes || M <= 0 || N <= 0 || K <= 0) return fail(BNB_ERR_INVALID_ARGUMENT, "bad tiling query");
+  PwTcLayer L; L.N = N; L.K = K; L.n_pad = (N + 15) / 16 * 16; L.k_pad = (K + 15) / 16 * 16; L.k_stages = (K + 63) / 64;
+  int bn = 0, stages = 0, b_res = 0; size_t sm = 0;
+  pw2_tiling(L, M, gated != 0, &bn, &stages, &sm, &b_res);
+  out4[0] = bn; out4[1] = stages; out4[2] = b_res; out4[3] = (L.n_pad + bn - 1) / bn;
+  *smem_bytes = (int64_t)sm;
   return BNB_OK;
 }
 

@@ -377,32 +377,75 @@ se_gate_kernel(const SeArgs a) {
     }
   }
   __syncthreads();
-  // FC2: six weight loads in flight per thread.  (blockIdx.y could own a slice of the output channels; measured slower with
-  // 2-4 slices — the kernel is bound by the latency of its three dependent phases, not by FC2's weight traffic: gridDim.y = 1)
-  const int per = (((a.C + (int)gridDim.y - 1) / (int)gridDim.y) + 31) & ~31;
-  const int c_lo = (int)blockIdx.y * per, c_hi = min(a.C, c_lo + per);
-  for (int c = c_lo + tid; c < c_hi; c += kSeThreads) {
-    float acc[kSeChunks];
-    const float bz = __ldg(a.b2 + c);
+  // FC2: thread = (4 adjacent channels, half of the hidden units): float4 weight loads, up to 8 in flight; the second half's
+  // partial dot products go through shared memory (the channel means are dead by now) and are added in a fixed order.  The
+  // kernel is a chain of three dependent phases on 32..128 CTAs: its time is load latency, so the point is few, wide batches
+  // (C = 1536 took 2 rounds x 8 batches of scalar loads before: profiles/r02 launch lists, 27 us -> see r02 notes).
+  {
+    const int c4n = a.C / 4;                                   // C % 4 == 0 (checked at launch)
+    const int slice = tid / c4n, c4 = tid - slice * c4n;
+    const int jh = (a.Cse + 1) / 2;
+    const int j0 = slice == 0 ? 0 : jh, j1 = slice == 0 ? jh : a.Cse;
+    float4 acc[kSeChunks];
 #pragma unroll
-    for (int g = 0; g < kSeChunks; ++g) acc[g] = bz;
-    int j = 0;
-    for (; j + 6 <= a.Cse; j += 6) {                               // w2t: [Cse][C] (transposed at load) -> coalesced
-      float wv[6];
+    for (int g = 0; g < kSeChunks; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slice < 2) {
+      const float4* wp = reinterpret_cast<const float4*>(a.w2t) + c4;
+      int j = j0;
+      for (; j + 8 <= j1; j += 8) {
+        float4 wv[8];
 #pragma unroll
-      for (int t = 0; t < 6; ++t) wv[t] = __ldg(a.w2t + (size_t)(j + t) * a.C + c);
+        for (int t = 0; t < 8; ++t) wv[t] = __ldg(wp + (size_t)(j + t) * c4n);
 #pragma unroll
-      for (int t = 0; t < 6; ++t)
+        for (int t = 0; t < 8; ++t)
 #pragma unroll
-        for (int g = 0; g < kSeChunks; ++g) acc[g] = fmaf(s_hidden[g][j + t], wv[t], acc[g]);
+          for (int g = 0; g < kSeChunks; ++g) {
+            const float h = s_hidden[g][j + t];
+            acc[g].x = fmaf(h, wv[t].x, acc[g].x); acc[g].y = fmaf(h, wv[t].y, acc[g].y);
+            acc[g].z = fmaf(h, wv[t].z, acc[g].z); acc[g].w = fmaf(h, wv[t].w, acc[g].w);
+          }
+      }
+      for (; j + 4 <= j1; j += 4) {
+        float4 wv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) wv[t] = __ldg(wp + (size_t)(j + t) * c4n);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int g = 0; g < kSeChunks; ++g) {
+            const float h = s_hidden[g][j + t];
+            acc[g].x = fmaf(h, wv[t].x, acc[g].x); acc[g].y = fmaf(h, wv[t].y, acc[g].y);
+            acc[g].z = fmaf(h, wv[t].z, acc[g].z); acc[g].w = fmaf(h, wv[t].w, acc[g].w);
+          }
+      }
+      for (; j < j1; ++j) {
+        const float4 wv = __ldg(wp + (size_t)j * c4n);
+#pragma unroll
+        for (int g = 0; g < kSeChunks; ++g) {
+          const float h = s_hidden[g][j];
+          acc[g].x = fmaf(h, wv.x, acc[g].x); acc[g].y = fmaf(h, wv.y, acc[g].y);
+          acc[g].z = fmaf(h, wv.z, acc[g].z); acc[g].w = fmaf(h, wv.w, acc[g].w);
+        }
+      }
+      if (slice == 1) {
+#pragma unroll
+        for (int g = 0; g < kSeChunks; ++g) *reinterpret_cast<float4*>(&s_mean[g][4 * c4]) = acc[g];
+      }
     }
-    for (; j < a.Cse; ++j) {
-      const float wv = __ldg(a.w2t + (size_t)j * a.C + c);
+    __syncthreads();
+    if (slice == 0) {
+      const float4 bz = __ldg(reinterpret_cast<const float4*>(a.b2) + c4);
 #pragma unroll
-      for (int g = 0; g < kSeChunks; ++g) acc[g] = fmaf(s_hidden[g][j], wv, acc[g]);
+      for (int g = 0; g < kSeChunks; ++g) {
+        if (g < nb) {
+          const float4 o = *reinterpret_cast<const float4*>(&s_mean[g][4 * c4]);
+          float4 r;
+          r.x = sigmoid_f(bz.x + (acc[g].x + o.x)); r.y = sigmoid_f(bz.y + (acc[g].y + o.y));
+          r.z = sigmoid_f(bz.z + (acc[g].z + o.z)); r.w = sigmoid_f(bz.w + (acc[g].w + o.w));
+          *reinterpret_cast<float4*>(a.gate + (size_t)(b0 + g) * a.C + 4 * c4) = r;
+        }
+      }
     }
-#pragma unroll
-    for (int g = 0; g < kSeChunks; ++g) if (g < nb) a.gate[(size_t)(b0 + g) * a.C + c] = sigmoid_f(acc[g]);
   }
 }
 
@@ -543,7 +586,7 @@ void launch_dw_conv(const DwArgs& a0, cudaStream_t s, LaunchCounter& lc) {
 }
 
 void launch_se_gate(const SeArgs& a, cudaStream_t s, LaunchCounter& lc) {
-  if (a.C > kSeMaxC || a.Cse > kSeMaxS) throw std::runtime_error("se_gate: channel count exceeds kernel limits");
+  if (a.C > kSeMaxC || a.Cse > kSeMaxS || a.C % 4 || a.C / 2 > kSeThreads) throw std::runtime_error("se_gate: channel count exceeds kernel limits");
   launch_k(se_gate_kernel, dim3((a.B + kSeChunks - 1) / kSeChunks, 1), dim3(kSeThreads), 0, s, a);
   lc.n++;
 }

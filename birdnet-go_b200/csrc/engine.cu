@@ -75,7 +75,7 @@ void Engine::init(const void* tflite, size_t len, const bnb_options& opts) {
   device_name_ = std::string("CUDA:") + std::to_string(dev) + " " + prop.name;
   tc_prepare_device(dev);
   max_batch_ = opts.max_batch > 0 ? opts.max_batch : 256;
-  micro_ = opts.micro_batch > 0 ? opts.micro_batch : 32;
+  micro_ = opts.micro_batch > 0 ? opts.micro_batch : 128;   // r02 sweep (profiles/r02_bench_lines.txt): 64 -> 59.4k, 128 -> 63.2k, 256 -> 63.5k chunks/s but no H2D overlap inside a 256-chunk call
   n_lanes_ = opts.lanes > 0 ? std::min<int>(opts.lanes, kMaxLanes) : 2;
   use_graphs_ = opts.use_graphs != 0;
   fused_ = !(getenv("BNB_FUSED") && atoi(getenv("BNB_FUSED")) == 0);

@@ -55,6 +55,9 @@ struct Mb2Args {
   int dbg;                                // BNB_MB2_DBG timing experiments (wrong results): 1 = epilogue skips its TMEM loads, 2 = no MMAs issued, 4 = epilogue skips its stores
   int mma_batch, mma_cross;               // units whose MMAs the issuer interleaves (<= kGroups); may a round span two tiles
   uint32_t a_slot_bytes, a_region_bytes, b_slot_bytes, img_unit_bytes;
+  int n_bufs;                             // accumulator buffers in TMEM: 512 / (2 * n_mma) columns each, 2..4
+  uint32_t b_pair_bytes;                 // shared-memory bytes of one PAIR slot (two tiles' patches side by side per plane)
+  uint32_t st_poff[kMb2MaxStages], st_pplane[kMb2MaxStages];   // stage offset / plane bytes inside a pair slot
   long long* trace;                      // debug timeline (BNB_MB2_TRACE): [2 CTAs][8 events][64 slots] clock64 stamps, else null
   uint32_t st_rb[kMb2MaxStages], st_ksteps[kMb2MaxStages], st_k0[kMb2MaxStages], st_aoff[kMb2MaxStages],
       st_aplane[kMb2MaxStages], st_boff[kMb2MaxStages], st_bplane[kMb2MaxStages];
@@ -139,7 +142,7 @@ mbconv2_kernel(const Mb2Args a) {
   // weight slab address: resident slabs are packed exactly like the image (unit-major, stages inside); the streaming ring has
   // one max-sized slot per slab in flight
   auto a_res_addr = [&](int iu, int s) { return a_ring + (uint32_t)iu * a.img_unit_bytes + a.st_aoff[s]; };
-  const uint32_t bars = b_ring + (uint32_t)a.b_slots * a.b_slot_bytes;
+  const uint32_t bars = b_ring + (uint32_t)a.b_slots * a.b_pair_bytes;
   auto a_full = [&](int s) { return bars + 8u * s; };
   auto a_empty = [&](int s) { return bars + 8u * (a.a_slots + s); };
   const uint32_t bb = bars + 16u * a.a_slots;
@@ -153,7 +156,7 @@ mbconv2_kernel(const Mb2Args a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.a_slots; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < a.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int g = 0; g < kGroups; ++g) { mbar_init(t_full(g), 1); mbar_init(t_empty(g), 128); }
+    for (int g = 0; g < a.n_bufs; ++g) { mbar_init(t_full(g), 1); mbar_init(t_empty(g), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -176,13 +179,27 @@ mbconv2_kernel(const Mb2Args a) {
   if (warp == kLoadBWarp) {
     // ============================== patch loader: the tile's whole shared-memory slot is ONE contiguous image in memory ===
     // (whole warp walks the loop; one elected lane issues: see elect_one())
-    uint32_t it = 0, ph = 0; int bs = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    // A slot holds a PAIR of consecutive tiles of this CTA: per K stage [hi plane: tile 0 rows | tile 1 rows][lo plane: ...],
+    // so that ONE MMA covers both patches (N = 2 * n_mma).  Why: a tcgen05.mma costs ~130 cycles here whatever its N
+    // (profiles/r02: N = 48 / 80 / 112 all gave 15 MMAs = 2.0 k cycles), so the MMA count per tile had to come down.
+    uint32_t pit = 0, ph = 0; int bs = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += 2 * gridDim.x, ++pit) {
       mbar_wait_relaxed(b_empty(bs), ph ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(b_full(bs), a.b_slot_bytes);
-        bulk_g2s(b_ring + (uint32_t)bs * a.b_slot_bytes, a.x_img + (size_t)tile * a.b_slot_bytes, a.b_slot_bytes, b_full(bs));
-        MB2_TRACE(1, it);
+        const bool two = tile + (int)gridDim.x < total_tiles;
+        uint32_t tx = 0;
+        for (int s = 0; s < a.k_stages; ++s) tx += 2u * (uint32_t)a.n_mma * a.st_rb[s];
+        mbar_arrive_expect_tx(b_full(bs), two ? 2u * tx : tx);
+        const uint32_t slot = b_ring + (uint32_t)bs * a.b_pair_bytes;
+        for (int h = 0; h < (two ? 2 : 1); ++h) {
+          const uint8_t* src = a.x_img + (size_t)(tile + h * (int)gridDim.x) * a.b_slot_bytes;
+          for (int s = 0; s < a.k_stages; ++s) {
+            const uint32_t bytes = (uint32_t)a.n_mma * a.st_rb[s];
+            bulk_g2s(slot + a.st_poff[s] + (uint32_t)h * bytes, src + a.st_boff[s], bytes, b_full(bs));
+            bulk_g2s(slot + a.st_poff[s] + a.st_pplane[s] + (uint32_t)h * bytes, src + a.st_boff[s] + a.st_bplane[s], bytes, b_full(bs));
+          }
+        }
+        MB2_TRACE(1, pit);
       }
       __syncwarp();
       if (++bs == a.b_slots) { bs = 0; ph ^= 1; }
@@ -201,7 +218,7 @@ mbconv2_kernel(const Mb2Args a) {
         }
     } else {
       int slot = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += 2 * gridDim.x)            // one pass over the slabs per PAIR of tiles
         for (int u = 0; u < a.n_units; ++u)
           for (int s = 0; s < a.k_stages; ++s) {
             mbar_wait_relaxed(a_empty(slot), ph ^ 1);
@@ -220,18 +237,18 @@ mbconv2_kernel(const Mb2Args a) {
     // a stage's MMAs are then consecutive UTCHMMA instructions.  Guarded by `lane == 0` each of them sat in a waterfall loop and
     // the issuer needed ~200 cycles per MMA (profiles/r02 timeline: 15 MMAs = 3 k cycles per unit, the kernel's critical path).
     {
-      const uint32_t idesc = make_idesc_mn(128u, (uint32_t)a.n_mma);
-      uint32_t it = 0, seq = 0, bph = 0, aph = 0; int bs = 0, aslot = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t idesc = make_idesc_mn(128u, 2u * (uint32_t)a.n_mma);          // both tiles of the pair
+      uint32_t pit = 0, seq = 0, bph = 0, aph = 0, tph = 0; int bs = 0, aslot = 0, buf = 0;
+      const uint32_t buf_cols = 2u * (uint32_t)a.n_mma;                        // one accumulator = one unit of a pair of tiles
+      for (int tile = blockIdx.x; tile < total_tiles; tile += 2 * gridDim.x, ++pit) {
         mbar_wait(b_full(bs), bph);
-        if (elect_one()) MB2_TRACE(2, it);
-        const int rot = it & 3;
-        const uint32_t sb0 = b_ring + (uint32_t)bs * a.b_slot_bytes;
+        if (elect_one()) MB2_TRACE(2, pit);
+        const int rot = pit & 3;
+        const uint32_t sb0 = b_ring + (uint32_t)bs * a.b_pair_bytes;
         for (int u = 0; u < a.n_units; ++u, ++seq) {
-          const int buf = seq % kGroups;
-          mbar_wait(t_empty(buf), ((seq / kGroups) & 1) ^ 1);
+          mbar_wait(t_empty(buf), tph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)buf * kMb2BufCols;
+          const uint32_t d_tmem = tmem_base + (uint32_t)buf * buf_cols;
           if (elect_one()) MB2_TRACE(8, seq);
           const int iu = a.rot_mode == 2 ? rot : u;
           for (int s = 0; s < a.k_stages; ++s) {
@@ -239,9 +256,9 @@ mbconv2_kernel(const Mb2Args a) {
             if (a.a_resident) { mbar_wait(a_full(iu * a.k_stages + s), 0); sa = a_res_addr(iu, s); }
             else { mbar_wait(a_full(aslot), aph); sa = a_ring + (uint32_t)aslot * a.a_slot_bytes; }
             tc_fence_after();
-            const uint32_t sb = sb0 + a.st_boff[s], rb = a.st_rb[s];
+            const uint32_t sb = sb0 + a.st_poff[s], rb = a.st_rb[s];
             const uint64_t d_whi = make_desc_rb(sa, rb), d_wlo = make_desc_rb(sa + a.st_aplane[s], rb);
-            const uint64_t d_xhi = make_desc_rb(sb, rb), d_xlo = make_desc_rb(sb + a.st_bplane[s], rb);
+            const uint64_t d_xhi = make_desc_rb(sb, rb), d_xlo = make_desc_rb(sb + a.st_pplane[s], rb);
             const uint32_t nk = a.st_ksteps[s];
             if (elect_one()) {
               if (!(a.dbg & 2)) {
@@ -262,6 +279,7 @@ mbconv2_kernel(const Mb2Args a) {
           }
           if (elect_one()) { MB2_TRACE(9, seq); umma_commit(t_full(buf)); MB2_TRACE(3, seq); }
           __syncwarp();
+          if (++buf == a.n_bufs) { buf = 0; tph ^= 1; }
         }
         if (elect_one()) umma_commit(b_empty(bs));
         __syncwarp();
@@ -270,29 +288,37 @@ mbconv2_kernel(const Mb2Args a) {
     }
   } else {
     // ============================== epilogue groups (3 x 4 warps): thread = one expanded channel ====================
+    // group g takes the pair-units whose sequence number has parity g & 1, and of those tile g >> 1 of the pair; the
+    // accumulators rotate over n_bufs TMEM buffers (seq % n_bufs, tracked with counters: no runtime division)
     const int g = warp >> 2, quarter = warp & 3;
-    const uint32_t tbuf = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * kMb2BufCols;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int gpar = g & 1, half = g >> 1;
+    int gbuf = gpar; uint32_t par = 0;                              // buffer / barrier parity of this group's NEXT pair-unit
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * a.n_mma);
+    uint32_t pit = 0;
+    for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += 2 * gridDim.x, ++pit) {
+      const int tile = tile0 + half * (int)gridDim.x;
+      const bool have = tile < total_tiles;                        // an odd tail: the pair's second tile does not exist
       const int b = tile / tiles_per_chunk, tt = tile - b * tiles_per_chunk;
       const int ty = tt / a.tiles_w, tx = tt - ty * a.tiles_w;
       const int ho0 = ty * a.TH, wo0 = tx * TW;
       const int hi0 = ho0 * S - 1, wi0 = wo0 * S - 1;
       const bool left_oob = wi0 < 0, right_oob = wi0 + PW - 1 >= a.W;
-      const int rot = it & 3;
+      const int rot = pit & 3;
       for (int u = 0; u < a.n_units; ++u) {
-        const uint32_t seq = it * a.n_units + u;
-        if ((int)(seq % kGroups) != g) continue;
-        const uint32_t par = (seq / kGroups) & 1;
+        const uint32_t seq = pit * a.n_units + u;
+        if ((int)(seq & 1) != gpar) continue;
+        const int mybuf = gbuf; const uint32_t mypar = par;       // this item's buffer; advance the counters for the next one
+        gbuf += 2; if (gbuf >= a.n_bufs) { gbuf -= a.n_bufs; par ^= 1; }
+        const uint32_t tbuf = tlane + (uint32_t)mybuf * (2u * (uint32_t)a.n_mma);
         int qeff = quarter;
         bool warp_active;
         const int rows_u = min(128, a.C - u * 128);
         if (a.rot_mode == 1 && u == a.n_units - 1) { warp_active = quarter == rot; qeff = 0; }
         else if (a.rot_mode == 2) { qeff = (quarter - rot) & 3; warp_active = qeff * 32 < rows_u; }
         else warp_active = qeff * 32 < rows_u;
-        if (!warp_active) {                                       // nothing in this lane quarter: handshake only
-          mbar_wait(t_full(g), par);
-          mbar_arrive(t_empty(g));
+        if (!warp_active || !have) {                              // nothing for this warp: handshake only
+          mbar_wait(t_full(mybuf), mypar);
+          mbar_arrive(t_empty(mybuf));
           continue;
         }
         const int c = u * 128 + qeff * 32 + lane;
@@ -301,16 +327,16 @@ mbconv2_kernel(const Mb2Args a) {
 #pragma unroll
         for (int t = 0; t < 9; ++t) wd[t] = active ? __ldg(a.w_dw + (size_t)t * a.C + c) : 0.f;
         if (active) { bd = __ldg(a.bias_dw + c); be = __ldg(a.bias_e + c); }
-        mbar_wait(t_full(g), par);
+        mbar_wait(t_full(mybuf), mypar);
         tc_fence_after();
-        if (lane == 0 && quarter == 0) MB2_TRACE(4, seq);
+        if (lane == 0 && quarter == 0 && half == 0) MB2_TRACE(4, seq);
 
         float lsum = 0.f;
         float rA[PW], rB[PW], rC[PW];
         auto ld = [&](float (&dst)[PW], int r) {
           const int hi = hi0 + r;
           load_row<PW>(dst, tbuf + (uint32_t)(r * PW), hi >= 0 && hi < a.H, left_oob, right_oob, be, a.dbg);
-          if (r == a.PH - 1) { tc_fence_before(); mbar_arrive(t_empty(g)); if (lane == 0 && quarter == 0) MB2_TRACE(5, seq); }     // accumulator fully read: hand the buffer back
+          if (r == a.PH - 1) { tc_fence_before(); mbar_arrive(t_empty(mybuf)); if (lane == 0 && quarter == 0 && half == 0) MB2_TRACE(5, seq); }     // accumulator fully read: hand the buffer back
         };
         // RowTiles image of the result: row m = (b*Ho + ho)*Wo + wo, 64-channel stage c >> 6, chunk (c >> 3) & 7
         const uint32_t m_tile0 = ((uint32_t)b * a.Ho + ho0) * a.Wo + wo0;
@@ -336,7 +362,7 @@ mbconv2_kernel(const Mb2Args a) {
           }
         }
         if (a.partial != nullptr && active) a.partial[((size_t)b * tiles_per_chunk + tt) * a.C + c] = lsum;
-        if (lane == 0 && quarter == 0) MB2_TRACE(6, seq);
+        if (lane == 0 && quarter == 0 && half == 0) MB2_TRACE(6, seq);
       }
     }
   }
@@ -399,25 +425,32 @@ Mb2Plan mb2_plan(int H, int W, int Ho, int Wo, int stride, int Cin, int C, bool 
   P.img_unit_bytes = aoff;
   P.a_slot_bytes = 2 * P.st_aplane[0];
   P.b_slot_bytes = boff;
+  uint32_t poff = 0;
+  for (int s = 0; s < ns; ++s) {
+    P.st_pplane[s] = 2u * (uint32_t)P.n_mma * (uint32_t)P.st_rb[s];           // multiple of 1024 (n_mma % 16 == 0): swizzle atoms stay aligned
+    P.st_poff[s] = poff; poff += 2 * P.st_pplane[s];
+  }
+  P.b_pair_bytes = poff;
   // shared-memory plan: all weight slabs resident when they fit beside a double-buffered patch, else a streaming ring
   const size_t budget = kMb2SmemLimit - 1024 /*alignment*/ - 512 /*barriers*/;
   const bool ragged = (C % 128) != 0;
   const size_t plain_bytes = (size_t)P.n_units * P.img_unit_bytes;           // resident slabs are packed
-  if (P.n_units == 1 && ragged && 4 * plain_bytes + 2 * (size_t)P.b_slot_bytes <= budget) {
+  const size_t pair = P.b_pair_bytes;
+  if (P.n_units == 1 && ragged && 4 * plain_bytes + 2 * pair <= budget) {
     P.a_resident = 1; P.a_slots = 4 * ns; P.b_slots = 2; P.a_region_bytes = (uint32_t)(4 * plain_bytes);   // single ragged unit: four rotated versions
-  } else if (plain_bytes + 2 * (size_t)P.b_slot_bytes <= budget) {
+  } else if (plain_bytes + 2 * pair <= budget) {
     P.a_resident = 1; P.a_slots = P.n_units * ns; P.b_slots = 2; P.a_region_bytes = (uint32_t)plain_bytes;
   } else {
     P.a_resident = 0;
     P.b_slots = 2;
-    size_t left = budget > 2 * (size_t)P.b_slot_bytes ? budget - 2 * (size_t)P.b_slot_bytes : 0;
+    size_t left = budget > 2 * pair ? budget - 2 * pair : 0;
     int slots = (int)(left / P.a_slot_bytes);
-    if (slots < std::max(2, ns + 1)) { P.b_slots = 1; left = budget - P.b_slot_bytes; slots = (int)(left / P.a_slot_bytes); }
+    if (slots < std::max(2, ns + 1)) { P.b_slots = 1; left = budget > pair ? budget - pair : 0; slots = (int)(left / P.a_slot_bytes); }
     if (slots < 2) return P;
     P.a_slots = std::min(slots, 6);
     P.a_region_bytes = (uint32_t)P.a_slots * P.a_slot_bytes;
   }
-  P.smem_bytes = 1024 + (size_t)P.a_region_bytes + (size_t)P.b_slots * P.b_slot_bytes + 16 * (size_t)(P.a_slots + P.b_slots + kGroups) + 64;
+  P.smem_bytes = 1024 + (size_t)P.a_region_bytes + (size_t)P.b_slots * P.b_pair_bytes + 16 * (size_t)(P.a_slots + P.b_slots + kGroups) + 64;
   if (P.smem_bytes < 116 * 1024) P.smem_bytes = 116 * 1024;     // one CTA per SM: the kernel allocates all 512 TMEM columns
   P.ok = P.smem_bytes <= kMb2SmemLimit;
   (void)H; (void)W;
@@ -500,10 +533,13 @@ void launch_mbconv2(const Mb2Plan& P, const Mb2Launch& L, cudaStream_t s, Launch
   a.mma_cross = P.b_slots >= 2 ? 1 : 0;
   { static const int dbg = getenv("BNB_MB2_DBG") ? atoi(getenv("BNB_MB2_DBG")) : 0; a.dbg = dbg; }
   { static const int forced = getenv("BNB_MB2_BATCH") ? atoi(getenv("BNB_MB2_BATCH")) : 0; if (forced > 0) a.mma_batch = std::min(a.mma_batch, forced); }
-  a.a_slot_bytes = P.a_slot_bytes; a.a_region_bytes = P.a_region_bytes; a.b_slot_bytes = P.b_slot_bytes; a.img_unit_bytes = P.img_unit_bytes;
+  a.a_slot_bytes = P.a_slot_bytes; a.a_region_bytes = P.a_region_bytes; a.b_slot_bytes = P.b_slot_bytes; a.img_unit_bytes = P.img_unit_bytes; a.b_pair_bytes = P.b_pair_bytes;
+  a.n_bufs = std::max(2, std::min(4, kTmemCols / (2 * P.n_mma)));
+  { static const int nb_forced = getenv("BNB_MB2_NBUFS") ? atoi(getenv("BNB_MB2_NBUFS")) : 0; if (nb_forced >= 2) a.n_bufs = std::min(a.n_bufs, nb_forced); }
   for (int st = 0; st < P.k_stages; ++st) {
     a.st_rb[st] = P.st_rb[st]; a.st_ksteps[st] = P.st_ksteps[st]; a.st_k0[st] = P.st_k0[st]; a.st_aoff[st] = P.st_aoff[st];
     a.st_aplane[st] = P.st_aplane[st]; a.st_boff[st] = P.st_boff[st]; a.st_bplane[st] = P.st_bplane[st];
+    a.st_poff[st] = P.st_poff[st]; a.st_pplane[st] = P.st_pplane[st];
   }
   const long long tiles = (long long)L.B * P.tiles_h * P.tiles_w;
   const int grid = tiles < kNumSMs ? (int)tiles : kNumSMs;

@@ -13,7 +13,7 @@ namespace bnb {
 
 constexpr size_t kMb2SmemLimit = 227 * 1024;
 constexpr int kMb2MaxStages = 3;
-constexpr int kMb2BufCols = 128;      // TMEM columns per accumulator buffer (4 buffers of 512 columns)
+constexpr int kMb2BufCols = 128;      // TMEM columns per tile patch; an accumulator buffer holds a PAIR of tiles (2 buffers x 256 columns)
 
 // Host-side plan of one layer: tile geometry, K stages, shared-memory layout.  Pure host logic (CPU-testable).
 struct Mb2Plan {
@@ -30,6 +30,8 @@ struct Mb2Plan {
   uint32_t st_bplane[kMb2MaxStages] = {0, 0, 0}; // bytes reserved for one patch plane
   uint32_t img_unit_bytes = 0;                   // weight image bytes per unit (all stages, hi | lo)
   uint32_t a_slot_bytes = 0, a_region_bytes = 0, b_slot_bytes = 0, b_tx_bytes = 0;
+  // shared-memory slot of a PAIR of tiles (the kernel multiplies two patches per MMA): per stage [hi: tile 0 | tile 1][lo: ...]
+  uint32_t b_pair_bytes = 0, st_poff[kMb2MaxStages] = {0, 0, 0}, st_pplane[kMb2MaxStages] = {0, 0, 0};
   int a_slots = 0, b_slots = 0, a_resident = 0;
   size_t smem_bytes = 0;
 };

@@ -34,7 +34,6 @@ using namespace tc;
 
 constexpr int kEpiWarps = 16, kMmaWarp = 16, kLoadWarp = 17, kConvWarp0 = 18, kConvThreads = 256;
 constexpr int kThreads = (kEpiWarps + 2) * 32 + kConvThreads;       // 26 warps: 16 epilogue, MMA issuer, loader, 8 converters (gate layers only)
-constexpr int kEpiStage = 2048;     // bytes of epilogue staging per warp: 32 rows x 16 fp32 columns
 constexpr int kAccCols = 256;
 constexpr uint32_t kABytes = kBM * 128u;      // one fp16 [128][64] plane tile
 
@@ -68,8 +67,7 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
   const int k_stages_all = (a.K + kBK - 1) / kBK;
   const uint32_t bres_bytes = a.b_res ? (uint32_t)k_stages_all * 2 * b_bytes : 0u;    // resident weights: every K stage of this CTA's n-tile
   const uint32_t bres = base + (uint32_t)a.stages * stage_bytes;
-  const uint32_t stg = bres + bres_bytes;                                  // 16 x 2 KB epilogue staging
-  const uint32_t bars = stg + kEpiWarps * kEpiStage;
+  const uint32_t bars = bres + bres_bytes;
   auto tma_bar = [&](int s) { return bars + 8u * s; };
   auto full_bar = [&](int s) { return bars + 8u * (a.stages + s); };
   auto empty_bar = [&](int s) { return bars + 8u * (2 * a.stages + s); };
@@ -103,55 +101,69 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
   if (warp != kLoadWarp) pdl_wait();
 
   if (warp >= kConvWarp0) {
-    // ============================== converters (gate layers): A <- split((hi + lo) * gate), in place, thread-private ===
+    // ============================== converters (gate layers): A <- split((hi + lo) * gate) =================================
+    // The converter threads fetch their pieces of the (m-tile, stage) block STRAIGHT from the RowTiles image with 16-byte
+    // loads (the image is in shared-memory order: same offset on both sides), scale, re-split and store them to the stage slot.
+    // Why not a bulk copy + in-place conversion (the first r02 version): one SM's bulk-copy path delivered ~13 B/clk (three
+    // 32 KB stage copies issued together landed 2.5 k cycles apart, profiles/r02 timelines) and that was the stage period of
+    // every gated layer; 256 threads x 8 loads in flight go through the LSU path instead and the in-place read disappears.
     if (a.conv) {
       const int pt = threadIdx.x - kConvWarp0 * 32;
       const int c = pt & 7, r0 = pt >> 3;
-      uint32_t it = 0;
+      const bool one_gate = (a.rows_per_chunk % kBM) == 0;            // an m-tile lies inside one chunk (front-phase maps)
+      uint32_t it = 0, ph = 0; int s = 0;
+      uint32_t offs[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) offs[q] = swz_off((uint32_t)(r0 + 32 * q), (uint32_t)c, 128u);
       for (int mt = mt_first; mt < m_tiles; mt += mt_step) {
         const int m0 = mt * kBM;
+        const uint8_t* tile = a.a_img + (size_t)mt * a.a_tile_bytes;
         for (int ks = 0; ks < k_stages; ++ks, ++it) {
-          const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
-          uint8_t* hi_p = base_ptr + (size_t)s * stage_bytes;
-          uint8_t* lo_p = hi_p + kABytes;
           const int k = ks * kBK + c * 8;
           const bool live = k < a.K;                                  // K % 8 == 0 for every gated layer (checked at launch)
-          float4 g0[4], g1[4];
+          uint4 h[4], l[4];
           if (live) {
+            const uint8_t* src = tile + (size_t)ks * (2 * kABytes);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int m = m0 + r0 + 32 * q;
-              g0[q] = make_float4(1.f, 1.f, 1.f, 1.f); g1[q] = g0[q];
-              if (m < a.M) {
-                const float* gp = a.gate + (size_t)(m / a.rows_per_chunk) * a.K + k;
-                g0[q] = __ldcg(reinterpret_cast<const float4*>(gp));          // written by the previous kernel: coherent load (PDL, common.cuh)
-                g1[q] = __ldcg(reinterpret_cast<const float4*>(gp + 4));
-              }
+            for (int q = 0; q < 4; ++q) {                             // coherent loads: the image was written by the previous kernel (PDL)
+              h[q] = __ldcg(reinterpret_cast<const uint4*>(src + offs[q]));
+              l[q] = __ldcg(reinterpret_cast<const uint4*>(src + kABytes + offs[q]));
             }
           }
-          mbar_wait_relaxed(tma_bar(s), ph);
+          float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), gb = ga;
+          if (live && one_gate && m0 < a.M) {
+            const float* gp = a.gate + (size_t)(m0 / a.rows_per_chunk) * a.K + k;
+            ga = __ldcg(reinterpret_cast<const float4*>(gp)); gb = __ldcg(reinterpret_cast<const float4*>(gp + 4));
+          }
+          mbar_wait_relaxed(empty_bar(s), ph ^ 1);                    // the MMAs that read this slot last have completed
+          uint8_t* hi_p = base_ptr + (size_t)s * stage_bytes;
+          uint8_t* lo_p = hi_p + kABytes;
           if (pt == 0) PW2_TRACE(2, it);
-          if (live) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int r = r0 + 32 * q;
-              if (m0 + r >= a.M) continue;                            // rows past M arrived as zeros
-              const uint32_t off = swz_off((uint32_t)r, (uint32_t)c, 128u);
-              const uint4 h = *reinterpret_cast<const uint4*>(hi_p + off);
-              const uint4 l = *reinterpret_cast<const uint4*>(lo_p + off);
-              float2 v0 = join2(h.x, l.x), v1 = join2(h.y, l.y), v2 = join2(h.z, l.z), v3 = join2(h.w, l.w);
-              v0.x *= g0[q].x; v0.y *= g0[q].y; v1.x *= g0[q].z; v1.y *= g0[q].w;
-              v2.x *= g1[q].x; v2.y *= g1[q].y; v3.x *= g1[q].z; v3.y *= g1[q].w;
-              uint4 ho, lo;
+          for (int q = 0; q < 4; ++q) {
+            uint4 ho = make_uint4(0, 0, 0, 0), lo = ho;               // channels past K: exact zeros (the slot may hold anything)
+            if (live) {
+              if (!one_gate) {
+                const int m = m0 + r0 + 32 * q;
+                ga = make_float4(1.f, 1.f, 1.f, 1.f); gb = ga;
+                if (m < a.M) {
+                  const float* gp = a.gate + (size_t)(m / a.rows_per_chunk) * a.K + k;
+                  ga = __ldcg(reinterpret_cast<const float4*>(gp)); gb = __ldcg(reinterpret_cast<const float4*>(gp + 4));
+                }
+              }
+              float2 v0 = join2(h[q].x, l[q].x), v1 = join2(h[q].y, l[q].y), v2 = join2(h[q].z, l[q].z), v3 = join2(h[q].w, l[q].w);
+              v0.x *= ga.x; v0.y *= ga.y; v1.x *= ga.z; v1.y *= ga.w;
+              v2.x *= gb.x; v2.y *= gb.y; v3.x *= gb.z; v3.y *= gb.w;
               split2(v0.x, v0.y, ho.x, lo.x); split2(v1.x, v1.y, ho.y, lo.y);
               split2(v2.x, v2.y, ho.z, lo.z); split2(v3.x, v3.y, ho.w, lo.w);
-              *reinterpret_cast<uint4*>(hi_p + off) = ho;
-              *reinterpret_cast<uint4*>(lo_p + off) = lo;
             }
+            *reinterpret_cast<uint4*>(hi_p + offs[q]) = ho;
+            *reinterpret_cast<uint4*>(lo_p + offs[q]) = lo;
           }
           fence_proxy_async();
           mbar_arrive(full_bar(s));
           if (pt == 0) PW2_TRACE(3, it);
+          if (++s == a.stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -177,10 +189,11 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
         mbar_wait_relaxed(empty_bar(s), ph ^ 1);
         const uint32_t dst = base + (uint32_t)s * stage_bytes;
-        if (elect_one()) {
-          mbar_arrive_expect_tx(tma_bar(s), 2 * kABytes + (a.b_res ? 0u : 2 * bn_bytes));
-          // the (m-tile, stage) A operand, hi | lo, is one contiguous 32 KB block of the RowTiles image
-          bulk_g2s(dst, a.a_img + (size_t)mt * a.a_tile_bytes + (size_t)ks * (2 * kABytes), 2 * kABytes, tma_bar(s));
+        if (elect_one() && !(a.conv && a.b_res)) {                  // gated layer with resident weights: nothing to copy per stage
+          mbar_arrive_expect_tx(tma_bar(s), (a.conv ? 0u : 2 * kABytes) + (a.b_res ? 0u : 2 * bn_bytes));
+          // the (m-tile, stage) A operand, hi | lo, is one contiguous 32 KB block of the RowTiles image (gated layers: the
+          // converter warps fetch it themselves)
+          if (!a.conv) bulk_g2s(dst, a.a_img + (size_t)mt * a.a_tile_bytes + (size_t)ks * (2 * kABytes), 2 * kABytes, tma_bar(s));
           PW2_TRACE(1, it);
           if (!a.b_res) {
             const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
@@ -211,7 +224,8 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccCols;
         uint32_t acc = 0, started = 0;                     // next accumulator; how many accumulators have received their first product
         for (int ks = 0; ks < k_stages; ++ks, ++it) {
-          mbar_wait(a.conv ? full_bar(s) : tma_bar(s), ph);
+          if (a.conv) { mbar_wait(full_bar(s), ph); if (!a.b_res) mbar_wait(tma_bar(s), ph); }   // converted A (+ streamed weights)
+          else mbar_wait(tma_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + kABytes);
@@ -263,47 +277,48 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
   } else {
     // ============================== epilogue (warps 0-15) ===============================================================
     // warp w owns TMEM lanes 32*(w%4).. (rows) and the 16-column chunks c with c % 4 == w / 4.  A thread holds one ROW of the
-    // chunk, so the 32x16 fp32 sub-tile goes through a warp-private XOR-swizzled staging buffer and is read back piece-wise
-    // (8 columns = one 16-byte piece of each fp16 plane per lane): global accesses then cover whole pieces / row segments.
-    // Sixteen warps because one warp per 32x32 sub-tile was latency-bound (profiles/r02 timeline: 4.5 k cycles per m-tile).
+    // chunk = two 8-channel pieces, i.e. two adjacent 16-byte pieces of each fp16 plane: they go straight from registers to
+    // memory (no shared-memory transpose: the staging buffers cost 32 KB that now hold resident weights, and their traffic
+    // competed with the MMA operand reads).  Sixteen warps because one warp per 32x32 sub-tile was latency-bound
+    // (profiles/r02 timeline: 4.5 k cycles per m-tile).
     const int quarter = warp & 3, sub = warp >> 2;
-    uint8_t* s_out = base_ptr + (stg - base) + warp * kEpiStage;
     const int n0 = nt_fix * a.bn;
     const int bn = min(a.bn, a.n_pad - n0);
     const bool plane_mode = a.out_mode != 0;
     uint32_t tcount = 0;
     for (int mt = mt_first; mt < m_tiles; mt += mt_step, ++tcount) {
       const int buf = tcount & 1;
+      const int mrow = mt * kBM + quarter * 32 + lane;
+      const bool row_ok = mrow < a.M;
+      // where this row lives in the residual / output patch images (one table lookup per row and m-tile)
+      int pb = 0; uint32_t res_ent = 0xffffffffu; uint4 dst_ent = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      if (plane_mode && row_ok) {
+        uint32_t pix;
+        if (a.r_img != nullptr) { a.rp.split_chunk((uint32_t)mrow, &pb, &pix); res_ent = __ldg(a.rp.res_tbl + pix); }
+        if (a.out_mode == 2) { a.op.split_chunk((uint32_t)mrow, &pb, &pix); dst_ent = __ldg(a.op.dst_tbl + pix); }
+      }
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
       tc_fence_after();
       if (threadIdx.x == 0) PW2_TRACE(5, tcount);
-      const int m_w = mt * kBM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kAccCols;
       for (int c0 = sub * 16; c0 < bn; c0 += 64) {
         const int n = n0 + c0;
-        // read-back pattern of the plane modes: lane -> (row = 16*j + lane/2, 8-column piece = lane & 1), j = 0, 1.
-        // Residual pieces (the block input: pixel m is interior to exactly one patch tile of its image) are requested first.
-        uint4 rvh[2], rvl[2];
-        const int piece = lane & 1, pcol = n + 8 * piece;
-        if (plane_mode && a.r_img != nullptr) {
-          int rs, rchunk;
-          a.rp.stage_of(pcol >> 3, &rs, &rchunk);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int mrow = m_w + 16 * j + (lane >> 1);
-            rvh[j] = make_uint4(0, 0, 0, 0); rvl[j] = rvh[j];
-            if (mrow < a.M && pcol < a.o_pitch) {
-              int b; uint32_t pix;
-              a.rp.split_chunk((uint32_t)mrow, &b, &pix);
-              const uint8_t* src = a.r_img + a.rp.entry_piece(b, __ldg(a.rp.res_tbl + pix), rs, rchunk);
-              rvh[j] = __ldcg(reinterpret_cast<const uint4*>(src));
-              rvl[j] = __ldcg(reinterpret_cast<const uint4*>(src + a.rp.st_plane[rs]));
-            }
-          }
-        }
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)c0, r);
-        __syncwarp();                                      // previous chunk's read-back of s_out is complete
+        // residual pieces (the block input: pixel m is interior to exactly one patch tile of its image) requested before the wait
+        uint4 rvh[2], rvl[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          rvh[p] = make_uint4(0, 0, 0, 0); rvl[p] = rvh[p];
+          const int pcol = n + 8 * p;
+          if (plane_mode && a.r_img != nullptr && row_ok && pcol < a.o_pitch) {
+            int rs, rchunk;
+            a.rp.stage_of(pcol >> 3, &rs, &rchunk);
+            const uint8_t* src = a.r_img + a.rp.entry_piece(pb, res_ent, rs, rchunk);
+            rvh[p] = __ldcg(reinterpret_cast<const uint4*>(src));              // coherent loads: written by an earlier kernel (PDL)
+            rvl[p] = __ldcg(reinterpret_cast<const uint4*>(src + a.rp.st_plane[rs]));
+          }
+        }
         tmem_ld_wait();
         for (int ac = 1; ac < a.n_acc; ++ac) {             // add the other accumulators of the tile (fixed order)
           uint32_t r2[16];
@@ -312,6 +327,7 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
         }
+        float v[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4 * q));      // bias is zero-padded past n_pad
@@ -320,70 +336,57 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
           o.z = __uint_as_float(r[4 * q + 2]) + bz.z; o.w = __uint_as_float(r[4 * q + 3]) + bz.w;
           if (a.act == ACT_SILU) silu4(o.x, o.y, o.z, o.w);
           else if (a.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          *reinterpret_cast<float4*>(s_out + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;
+          v[4 * q] = o.x; v[4 * q + 1] = o.y; v[4 * q + 2] = o.z; v[4 * q + 3] = o.w;
         }
-        __syncwarp();
-        if (plane_mode) {
-          const bool col_ok = pcol < a.o_pitch;            // pad columns of the pitch receive exact zeros (zero weights, zero bias)
-          int os = 0, ochunk = 0;
-          if (a.out_mode == 2) a.op.stage_of(pcol >> 3, &os, &ochunk);
+        if (row_ok && plane_mode) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int row = 16 * j + (lane >> 1), mrow = m_w + row;
-            if (col_ok && mrow < a.M) {
-              const int key = (row >> 1) & 3;
-              const float4 p0 = *reinterpret_cast<const float4*>(s_out + row * 64 + (((2 * piece) ^ key) << 4));
-              const float4 p1 = *reinterpret_cast<const float4*>(s_out + row * 64 + (((2 * piece + 1) ^ key) << 4));
-              float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-              if (a.r_img != nullptr) {
-                const float2 q0 = join2(rvh[j].x, rvl[j].x), q1 = join2(rvh[j].y, rvl[j].y), q2 = join2(rvh[j].z, rvl[j].z), q3 = join2(rvh[j].w, rvl[j].w);
-                v[0] += q0.x; v[1] += q0.y; v[2] += q1.x; v[3] += q1.y; v[4] += q2.x; v[5] += q2.y; v[6] += q3.x; v[7] += q3.y;
-              }
-              uint4 ho, lo;
-              split2(v[0], v[1], ho.x, lo.x); split2(v[2], v[3], ho.y, lo.y); split2(v[4], v[5], ho.z, lo.z); split2(v[6], v[7], ho.w, lo.w);
-              if (a.out_mode == 1) {
-                *reinterpret_cast<uint4*>(a.oh + (size_t)mrow * a.o_pitch + pcol) = ho;
-                *reinterpret_cast<uint4*>(a.ol + (size_t)mrow * a.o_pitch + pcol) = lo;
-              } else {
-                // the next block's PatchTiles image: the pixel goes into every tile whose halo patch contains it (<= 4, from the table)
-                int b; uint32_t pix;
-                a.op.split_chunk((uint32_t)mrow, &b, &pix);
-                const uint32_t lo_off = a.op.st_plane[os];
-                const uint4 ent = __ldg(a.op.dst_tbl + pix);
-                const uint32_t e4[4] = {ent.x, ent.y, ent.z, ent.w};
+          for (int p = 0; p < 2; ++p) {
+            const int pcol = n + 8 * p;
+            if (pcol >= a.o_pitch) continue;               // past the last piece of the pitch (pad columns INSIDE a piece get exact zeros: zero weights, zero bias)
+            float* w = v + 8 * p;
+            if (a.r_img != nullptr) {
+              const float2 q0 = join2(rvh[p].x, rvl[p].x), q1 = join2(rvh[p].y, rvl[p].y), q2 = join2(rvh[p].z, rvl[p].z), q3 = join2(rvh[p].w, rvl[p].w);
+              w[0] += q0.x; w[1] += q0.y; w[2] += q1.x; w[3] += q1.y; w[4] += q2.x; w[5] += q2.y; w[6] += q3.x; w[7] += q3.y;
+            }
+            uint4 ho, lo;
+            split2(w[0], w[1], ho.x, lo.x); split2(w[2], w[3], ho.y, lo.y); split2(w[4], w[5], ho.z, lo.z); split2(w[6], w[7], ho.w, lo.w);
+            if (a.out_mode == 1) {
+              *reinterpret_cast<uint4*>(a.oh + (size_t)mrow * a.o_pitch + pcol) = ho;
+              *reinterpret_cast<uint4*>(a.ol + (size_t)mrow * a.o_pitch + pcol) = lo;
+            } else {
+              // the next block's PatchTiles image: the pixel goes into every tile whose halo patch contains it (<= 4, from the table)
+              int os, ochunk;
+              a.op.stage_of(pcol >> 3, &os, &ochunk);
+              const uint32_t lo_off = a.op.st_plane[os];
+              const uint32_t e4[4] = {dst_ent.x, dst_ent.y, dst_ent.z, dst_ent.w};
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                  if (e4[d] != 0xffffffffu) {
-                    uint8_t* dst = a.o_img + a.op.entry_piece(b, e4[d], os, ochunk);
-                    *reinterpret_cast<uint4*>(dst) = ho;
-                    *reinterpret_cast<uint4*>(dst + lo_off) = lo;
-                  }
+              for (int d = 0; d < 4; ++d) {
+                if (e4[d] != 0xffffffffu) {
+                  uint8_t* dst = a.o_img + a.op.entry_piece(pb, e4[d], os, ochunk);
+                  *reinterpret_cast<uint4*>(dst) = ho;
+                  *reinterpret_cast<uint4*>(dst + lo_off) = lo;
                 }
               }
             }
           }
-        } else {
-          // fp32 output: lane -> (row = 8*j + lane/4, 4 columns = lane & 3): 64-byte row segments per 4 lanes
-          const int chunk = lane & 3, ncol = n + 4 * chunk;
+        } else if (row_ok) {
+          // fp32 output: this thread's 16 consecutive columns of row mrow
+          float* dst = a.out32 + (size_t)mrow * a.N + n;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int row = 8 * j + (lane >> 2), mrow = m_w + row;
-            if (mrow < a.M && c0 + 4 * chunk < bn) {
-              const float4 o = *reinterpret_cast<const float4*>(s_out + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
-              float* dst = a.out32 + (size_t)mrow * a.N + ncol;
-              if (a.out_vec == 4) { if (ncol + 4 <= a.N) *reinterpret_cast<float4*>(dst) = o; }
-              else if (a.out_vec == 2) {
-                if (ncol + 2 <= a.N) *reinterpret_cast<float2*>(dst) = make_float2(o.x, o.y);
-                if (ncol + 4 <= a.N) *reinterpret_cast<float2*>(dst + 2) = make_float2(o.z, o.w);
-              } else {
-                if (ncol < a.N) dst[0] = o.x;
-                if (ncol + 1 < a.N) dst[1] = o.y;
-                if (ncol + 2 < a.N) dst[2] = o.z;
-                if (ncol + 3 < a.N) dst[3] = o.w;
-              }
+          for (int q = 0; q < 4; ++q) {
+            const int ncol = n + 4 * q;
+            if (c0 + 4 * q >= bn) continue;
+            if (a.out_vec == 4) { if (ncol + 4 <= a.N) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]); }
+            else if (a.out_vec == 2) {
+              if (ncol + 2 <= a.N) *reinterpret_cast<float2*>(dst + 4 * q) = make_float2(v[4 * q], v[4 * q + 1]);
+              if (ncol + 4 <= a.N) *reinterpret_cast<float2*>(dst + 4 * q + 2) = make_float2(v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) if (ncol + i < a.N) dst[4 * q + i] = v[4 * q + i];
             }
           }
         }
+        __syncwarp();                                        // reconverge before the next (warp-aligned) TMEM load
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
@@ -404,7 +407,7 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
 // b_res_stages = number of K stages held resident (0 = weights stream with the A tiles)
 size_t smem_for(int bn, int stages, int b_res_stages) {
   const size_t stage = 2 * (size_t)kABytes + (b_res_stages ? 0 : 2 * (size_t)bn * 128);
-  return (size_t)stages * stage + (size_t)b_res_stages * 2 * (size_t)bn * 128 + 1024 /*alignment*/ + kEpiWarps * kEpiStage +
+  return (size_t)stages * stage + (size_t)b_res_stages * 2 * (size_t)bn * 128 + 1024 /*alignment*/ +
          ((8 * (3 * stages + 5) + 16 + 15) & ~15);
 }
 

@@ -219,12 +219,23 @@ __device__ __forceinline__ float silu_e(float t) {       // 1 + exp(-x) from t =
 }
 __device__ __forceinline__ float rcp_f(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 constexpr float kNegLog2e = -1.4426950408889634f;
+__device__ __forceinline__ float ex2_f(float t) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t)); return e; }
+// Four SiLUs with ONE reciprocal (of the product of the four denominators) and packed fp32 multiplies / adds (sm_100 FMUL2 /
+// FADD2 work on register pairs): 22 instructions instead of 30.  Bit-identical to the scalar form: every product is formed
+// in the same association, and the packed instructions round each half like their scalar counterparts.
 __device__ __forceinline__ void silu4(float& x0, float& x1, float& x2, float& x3) {
-  const float a = silu_e(x0 * kNegLog2e), b = silu_e(x1 * kNegLog2e), c = silu_e(x2 * kNegLog2e), d = silu_e(x3 * kNegLog2e);
-  const float ab = a * b, cd = c * d;
+  const float2 k = make_float2(kNegLog2e, kNegLog2e), one = make_float2(1.0f, 1.0f);
+  const float2 t01 = __fmul2_rn(make_float2(x0, x1), k), t23 = __fmul2_rn(make_float2(x2, x3), k);
+  const float2 e01 = make_float2(ex2_f(fminf(t01.x, 30.f)), ex2_f(fminf(t01.y, 30.f)));
+  const float2 e23 = make_float2(ex2_f(fminf(t23.x, 30.f)), ex2_f(fminf(t23.y, 30.f)));
+  const float2 ab2 = __fadd2_rn(e01, one), cd2 = __fadd2_rn(e23, one);          // (a, b), (c, d) = 1 + exp(-x)
+  const float ab = ab2.x * ab2.y, cd = cd2.x * cd2.y;
   const float r = rcp_f(ab * cd);
   const float rab = r * cd, rcd = r * ab;
-  x0 *= rab * b; x1 *= rab * a; x2 *= rcd * d; x3 *= rcd * c;
+  const float2 s01 = __fmul2_rn(make_float2(ab2.y, ab2.x), make_float2(rab, rab));   // 1 / a = rab * b, 1 / b = rab * a
+  const float2 s23 = __fmul2_rn(make_float2(cd2.y, cd2.x), make_float2(rcd, rcd));
+  const float2 y01 = __fmul2_rn(make_float2(x0, x1), s01), y23 = __fmul2_rn(make_float2(x2, x3), s23);
+  x0 = y01.x; x1 = y01.y; x2 = y23.x; x3 = y23.y;
 }
 __device__ __forceinline__ void silu2b(float& x0, float& x1) {
   const float a = silu_e(x0 * kNegLog2e), b = silu_e(x1 * kNegLog2e);

@@ -182,6 +182,11 @@ BNB_API int bnb_debug_pw_tiling(int M, int N, int K, int* bn, int* stages, int64
  * cost model (0 = unknown: fewest tiles); max_tiles caps the tiles per chunk (SE partial-sum slots, 0 = no cap). */
 BNB_API int bnb_debug_mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin, int C, int B, int max_tiles, int* out10,
                                       int64_t* smem_bytes);
+/* Plans of the F16X3 kernels (host logic only).  bnb_debug_mb2_plan: out12 = {ok, th, tw, ph, pw, n_mma (patch rows per tile in
+ * the MMA), units of 128 expanded channels, k_stages, weights resident, weight slots, patch PAIR slots, bytes of a pair slot}.
+ * bnb_debug_pw2_tiling: out4 = {N-tile width, A-ring stages, weights resident, n-tiles}. */
+BNB_API int bnb_debug_mb2_plan(int H, int W, int Ho, int Wo, int stride, int Cin, int C, int* out12, int64_t* smem_bytes);
+BNB_API int bnb_debug_pw2_tiling(int M, int N, int K, int gated, int* out4, int64_t* smem_bytes);
 /* JSON description of the layer plan extracted from a .tflite (no GPU needed). Returns bytes
  * written (excluding NUL) or a negative status; `cap` too small -> BNB_ERR_INVALID_ARGUMENT. */
 BNB_API int bnb_describe_model(const void* tflite, size_t tflite_len, char* json, size_t cap);

@@ -256,11 +256,13 @@ def test_fused_and_unfused_chains_agree(lib_path, golden, audio, monkeypatch):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # round 2: the benched geometry, the async / graph entry points, hostile inputs, several devices in one process
-def test_benched_geometry_matches_golden(lib_path, golden):
-    """bench.py's exact classifier (max_batch 256, micro-batch 64, 2 lanes): all 79 golden soundscape rows, wherever they sit in
-    the tiled batch of 256, against the float64 oracle (VERDICT r1 weak #1: the benched configuration had no oracle test)."""
+@pytest.mark.parametrize("micro", [128, 64])
+def test_benched_geometry_matches_golden(lib_path, golden, micro):
+    """bench.py's exact classifier (max_batch 256, micro-batch 128 — the library default — and the 64 of earlier runs, 2 lanes):
+    all 79 golden soundscape rows, wherever they sit in the tiled batch of 256, against the float64 oracle (VERDICT r1 weak #1:
+    the benched configuration had no oracle test)."""
     from bench import soundscape_batch
-    c = bb.B200Classifier(max_batch=256, micro_batch=64, lanes=2)
+    c = bb.B200Classifier(max_batch=256, micro_batch=micro, lanes=2)
     x = soundscape_batch(256)
     y = c.predict_batch(x)
     ref = golden["soundscape_logits"].astype(np.float64)
@@ -280,7 +282,7 @@ def test_config3_shape_max_batch_1024(lib_path):
     from bench import synth_chunks
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "synth512_golden.npz"))
     x = synth_chunks(512, seed0=1234)
-    c = bb.B200Classifier(max_batch=1024, micro_batch=64, lanes=2)
+    c = bb.B200Classifier(max_batch=1024, lanes=2)                            # library-default micro-batch (128)
     big = np.concatenate([x, x[::-1]])
     idx, conf, logits = c.analyze_batch(big, 1.0, 10, want_logits=True)
     assert np.array_equal(logits[:512], logits[1023:511:-1])                 # same chunk, another slot of the batch: same bits
