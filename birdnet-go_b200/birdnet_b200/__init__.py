@@ -72,6 +72,10 @@ SYMBOLS = {
     "bnb_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bnb_profile_launches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bnb_debug_pw_tiling": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "bnb_analyze_batch_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "bnb_ultrasonic_cv_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bnb_dense_head_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "bnb_debug_mb2_plan": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "bnb_debug_pw2_tiling": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "bnb_debug_mbconv_geometry": (C.c_int, [C.c_int] * 9 + [C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
@@ -123,6 +127,33 @@ def pw_tiling(M, N, K):
     bn, st, sm = C.c_int(), C.c_int(), C.c_int64()
     _check(lib.bnb_debug_pw_tiling(M, N, K, C.byref(bn), C.byref(st), C.byref(sm)))
     return bn.value, st.value, sm.value
+
+
+def ultrasonic_cv_batch(pcm, sample_rate, fft_size=8192, hop_size=4096, frequency_split_hz=20000, device=-1):
+    """N2: ultrasonic.ComputeUSFrameCV for a batch of chunks on the GPU.  pcm: [B, n] int16 (scaled by 1/32768) or float32.
+    Returns (cv float64 [B], ok bool [B]); ok is False exactly where the reference returns (0, false)."""
+    lib = load_library()
+    pcm = np.ascontiguousarray(pcm)
+    if pcm.ndim == 1:
+        pcm = pcm[None]
+    if pcm.dtype not in (np.int16, np.float32):
+        raise ValueError("pcm must be int16 or float32")
+    B, n = pcm.shape
+    cv = np.zeros(B, np.float64); ok = np.zeros(B, np.int32)
+    _check(lib.bnb_ultrasonic_cv_batch(device, _ptr(pcm), PCM_S16 if pcm.dtype == np.int16 else PCM_F32, B, n, int(sample_rate), int(fft_size),
+                                       int(hop_size), int(frequency_split_hz), _ptr(cv), _ptr(ok)))
+    return cv, ok.astype(bool)
+
+
+def dense_head_batch(embeddings, weights, bias, device=-1):
+    """N2: custom classification head on embeddings: sigmoid(embeddings @ weights.T + bias), float32, on the GPU."""
+    lib = load_library()
+    e = np.ascontiguousarray(embeddings, np.float32); w = np.ascontiguousarray(weights, np.float32); b = np.ascontiguousarray(bias, np.float32)
+    if e.ndim != 2 or w.ndim != 2 or e.shape[1] != w.shape[1] or b.shape != (w.shape[0],):
+        raise ValueError("shapes: embeddings [B, n_in], weights [n_out, n_in], bias [n_out]")
+    out = np.empty((e.shape[0], w.shape[0]), np.float32)
+    _check(lib.bnb_dense_head_batch(device, _ptr(e), e.shape[0], e.shape[1], _ptr(w), _ptr(b), w.shape[0], _ptr(out)))
+    return out
 
 
 def mb2_plan(H, W, Ho, Wo, stride, Cin, C_exp):
@@ -284,6 +315,20 @@ class B200Classifier:
         _check(self._lib.bnb_analyze_batch_submit(self._h, _ptr(pcm), self._fmt(pcm), B, float(sensitivity), k, _ptr(idx), _ptr(conf),
                                                   _ptr(logits) if logits is not None else None, C.byref(t)))
         return _Ticket(self, t.value, pcm, idx, conf, logits)
+
+    def analyze_batch_detections(self, pcm, sensitivity=1.0, threshold=0.1, k=DEFAULT_TOP_K, max_det=None):
+        """N1: sigmoid, threshold and compaction on the device.  Returns (chunk, species_idx, conf, counts): the detections with
+        conf >= threshold among each chunk's top-k, ordered by chunk then by descending confidence; counts[b] per chunk."""
+        pcm = self._check_batch(pcm, k)
+        B = pcm.shape[0]
+        cap = B * k if max_det is None else int(max_det)
+        chunk = np.empty(max(cap, 1), np.int32); idx = np.empty(max(cap, 1), np.int32); conf = np.empty(max(cap, 1), np.float32)
+        counts = np.zeros(max(B, 1), np.int32)
+        n = C.c_int32()
+        _check(self._lib.bnb_analyze_batch_detections(self._h, _ptr(pcm), self._fmt(pcm), B, float(sensitivity), float(threshold), k, cap,
+                                                      _ptr(chunk), _ptr(idx), _ptr(conf), _ptr(counts), C.byref(n)))
+        m = min(n.value, cap)
+        return chunk[:m], idx[:m], conf[:m], counts[:B]
 
     # raw-pointer variants (device memory owned by the caller, e.g. torch tensors' data_ptr())
     def predict_batch_device(self, d_pcm, fmt, B, d_logits, d_emb=0, stream=0):
@@ -465,8 +510,9 @@ class BirdNET:
 
     def analyze_file(self, pcm_int16, overlap_s=0.0, threshold=0.1, batch=None, sample_rate=48000):
         """Batched offline file analysis (BASELINE config 2; doc/wiki/file-analysis.md:1-13): slide a 3 s window with `overlap_s`
-        seconds of overlap over mono int16 PCM, run ALL windows through the batched int16 entry point (device-side /32768,
-        sigmoid(sensitivity * logit), top-10) and keep, per window, the results at or above `threshold`
+        seconds of overlap over mono int16 PCM, run ALL windows through the batched int16 detection entry point (device-side /32768,
+        sigmoid(sensitivity * logit), top-10, threshold and compaction: bnb_analyze_batch_detections) which keeps, per window,
+        the results at or above `threshold`
         (the reference's file mode keeps what passes --threshold).  Returns [(begin_s, end_s, species, confidence)], window order,
         descending confidence inside a window.  The trailing partial window is zero-padded when it holds >= 1.5 s."""
         pcm = np.ascontiguousarray(pcm_int16, np.int16).reshape(-1)
@@ -485,11 +531,11 @@ class BirdNET:
             for j, s0 in enumerate(starts[i:i + B]):
                 seg = pcm[s0:s0 + n]
                 win[j, :len(seg)] = seg
-            idx, conf = self.classifier.analyze_batch(win, self.sensitivity, DEFAULT_TOP_K)
-            for j, s0 in enumerate(starts[i:i + B]):
-                for ii, cc in zip(idx[j], conf[j]):
-                    if cc >= threshold:
-                        out.append((s0 / sample_rate, (s0 + n) / sample_rate, self.labels[ii], float(cc)))
+            # threshold + compaction on the device (N1): only the detections come back, already in window / confidence order
+            ch, sp, cf, _ = self.classifier.analyze_batch_detections(win, self.sensitivity, threshold, DEFAULT_TOP_K)
+            for j, ii, cc in zip(ch, sp, cf):
+                s0 = starts[i + int(j)]
+                out.append((s0 / sample_rate, (s0 + n) / sample_rate, self.labels[ii], float(cc)))
         return out
 
     def close(self):

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)                       # birdnet-go_b200/
 CSRC = os.path.join(ROOT, "csrc")
 LIB = os.path.join(ROOT, "lib", "libbirdnet_b200.so")
 SOURCES = ["capi.cu", "engine.cu", "frontend.cu", "conv_f32.cu", "post.cu", "pw_tc.cu", "mbconv_tc.cu", "mbconv2.cu", "pw2.cu",
-           "tma_host.cu", "debug_api.cu", "range_filter.cu"]
+           "tma_host.cu", "debug_api.cu", "range_filter.cu", "ultrasonic.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -193,6 +193,17 @@ int bnb_analyze_batch_submit(bnb_classifier* h, const void* pcm, int format, int
   return guarded([&] { *ticket = h->eng->submit_host(pcm, format, B, sensitivity, k, idx, conf, logits_or_null, nullptr); });
 }
 
+int bnb_analyze_batch_detections(bnb_classifier* h, const void* pcm, int format, int B, float sensitivity, float threshold, int k,
+                                 int max_det, int32_t* det_chunk, int32_t* det_idx, float* det_conf, int32_t* counts_or_null, int32_t* n_det) {
+  if (int rc = check_batch(h, pcm, format, B)) return rc;
+  if (!n_det || k <= 0 || max_det < 0 || (max_det > 0 && (!det_chunk || !det_idx || !det_conf))) return fail(BNB_ERR_INVALID_ARGUMENT, "NULL output or k <= 0");
+  if (B > h->eng->max_batch()) return fail(BNB_ERR_INVALID_ARGUMENT, "batch exceeds max_batch");
+  *n_det = 0;
+  if (B == 0) return BNB_OK;
+  DeviceRestore dr;
+  return guarded([&] { *n_det = h->eng->detect_host(pcm, format, B, sensitivity, threshold, k, max_det, det_chunk, det_idx, det_conf, counts_or_null); });
+}
+
 int bnb_wait(bnb_classifier* h, int32_t ticket) {
   if (int rc = check_handle(h)) return rc;
   DeviceRestore dr;
@@ -257,6 +268,62 @@ int bnb_debug_mbconv_geometry(int H, int W, int Ho, int Wo, int stride, int Cin,
   for (int i = 0; i < 10; ++i) out10[i] = v[i];
   *smem_bytes = (int64_t)g.smem_bytes;
   return BNB_OK;
+}
+
+// ---- N2: bat pipeline helpers (no classifier handle: they work on raw PCM / embeddings) ------------------------------------
+namespace {
+struct DevMem {
+  void* p = nullptr;
+  explicit DevMem(size_t n) { BNB_CUDA(cudaMalloc(&p, n ? n : 1)); }
+  ~DevMem() { if (p) cudaFree(p); }
+  DevMem(const DevMem&) = delete; DevMem& operator=(const DevMem&) = delete;
+};
+int pick_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return -1; }
+  return device < 0 ? 0 : (device < n ? device : -1);
+}
+}  // namespace
+
+int bnb_ultrasonic_cv_batch(int device, const void* pcm, int format, int B, int n_samples, int sample_rate, int fft_size, int hop_size,
+                            int frequency_split_hz, double* cv, int32_t* ok) {
+  if (!pcm || !cv || !ok || B < 0 || n_samples < 0 || (format != BNB_PCM_F32 && format != BNB_PCM_S16)) return fail(BNB_ERR_INVALID_ARGUMENT, "bad ultrasonic filter arguments");
+  const int frames = ultrasonic_frames(n_samples, sample_rate, fft_size, hop_size, frequency_split_hz);
+  if (frames == 0 || fft_size > 8192) {                       // the reference's (0, false): not an error (filter.go:21-39)
+    for (int b = 0; b < B; ++b) { cv[b] = 0.0; ok[b] = 0; }
+    return frames == 0 ? BNB_OK : fail(BNB_ERR_INVALID_ARGUMENT, "FFT sizes above 8192 are not supported by the GPU filter");
+  }
+  if (B == 0) return BNB_OK;
+  const int dev = pick_device(device);
+  if (dev < 0) return fail(BNB_ERR_NO_DEVICE, "no usable CUDA device");
+  DeviceRestore dr;
+  return guarded([&] {
+    BNB_CUDA(cudaSetDevice(dev));
+    const size_t in_bytes = (size_t)B * n_samples * (format == BNB_PCM_S16 ? 2 : 4);
+    DevMem d_in(in_bytes), ws(ultrasonic_workspace_bytes(B, frames, fft_size));
+    BNB_CUDA(cudaMemcpy(d_in.p, pcm, in_bytes, cudaMemcpyHostToDevice));
+    double* d_cv = reinterpret_cast<double*>(static_cast<char*>(ws.p) + ultrasonic_workspace_bytes(B, frames, fft_size) - (size_t)B * sizeof(double));
+    launch_ultrasonic_cv(d_in.p, format, B, n_samples, sample_rate, fft_size, hop_size, frequency_split_hz, ws.p, d_cv, nullptr);
+    BNB_CUDA(cudaMemcpy(cv, d_cv, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b) ok[b] = 1;
+  });
+}
+
+int bnb_dense_head_batch(int device, const float* embeddings, int B, int n_in, const float* weights, const float* bias, int n_out, float* scores) {
+  if (!embeddings || !weights || !bias || !scores || B < 0 || n_in <= 0 || n_out <= 0) return fail(BNB_ERR_INVALID_ARGUMENT, "bad dense head arguments");
+  if (B == 0) return BNB_OK;
+  const int dev = pick_device(device);
+  if (dev < 0) return fail(BNB_ERR_NO_DEVICE, "no usable CUDA device");
+  DeviceRestore dr;
+  return guarded([&] {
+    BNB_CUDA(cudaSetDevice(dev));
+    DevMem d_e((size_t)B * n_in * 4), d_w((size_t)n_out * n_in * 4), d_b((size_t)n_out * 4), d_o((size_t)B * n_out * 4);
+    BNB_CUDA(cudaMemcpy(d_e.p, embeddings, (size_t)B * n_in * 4, cudaMemcpyHostToDevice));
+    BNB_CUDA(cudaMemcpy(d_w.p, weights, (size_t)n_out * n_in * 4, cudaMemcpyHostToDevice));
+    BNB_CUDA(cudaMemcpy(d_b.p, bias, (size_t)n_out * 4, cudaMemcpyHostToDevice));
+    launch_dense_head(static_cast<float*>(d_e.p), static_cast<float*>(d_w.p), static_cast<float*>(d_b.p), B, n_in, n_out, static_cast<float*>(d_o.p), nullptr);
+    BNB_CUDA(cudaMemcpy(scores, d_o.p, (size_t)B * n_out * 4, cudaMemcpyDeviceToHost));
+  });
 }
 
 int bnb_debug_mb2_plan(int H, int W, int Ho, int Wo, int stride, int Cin, int C, int* out12, int64_t* smem_bytes) {

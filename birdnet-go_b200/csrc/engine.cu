@@ -136,6 +136,8 @@ void Engine::release() noexcept {
     if (S.start) cudaEventDestroy(S.start);
     if (S.done) cudaEventDestroy(S.done);
   }
+  if (d_det_) cudaFree(d_det_);
+  if (h_det_) cudaFreeHost(h_det_);
   for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second.exec);
   for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
   if (compute_) cudaStreamDestroy(compute_);
@@ -745,7 +747,7 @@ int Engine::submit_host(const void* pcm, int fmt, int B, float sensitivity, int 
     if (k > 0) { ProfScope ps(this, C_TOPK, compute_); launch_sigmoid_topk(S.d_logits, B, n_species_, sensitivity, k, S.d_idx, S.d_conf, compute_, lc_); }
   }
   // results -> pinned staging (asynchronous); wait_host hands them to the caller's buffers
-  if (k > 0) {
+  if (k > 0 && idx != nullptr) {                                      // idx == nullptr: the top-k stays on the device (detect_host)
     BNB_CUDA(cudaMemcpyAsync(S.h_out + S.off_idx, S.d_idx, (size_t)B * k * 4, cudaMemcpyDeviceToHost, compute_));
     BNB_CUDA(cudaMemcpyAsync(S.h_out + S.off_conf, S.d_conf, (size_t)B * k * 4, cudaMemcpyDeviceToHost, compute_));
   }
@@ -766,9 +768,43 @@ void Engine::wait_host(int ticket) {
   S->busy = false;
   BNB_CUDA(cudaEventElapsedTime(&last_ms_, S->start, S->done));
   const size_t B = (size_t)S->B, k = (size_t)S->k;
-  if (S->k > 0) { memcpy(S->u_idx, S->h_out + S->off_idx, B * k * 4); memcpy(S->u_conf, S->h_out + S->off_conf, B * k * 4); }
+  if (S->k > 0 && S->u_idx) { memcpy(S->u_idx, S->h_out + S->off_idx, B * k * 4); memcpy(S->u_conf, S->h_out + S->off_conf, B * k * 4); }
   if (S->u_logits) memcpy(S->u_logits, S->h_out, B * n_species_ * 4);
   if (S->u_emb) memcpy(S->u_emb, S->h_out + S->off_emb, B * emb_dim_ * 4);
+}
+
+int Engine::detect_host(const void* pcm, int fmt, int B, float sensitivity, float threshold, int k, int max_det, int32_t* det_chunk,
+                        int32_t* det_idx, float* det_conf, int32_t* counts) {
+  BNB_CUDA(cudaSetDevice(device_));
+  if (k <= 0 || k > topk_cap_) throw std::invalid_argument("k must be in 1..64");
+  const size_t cap = (size_t)max_batch_ * topk_cap_;
+  if (!d_det_) {                                   // [3][cap] (chunk, idx, conf bits) + counts[max_batch] + length
+    const size_t bytes = (3 * cap + (size_t)max_batch_ + 1) * sizeof(int32_t);
+    BNB_CUDA(cudaMalloc(&d_det_, bytes));
+    BNB_CUDA(cudaMallocHost(&h_det_, bytes));
+    det_cap_ = cap;
+  }
+  const int list_cap = (int)std::min<size_t>(cap, (size_t)std::max(0, max_det));
+  const int si = next_slot_;
+  const int ticket = submit_host(pcm, fmt, B, sensitivity, k, nullptr, nullptr, nullptr, nullptr);    // chain + sigmoid/top-k, results stay on the device
+  Slot& S = slots_[si];
+  int32_t* d_chunk = d_det_; int32_t* d_idx = d_det_ + cap; float* d_conf = reinterpret_cast<float*>(d_det_ + 2 * cap);
+  int32_t* d_counts = d_det_ + 3 * cap; int32_t* d_n = d_counts + max_batch_;
+  launch_compact_detections(S.d_idx, S.d_conf, B, k, threshold, list_cap, d_chunk, d_idx, d_conf, d_counts, d_n, compute_, lc_);
+  int32_t* h_counts = h_det_ + 3 * cap; int32_t* h_n = h_counts + max_batch_;
+  BNB_CUDA(cudaMemcpyAsync(h_counts, d_counts, ((size_t)max_batch_ + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, compute_));
+  BNB_CUDA(cudaStreamSynchronize(compute_));
+  wait_host(ticket);
+  const int found = *h_n, n = std::min(found, list_cap);
+  if (n > 0) {                                      // only the detections cross PCIe: 12 B each
+    BNB_CUDA(cudaMemcpyAsync(h_det_, d_chunk, (size_t)n * 4, cudaMemcpyDeviceToHost, compute_));
+    BNB_CUDA(cudaMemcpyAsync(h_det_ + cap, d_idx, (size_t)n * 4, cudaMemcpyDeviceToHost, compute_));
+    BNB_CUDA(cudaMemcpyAsync(h_det_ + 2 * cap, d_conf, (size_t)n * 4, cudaMemcpyDeviceToHost, compute_));
+    BNB_CUDA(cudaStreamSynchronize(compute_));
+    memcpy(det_chunk, h_det_, (size_t)n * 4); memcpy(det_idx, h_det_ + cap, (size_t)n * 4); memcpy(det_conf, h_det_ + 2 * cap, (size_t)n * 4);
+  }
+  if (counts) memcpy(counts, h_counts, (size_t)B * 4);
+  return found;
 }
 
 // ------------------------------------------------------------------------------------------------

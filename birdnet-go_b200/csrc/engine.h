@@ -70,6 +70,11 @@ class Engine {
   // tickets may be outstanding.  k == 0 -> no top-k; logits / emb may be null.
   int submit_host(const void* pcm, int fmt, int B, float sensitivity, int k, int32_t* idx, float* conf, float* logits, float* emb);
   void wait_host(int ticket);
+  // N1: the same path, but sigma >= threshold and the compaction of the per-chunk top-k into ONE detection list run on the
+  // device; only counts[B], the list length and the list itself cross PCIe (returns the number of detections found, which may
+  // exceed max_det: the list is then truncated, counts[] is not)
+  int detect_host(const void* pcm, int fmt, int B, float sensitivity, float threshold, int k, int max_det, int32_t* det_chunk,
+                  int32_t* det_idx, float* det_conf, int32_t* counts);
 
   void keep_intermediates(bool on) { keep_ = on; }
   // per-category device timing (CUDA events around every launch); see bnb_profile_* in the C ABI
@@ -177,6 +182,8 @@ class Engine {
   cudaEvent_t ev_small_ = nullptr;                       // end of the last single-stream (small batch) chain: lane streams order after it
   float* ws_mid_base_ = nullptr; uint8_t* mid2_base_ = nullptr;
   int topk_cap_ = 0;
+  // detection compaction buffers (device + pinned host), allocated on first use: [max_batch * topk_cap] triples, counts, length
+  int32_t* d_det_ = nullptr; int32_t* h_det_ = nullptr; size_t det_cap_ = 0;
   cudaStream_t compute_ = nullptr, copy_ = nullptr;
 
 };

@@ -110,5 +110,14 @@ void launch_row_mean2(const float* in, float* out, uint8_t* o_img, int B, int ro
 // conf = sigmoid(sensitivity * logit) (float64 exp like analyze.go:113-115), top-k descending, ties -> lower index
 void launch_sigmoid_topk(const float* logits, int B, int n, float sensitivity, int k, int32_t* idx, float* conf,
                          cudaStream_t s, LaunchCounter& lc);
+// N1: detections >= threshold of the sorted per-chunk top-k, compacted over the batch (chunk order, then confidence order)
+void launch_compact_detections(const int32_t* idx, const float* conf, int B, int k, float threshold, int max_det, int32_t* det_chunk,
+                               int32_t* det_idx, float* det_conf, int32_t* counts, int32_t* n_det, cudaStream_t s, LaunchCounter& lc);
+// N2: dense + sigmoid head on embeddings (bat pipeline), and the ultrasonic frame-power CV filter (ultrasonic.cu)
+void launch_dense_head(const float* emb, const float* w, const float* bias, int B, int n_in, int n_out, float* out, cudaStream_t s);
+int ultrasonic_frames(int n_samples, int sample_rate, int fft, int hop, int split_hz);
+size_t ultrasonic_workspace_bytes(int B, int n_frames, int fft);
+void launch_ultrasonic_cv(const void* d_pcm, int fmt, int B, int n_samples, int sample_rate, int fft, int hop, int split_hz,
+                          void* workspace, double* d_cv, cudaStream_t s);
 
 }  // namespace bnb

@@ -5,14 +5,16 @@
 // Replaces the CONV_2D 1x1 / FULLY_CONNECTED ops the reference executes inside TFLite-XNNPACK
 // (/root/reference/internal/inference/tflite/classifier.go:107).
 //
-// Round-2 design (against pw_tc.cu, VERDICT r1 "weak" #4): the A operand arrives as fp16 hi and lo PLANES written by
-// the producing kernel, so an A tile goes  TMA (2-D box, 128-byte hardware swizzle) -> shared memory -> tcgen05.mma
-// directly: no converter warps, no in-place overwrite, no bar.sync between the load and the MMA.  Three MMAs per
-// K-step keep the fp32-level accuracy:  D += Ahi*Bhi + Alo*Bhi + Ahi*Blo.
-// Layers with a squeeze-excite gate on A still pass through 8 converter warps, but those now rewrite each 16-byte chunk
-// in place thread-privately (hi+lo -> *gate -> hi/lo), with no barrier among them.
-// The epilogue adds bias (+ residual read as planes), and writes either fp32 (post conv, logits) or hi/lo planes (the next
-// block's input) in 64-byte coalesced row segments through a swizzled shared-memory transpose.
+// Round-2 design (against pw_tc.cu, VERDICT r1 "weak" #4; measurements in profiles/r02_*): the A operand arrives as a RowTiles
+// image (layouts.h) — fp16 hi and lo planes already in this kernel's swizzled shared-memory order, written by the producing
+// kernel — so an (m-tile, K stage) block is ONE 32 KB cp.async.bulk and goes straight into tcgen05.mma: no fp32 -> fp16
+// converter, no bar.sync between the load and the MMA.  Three MMAs per K-step keep the fp32-level accuracy:
+// D += Ahi*Bhi + Alo*Bhi + Ahi*Blo.  Layers with a squeeze-excite gate on A pass through 8 converter warps that rewrite each
+// 16-byte piece in place thread-privately (hi+lo -> *gate -> hi/lo), with no barrier among them.  Weights stay resident in
+// shared memory whenever a 3-deep A ring still fits (all front-phase layers).  One elected lane issues MMAs / copies
+// (tc_common.cuh: elect_one).  The 16 epilogue warps add bias (+ residual, read from the block input's PatchTiles image) and
+// write 16-byte pieces STRAIGHT from registers: into the next block's PatchTiles image (a pixel goes to every tile whose halo
+// holds it: per-pixel lookup table), into plain planes, or as fp32 (post conv, logits).
 #include "pw2.h"
 
 #include <stdio.h>
@@ -44,6 +46,7 @@ struct Pw2Args {
   int o_pitch, out_mode;                  // out_mode: 0 fp32, 1 plain planes, 2 PatchTiles image
   uint32_t a_tile_bytes;
   int n_pad, k_pad, n_tiles, bn, stages, b_res, conv, out_vec;
+  int a_ldgsts;                           // A stage blocks fetched by the loader warp's 32 lanes with cp.async (16 B each) instead of one bulk copy
   int n_acc;                              // independent accumulators per tile (column ranges of bn): MMA i goes to accumulator i % n_acc
   PatchTiles rp, op;                      // residual / output patch layouts
   long long* trace;                       // debug timeline (BNB_PW2_TRACE): [2 CTAs][8 events][64 slots] clock64 stamps, else null
@@ -77,7 +80,7 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + (bars - base) + 8u * (3 * a.stages + 5));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) { mbar_init(tma_bar(s), 1); mbar_init(full_bar(s), kConvThreads); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(tma_bar(s), a.a_ldgsts ? 33 : 1); mbar_init(full_bar(s), kConvThreads); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps * 32); }
     mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -101,69 +104,58 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
   if (warp != kLoadWarp) pdl_wait();
 
   if (warp >= kConvWarp0) {
-    // ============================== converters (gate layers): A <- split((hi + lo) * gate) =================================
-    // The converter threads fetch their pieces of the (m-tile, stage) block STRAIGHT from the RowTiles image with 16-byte
-    // loads (the image is in shared-memory order: same offset on both sides), scale, re-split and store them to the stage slot.
-    // Why not a bulk copy + in-place conversion (the first r02 version): one SM's bulk-copy path delivered ~13 B/clk (three
-    // 32 KB stage copies issued together landed 2.5 k cycles apart, profiles/r02 timelines) and that was the stage period of
-    // every gated layer; 256 threads x 8 loads in flight go through the LSU path instead and the in-place read disappears.
+    // ============================== converters (gate layers): A <- split((hi + lo) * gate), in place, thread-private ===
+    // (Fetching the pieces with LDG straight from the image instead of bulk copy + in-place rewrite was tried in r02: the stage
+    // period stayed ~2.4 k cycles — one SM pulls ~13 B/clk from L2 whichever path asks — and the layers whose m-tiles span
+    // several chunks got slower: profiles/r02 notes.)
     if (a.conv) {
       const int pt = threadIdx.x - kConvWarp0 * 32;
       const int c = pt & 7, r0 = pt >> 3;
-      const bool one_gate = (a.rows_per_chunk % kBM) == 0;            // an m-tile lies inside one chunk (front-phase maps)
-      uint32_t it = 0, ph = 0; int s = 0;
-      uint32_t offs[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) offs[q] = swz_off((uint32_t)(r0 + 32 * q), (uint32_t)c, 128u);
+      uint32_t it = 0;
       for (int mt = mt_first; mt < m_tiles; mt += mt_step) {
         const int m0 = mt * kBM;
-        const uint8_t* tile = a.a_img + (size_t)mt * a.a_tile_bytes;
         for (int ks = 0; ks < k_stages; ++ks, ++it) {
-          const int k = ks * kBK + c * 8;
-          const bool live = k < a.K;                                  // K % 8 == 0 for every gated layer (checked at launch)
-          uint4 h[4], l[4];
-          if (live) {
-            const uint8_t* src = tile + (size_t)ks * (2 * kABytes);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {                             // coherent loads: the image was written by the previous kernel (PDL)
-              h[q] = __ldcg(reinterpret_cast<const uint4*>(src + offs[q]));
-              l[q] = __ldcg(reinterpret_cast<const uint4*>(src + kABytes + offs[q]));
-            }
-          }
-          float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), gb = ga;
-          if (live && one_gate && m0 < a.M) {
-            const float* gp = a.gate + (size_t)(m0 / a.rows_per_chunk) * a.K + k;
-            ga = __ldcg(reinterpret_cast<const float4*>(gp)); gb = __ldcg(reinterpret_cast<const float4*>(gp + 4));
-          }
-          mbar_wait_relaxed(empty_bar(s), ph ^ 1);                    // the MMAs that read this slot last have completed
+          const int s = it % a.stages; const uint32_t ph = (it / a.stages) & 1;
           uint8_t* hi_p = base_ptr + (size_t)s * stage_bytes;
           uint8_t* lo_p = hi_p + kABytes;
-          if (pt == 0) PW2_TRACE(2, it);
+          const int k = ks * kBK + c * 8;
+          const bool live = k < a.K;                                  // K % 8 == 0 for every gated layer (checked at launch)
+          float4 g0[4], g1[4];
+          if (live) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 ho = make_uint4(0, 0, 0, 0), lo = ho;               // channels past K: exact zeros (the slot may hold anything)
-            if (live) {
-              if (!one_gate) {
-                const int m = m0 + r0 + 32 * q;
-                ga = make_float4(1.f, 1.f, 1.f, 1.f); gb = ga;
-                if (m < a.M) {
-                  const float* gp = a.gate + (size_t)(m / a.rows_per_chunk) * a.K + k;
-                  ga = __ldcg(reinterpret_cast<const float4*>(gp)); gb = __ldcg(reinterpret_cast<const float4*>(gp + 4));
-                }
+            for (int q = 0; q < 4; ++q) {
+              const int m = m0 + r0 + 32 * q;
+              g0[q] = make_float4(1.f, 1.f, 1.f, 1.f); g1[q] = g0[q];
+              if (m < a.M) {
+                const float* gp = a.gate + (size_t)(m / a.rows_per_chunk) * a.K + k;
+                g0[q] = __ldcg(reinterpret_cast<const float4*>(gp));          // written by the previous kernel: coherent load (PDL, common.cuh)
+                g1[q] = __ldcg(reinterpret_cast<const float4*>(gp + 4));
               }
-              float2 v0 = join2(h[q].x, l[q].x), v1 = join2(h[q].y, l[q].y), v2 = join2(h[q].z, l[q].z), v3 = join2(h[q].w, l[q].w);
-              v0.x *= ga.x; v0.y *= ga.y; v1.x *= ga.z; v1.y *= ga.w;
-              v2.x *= gb.x; v2.y *= gb.y; v3.x *= gb.z; v3.y *= gb.w;
+            }
+          }
+          mbar_wait_relaxed(tma_bar(s), ph);
+          if (pt == 0) PW2_TRACE(2, it);
+          if (live) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int r = r0 + 32 * q;
+              if (m0 + r >= a.M) continue;                            // rows past M arrived as zeros
+              const uint32_t off = swz_off((uint32_t)r, (uint32_t)c, 128u);
+              const uint4 h = *reinterpret_cast<const uint4*>(hi_p + off);
+              const uint4 l = *reinterpret_cast<const uint4*>(lo_p + off);
+              float2 v0 = join2(h.x, l.x), v1 = join2(h.y, l.y), v2 = join2(h.z, l.z), v3 = join2(h.w, l.w);
+              v0.x *= g0[q].x; v0.y *= g0[q].y; v1.x *= g0[q].z; v1.y *= g0[q].w;
+              v2.x *= g1[q].x; v2.y *= g1[q].y; v3.x *= g1[q].z; v3.y *= g1[q].w;
+              uint4 ho, lo;
               split2(v0.x, v0.y, ho.x, lo.x); split2(v1.x, v1.y, ho.y, lo.y);
               split2(v2.x, v2.y, ho.z, lo.z); split2(v3.x, v3.y, ho.w, lo.w);
+              *reinterpret_cast<uint4*>(hi_p + off) = ho;
+              *reinterpret_cast<uint4*>(lo_p + off) = lo;
             }
-            *reinterpret_cast<uint4*>(hi_p + offs[q]) = ho;
-            *reinterpret_cast<uint4*>(lo_p + offs[q]) = lo;
           }
           fence_proxy_async();
           mbar_arrive(full_bar(s));
           if (pt == 0) PW2_TRACE(3, it);
-          if (++s == a.stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -189,11 +181,17 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
         mbar_wait_relaxed(empty_bar(s), ph ^ 1);
         const uint32_t dst = base + (uint32_t)s * stage_bytes;
-        if (elect_one() && !(a.conv && a.b_res)) {                  // gated layer with resident weights: nothing to copy per stage
-          mbar_arrive_expect_tx(tma_bar(s), (a.conv ? 0u : 2 * kABytes) + (a.b_res ? 0u : 2 * bn_bytes));
-          // the (m-tile, stage) A operand, hi | lo, is one contiguous 32 KB block of the RowTiles image (gated layers: the
-          // converter warps fetch it themselves)
-          if (!a.conv) bulk_g2s(dst, a.a_img + (size_t)mt * a.a_tile_bytes + (size_t)ks * (2 * kABytes), 2 * kABytes, tma_bar(s));
+        // the (m-tile, stage) A operand, hi | lo, is one contiguous 32 KB block of the RowTiles image
+        const uint8_t* asrc = a.a_img + (size_t)mt * a.a_tile_bytes + (size_t)ks * (2 * kABytes);
+        if (a.a_ldgsts) {
+          // BNB_PW2_LDGSTS=1 (experiment, see launch_pw2): 2048 x 16 B through the LSU path, 64 per lane
+#pragma unroll 8
+          for (int i = lane; i < 2 * kABytes / 16; i += 32) cp_async16(dst + 16u * (uint32_t)i, asrc + 16 * i);
+          cp_async_mbar_arrive(tma_bar(s));
+        }
+        if (elect_one()) {
+          mbar_arrive_expect_tx(tma_bar(s), (a.a_ldgsts ? 0u : 2 * kABytes) + (a.b_res ? 0u : 2 * bn_bytes));
+          if (!a.a_ldgsts) bulk_g2s(dst, asrc, 2 * kABytes, tma_bar(s));
           PW2_TRACE(1, it);
           if (!a.b_res) {
             const uint8_t* wsrc = a.Wimg + ((size_t)ks * 2) * (size_t)a.n_pad * 128 + (size_t)n0 * 128;
@@ -224,8 +222,8 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * kAccCols;
         uint32_t acc = 0, started = 0;                     // next accumulator; how many accumulators have received their first product
         for (int ks = 0; ks < k_stages; ++ks, ++it) {
-          if (a.conv) { mbar_wait(full_bar(s), ph); if (!a.b_res) mbar_wait(tma_bar(s), ph); }   // converted A (+ streamed weights)
-          else mbar_wait(tma_bar(s), ph);
+          mbar_wait(a.conv ? full_bar(s) : tma_bar(s), ph);
+          if (a.a_ldgsts && !a.conv) fence_proxy_async();     // cp.async wrote through the generic proxy; the MMA reads through the async one
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint64_t d_ahi = make_desc(sa), d_alo = make_desc(sa + kABytes);
@@ -458,6 +456,9 @@ void launch_pw2(const PwTcLayer& L, const Pw2Launch& p, cudaStream_t s, LaunchCo
   a.rp = p.r_patch; a.op = p.o_patch;
   a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.bn = bn; a.n_tiles = (L.n_pad + bn - 1) / bn; a.stages = stages; a.b_res = b_res;
   a.conv = p.gate != nullptr ? 1 : 0;
+  // experiment knob: A stage blocks by 2048 per-thread cp.async instead of one bulk copy.  Measured (r02 run k16): the blocks
+  // still land ~2.5 k cycles apart and the step is 1 % slower, so one SM ingests ~13 B/clk whichever engine asks: default off.
+  { static const int ld = getenv("BNB_PW2_LDGSTS") ? atoi(getenv("BNB_PW2_LDGSTS")) : 0; a.a_ldgsts = ld; }
   // one accumulator by default; BNB_PW2_NACC=2|3 deals the products to independent accumulators (experiment knob: no gain measured)
   a.n_acc = 1;
   { static const int forced = getenv("BNB_PW2_NACC") ? atoi(getenv("BNB_PW2_NACC")) : 0;

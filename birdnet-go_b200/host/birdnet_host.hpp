@@ -95,6 +95,17 @@ class B200Classifier final : public EmbeddingExtractor {
     idx->assign((size_t)B * k, 0); conf->assign((size_t)B * k, 0.f);
     check(bnb_analyze_batch(h_, pcm, format, B, sensitivity, k, idx->data(), conf->data(), nullptr), "analyze_batch");
   }
+  // N1: threshold + compaction on the device; chunk / species index / confidence triples in chunk-then-confidence order
+  int AnalyzeBatchDetections(const void* pcm, int format, int B, float sensitivity, float threshold, int k, std::vector<int32_t>* chunk,
+                             std::vector<int32_t>* idx, std::vector<float>* conf) {
+    check_open();
+    const size_t cap = (size_t)B * k;
+    chunk->assign(cap, 0); idx->assign(cap, 0); conf->assign(cap, 0.f);
+    int32_t n = 0;
+    check(bnb_analyze_batch_detections(h_, pcm, format, B, sensitivity, threshold, k, (int)cap, chunk->data(), idx->data(), conf->data(), nullptr, &n), "analyze_batch_detections");
+    chunk->resize((size_t)n); idx->resize((size_t)n); conf->resize((size_t)n);
+    return n;
+  }
   int NumSpecies() const override { return numSpecies_; }
   int NumSamples() const { return numSamples_; }
   int EmbeddingDim() const { return embDim_; }
@@ -254,7 +265,7 @@ inline std::vector<Detection> AnalyzeFileBatched(inference::B200Classifier& clf,
   if (nSamples > tail && nSamples - tail >= n / 2) starts.push_back(tail);
   std::vector<Detection> out;
   std::vector<int16_t> win;
-  std::vector<int32_t> idx; std::vector<float> conf;
+  std::vector<int32_t> chunk, idx; std::vector<float> conf;
   for (size_t i = 0; i < starts.size(); i += (size_t)maxBatch) {
     const int B = (int)std::min((size_t)maxBatch, starts.size() - i);
     win.assign((size_t)B * n, 0);
@@ -262,16 +273,13 @@ inline std::vector<Detection> AnalyzeFileBatched(inference::B200Classifier& clf,
       const size_t s0 = starts[i + j], len = std::min(n, nSamples - s0);
       std::memcpy(&win[(size_t)j * n], pcm + s0, len * sizeof(int16_t));
     }
-    clf.AnalyzeBatch(win.data(), BNB_PCM_S16, B, (float)sensitivity, defaultTopKResults, &idx, &conf);
-    for (int j = 0; j < B; ++j)
-      for (int r = 0; r < defaultTopKResults; ++r) {
-        const float c = conf[(size_t)j * defaultTopKResults + r];
-        if (c >= (float)threshold) {
-          Detection d; d.Begin = (double)starts[i + j] / sampleRate; d.End = d.Begin + (double)n / sampleRate;
-          d.Species = labels[(size_t)idx[(size_t)j * defaultTopKResults + r]]; d.Confidence = c;
-          out.push_back(d);
-        }
-      }
+    // sigmoid, top-10, threshold and compaction all on the device: only the detections come back (window, then confidence order)
+    const int found = clf.AnalyzeBatchDetections(win.data(), BNB_PCM_S16, B, (float)sensitivity, (float)threshold, defaultTopKResults, &chunk, &idx, &conf);
+    for (int r = 0; r < found; ++r) {
+      Detection d; d.Begin = (double)starts[i + (size_t)chunk[(size_t)r]] / sampleRate; d.End = d.Begin + (double)n / sampleRate;
+      d.Species = labels[(size_t)idx[(size_t)r]]; d.Confidence = conf[(size_t)r];
+      out.push_back(d);
+    }
   }
   return out;
 }

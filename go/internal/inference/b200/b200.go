@@ -65,7 +65,7 @@ type TopK struct {
 }
 
 // Detections is the thresholded form of one chunk: every label whose confidence is >= the
-// threshold, in descending confidence (at most the k passed to AnalyzeThreshold).
+// threshold, in descending confidence (at most the k passed to DetectBatchInt16).
 type Detections struct {
 	Index      []int32
 	Confidence []float32

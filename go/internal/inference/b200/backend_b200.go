@@ -215,6 +215,69 @@ func (c *Classifier) AnalyzeBatchInt16(pcm []int16, batchSize int, sensitivity f
 	return c.analyze(unsafe.Pointer(&pcm[0]), C.BNB_PCM_S16, batchSize, sensitivity, k)
 }
 
+// DetectBatchInt16 runs sigmoid(sensitivity*logit), the top-k, the confidence threshold and the
+// compaction of the survivors on the device (SURVEY 8(f) N1); only the detections cross PCIe.
+// The result holds one Detections per chunk (possibly empty), in descending confidence —
+// what processor.go:820-876 keeps of BirdNET.Predict's ten Results.
+func (c *Classifier) DetectBatchInt16(pcm []int16, batchSize int, sensitivity, threshold float32, k int) ([]Detections, error) {
+	if c == nil || c.h == nil {
+		return nil, ErrClosed
+	}
+	if batchSize <= 0 || batchSize > c.maxBatch || len(pcm) != batchSize*c.numSamples {
+		return nil, sizeMismatch(batchSize*c.numSamples, len(pcm))
+	}
+	if k <= 0 {
+		return nil, errors.Newf("k must be positive, got %d", k).Component("inference.b200").Category(errors.CategoryValidation).Build()
+	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	capacity := batchSize * k
+	chunk := make([]int32, capacity)
+	idx := make([]int32, capacity)
+	conf := make([]float32, capacity)
+	counts := make([]int32, batchSize)
+	var found C.int32_t
+	rc := C.bnb_analyze_batch_detections(c.h, unsafe.Pointer(&pcm[0]), C.BNB_PCM_S16, C.int(batchSize), C.float(sensitivity), C.float(threshold),
+		C.int(k), C.int(capacity), (*C.int32_t)(unsafe.Pointer(&chunk[0])), (*C.int32_t)(unsafe.Pointer(&idx[0])),
+		(*C.float)(unsafe.Pointer(&conf[0])), (*C.int32_t)(unsafe.Pointer(&counts[0])), &found)
+	if rc != C.BNB_OK {
+		return nil, lastErr("analyze_batch_detections", rc)
+	}
+	out := make([]Detections, batchSize)
+	pos := 0
+	for b := range out {
+		n := int(counts[b])
+		out[b] = Detections{Index: idx[pos : pos+n : pos+n], Confidence: conf[pos : pos+n : pos+n]}
+		pos += n
+	}
+	return out, nil
+}
+
+// UltrasonicFrameCV is ultrasonic.ComputeUSFrameCV (internal/audiocore/ultrasonic/filter.go:20-66)
+// for a batch of int16 chunks at the SOURCE rate, computed in float64 on the device.
+// ok[b] is false exactly where the reference returns (0, false).
+func UltrasonicFrameCV(device int, pcm []int16, batchSize, sampleRate, fftSize, hopSize, frequencySplitHz int) (cv []float64, ok []bool, err error) {
+	if batchSize <= 0 || len(pcm)%batchSize != 0 {
+		return nil, nil, errors.Newf("pcm length %d is not a multiple of the batch size %d", len(pcm), batchSize).
+			Component("inference.b200").Category(errors.CategoryValidation).Build()
+	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	cv = make([]float64, batchSize)
+	flags := make([]int32, batchSize)
+	rc := C.bnb_ultrasonic_cv_batch(C.int(device), unsafe.Pointer(&pcm[0]), C.BNB_PCM_S16, C.int(batchSize), C.int(len(pcm)/batchSize),
+		C.int(sampleRate), C.int(fftSize), C.int(hopSize), C.int(frequencySplitHz), (*C.double)(unsafe.Pointer(&cv[0])),
+		(*C.int32_t)(unsafe.Pointer(&flags[0])))
+	if rc != C.BNB_OK {
+		return nil, nil, lastErr("ultrasonic_cv_batch", rc)
+	}
+	ok = make([]bool, batchSize)
+	for i, f := range flags {
+		ok[i] = f != 0
+	}
+	return cv, ok, nil
+}
+
 // NumSpecies implements inference.Classifier (6522, read from the model).
 func (c *Classifier) NumSpecies() int { return c.numSpecies }
 

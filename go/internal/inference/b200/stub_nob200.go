@@ -44,6 +44,16 @@ func (c *Classifier) AnalyzeBatch(_ []float32, _ int, _ float32, _ int) ([]TopK,
 	return nil, ErrB200Unavailable
 }
 
+// DetectBatchInt16 always fails without the b200 build tag.
+func (c *Classifier) DetectBatchInt16(_ []int16, _ int, _, _ float32, _ int) ([]Detections, error) {
+	return nil, ErrB200Unavailable
+}
+
+// UltrasonicFrameCV always fails without the b200 build tag (callers keep using ultrasonic.ComputeUSFrameCV).
+func UltrasonicFrameCV(_ int, _ []int16, _, _, _, _, _ int) ([]float64, []bool, error) {
+	return nil, nil, ErrB200Unavailable
+}
+
 // NumSpecies reports 0 without the b200 build tag.
 func (c *Classifier) NumSpecies() int { return 0 }
 

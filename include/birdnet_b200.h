@@ -133,6 +133,27 @@ BNB_API int bnb_analyze_batch_submit(bnb_classifier* h, const void* pcm, int for
                                      int32_t* idx, float* conf, float* logits_or_null, int32_t* ticket);
 BNB_API int bnb_wait(bnb_classifier* h, int32_t ticket);
 
+/* sigma(sensitivity * x) >= threshold and the compaction of the per-chunk top-k run on the device; only the
+ * detections cross PCIe.  The list is ordered by chunk, then by descending confidence (what the reference's loop over a chunk's
+ * Results produces: internal/analysis/processor/processor.go:820-876 with analyze.go:82-99 before it).  det_* hold up to max_det
+ * entries; *n_det is the number FOUND (> max_det means the list was truncated); counts_or_null[b] = detections of chunk b.
+ * Same input contract as bnb_analyze_batch. */
+BNB_API int bnb_analyze_batch_detections(bnb_classifier* h, const void* pcm, int format, int B, float sensitivity, float threshold, int k,
+                                         int max_det, int32_t* det_chunk, int32_t* det_idx, float* det_conf, int32_t* counts_or_null,
+                                         int32_t* n_det);
+
+/* SURVEY 8(f) N2, bat pipeline.  bnb_ultrasonic_cv_batch = ultrasonic.ComputeUSFrameCV
+ * (internal/audiocore/ultrasonic/filter.go:20-66) for B chunks of n_samples PCM samples at the SOURCE rate (int16 scaled by
+ * 1/32768 like convert.BytesToFloat64PCM16, or float32): float64 STFT (fft_size <= 8192, power of two), energy above
+ * frequency_split_hz per frame, cv[b] = std / mean of the frame powers; ok[b] = 0 (and cv[b] = 0) exactly where the reference
+ * returns (0, false).  bnb_dense_head_batch = the custom classification head on embeddings
+ * (internal/inference/onnx/custom_classifier.go:147-173): scores[b][c] = sigmoid(bias[c] + <embeddings[b], weights[c]>).
+ * device < 0 selects device 0.  Both are stateless convenience entry points (they allocate and free their device buffers). */
+BNB_API int bnb_ultrasonic_cv_batch(int device, const void* pcm, int format, int B, int n_samples, int sample_rate, int fft_size,
+                                    int hop_size, int frequency_split_hz, double* cv, int32_t* ok);
+BNB_API int bnb_dense_head_batch(int device, const float* embeddings, int B, int n_in, const float* weights, const float* bias,
+                                 int n_out, float* scores);
+
 /* ---- device-buffer entry points (batched offline driver, bench, multi-GPU harness) ----------- */
 
 /* Same computation with inputs/outputs already resident in device memory of the handle's device;

@@ -123,3 +123,30 @@ def test_fused_block_geometry_covers_every_block(lib_path):
             assert g["k_stages"] == (cin + 63) // 64 and g["a_slots"] >= g["k_stages"]
             if b["se"]:
                 assert g["tiles_h"] * g["tiles_w"] <= 32
+
+
+def test_f16x3_plans_cover_every_block(lib_path):
+    """Round-2 kernels (mbconv2.cu / pw2.cu): every block has a plan; a pair of halo patches fits one MMA (2 * n_mma <= 256
+    TMEM columns, n_mma % 16 == 0), the accumulators fit the 512 TMEM columns at least twice, tiles cover the output exactly,
+    shared memory <= 227 KB; the 288 -> 72 project GEMMs keep their weights resident with a 3-deep A ring (the r02 fix)."""
+    d = json.loads(bb.describe_model(open(bb.DEFAULT_MODEL, "rb").read()))
+    for i, b in enumerate(d["blocks"]):
+        hin, win, cin = b["in"]; ho, wo, co = b["out"]
+        p = bb.mb2_plan(hin, win, ho, wo, b["stride"], cin, b["cexp"])
+        assert p["ok"] == 1, (i, p)
+        assert p["ph"] == (p["th"] - 1) * b["stride"] + 3 and p["pw"] == (p["tw"] - 1) * b["stride"] + 3
+        assert p["ph"] * p["pw"] <= p["n_mma"] <= 128 and p["n_mma"] % 16 == 0
+        assert ho % p["th"] == 0 and wo % p["tw"] == 0
+        assert p["units"] == (b["cexp"] + 127) // 128 and p["k_stages"] >= 1
+        assert p["pair_slots"] >= 1 and p["smem_bytes"] <= 227 * 1024, (i, p)
+        assert p["pair_bytes"] % 1024 == 0                                   # swizzle atoms of the second tile stay aligned
+        for chunks in (1, 64, 128, 256, 1024):
+            bn, stages, b_res, n_tiles, smem = bb.pw2_tiling(ho * wo * chunks, co, b["cexp"], b["se"] > 0)
+            assert 16 <= bn <= 256 and bn % 16 == 0 and stages >= 2 and smem <= 227 * 1024, (i, chunks, bn, stages, smem)
+            assert n_tiles * bn >= co
+        if b["cexp"] == 288 and b["stride"] == 1:
+            bn, stages, b_res, n_tiles, smem = bb.pw2_tiling(ho * wo * 128, co, b["cexp"], True)
+            assert b_res == 1 and stages >= 3, (bn, stages, b_res)
+    for M, N, K in ((6 * 256, 1024, 1728), (256, 6522, 1024), (1, 6522, 1024)):
+        bn, stages, b_res, n_tiles, smem = bb.pw2_tiling(M, N, K, False)
+        assert stages >= 2 and smem <= 227 * 1024 and n_tiles * bn >= N

@@ -359,3 +359,26 @@ def test_two_devices_in_one_process(lib_path, audio):
     [t.start() for t in ths]; [t.join() for t in ths]
     assert np.array_equal(out["a"], ya) and np.array_equal(out["b"], ya)
     a.close(); b.close()
+
+
+def test_detections_on_device_match_host_filter(lib_path, golden):
+    """N1: bnb_analyze_batch_detections (sigmoid + threshold + compaction on the device) = thresholding the analyze_batch top-10
+    on the host, in chunk-then-confidence order; the published soundscape table (threshold 0.1, sensitivity 1.5: 25 rows of
+    /root/reference/doc/wiki/file-analysis.md:20-44) comes back as the top-1 entries of its chunks."""
+    from bench import soundscape_batch
+    x = soundscape_batch(160)
+    c = bb.B200Classifier(max_batch=256)
+    idx, conf = c.analyze_batch(x, 1.5, 10)
+    for thr in (0.1, 0.5, 0.0001):
+        ch, sp, cf, counts = c.analyze_batch_detections(x, 1.5, thr, 10)
+        keep = conf >= thr
+        assert np.array_equal(counts, keep.sum(1))
+        rows = np.nonzero(keep)
+        assert np.array_equal(ch, rows[0]) and np.array_equal(sp, idx[keep]) and np.array_equal(cf, conf[keep])
+    ch, sp, cf, counts = c.analyze_batch_detections(x, 1.5, 0.1, 10, max_det=7)            # truncated list, full counts
+    assert len(ch) == 7 and counts.sum() == (conf >= 0.1).sum()
+    x16 = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)                     # int16 ingest through the same entry
+    ch16, sp16, cf16, _ = c.analyze_batch_detections(x16, 1.5, 0.1, 10)
+    i16, c16 = c.analyze_batch(x16, 1.5, 10)
+    assert np.array_equal(sp16, i16[c16 >= 0.1])
+    c.close()
