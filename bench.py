@@ -9,10 +9,12 @@ One "step" = one pass of the hot path over one batch of 3 s chunks:
   N > 1 : the same batch per GPU (weak scaling, independent chunks, no data-path collective); the only
           collective is the NCCL all-gather of the per-chunk top-10 (80 B/chunk), inside the timed region.
 `value`  : chunks/s with the PCM already resident in HBM (device pointers through the C ABI).
-`e2e`    : chunks/s through the host-buffer C-ABI call (bnb_analyze_batch): pinned host float32 PCM -> H2D ->
-           kernels -> sigmoid/top-10 -> D2H, every step, one synchronous caller.  Extra keys beside it:
-           `value_int16_pcm` (same call, int16 PCM as the reference's queue holds it), `value_two_callers` (two host
-           threads with a handle each), and top-level `latency_batch1_ms` (bnb_predict on one chunk, median of 30).
+`e2e`    : chunks/s through the host-buffer C ABI: pinned host float32 PCM -> H2D -> kernels -> sigmoid/top-10 -> D2H,
+           every step, ONE caller using bnb_analyze_batch_submit / bnb_wait (two batches in flight, so the copy-in of step
+           i+1 overlaps the kernels of step i).  Extra keys beside it: `value_synchronous_call` (bnb_analyze_batch, nothing
+           overlapped), `value_int16_pcm` (int16 PCM as the reference's queue holds it), `value_two_callers` (two host
+           threads with a handle each), top-level `latency_batch1_ms` (bnb_predict on one chunk from a CUDA graph, median of
+           30), `config5_*` (8 realtime windows coalesced into one call: p50 / p99) and `config4_*` (bat backbone, embeddings).
 `roofline`: the tcgen05 kernels (fused expand+depthwise and the other 1x1 GEMMs): algorithmic FLOPs / their CUDA-event
            time measured on ONE lane (no overlap) vs the measured bf16 dense peak; `traffic` from the committed ncu list.
 `cpu_baseline` (N = 1 only): the oracle port on the host cores, bounded sample.  `clocks`: nvidia-smi samples taken
@@ -380,10 +382,15 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=128)
     ap.add_argument("--lanes", type=int, default=2)
     ap.add_argument("--precision", default="default", choices=["default", "f32", "f16x3"])
+    ap.add_argument("--workload", default="config1", choices=["config1", "config2"],
+                    help="config1 = BASELINE configs[1] (soundscape.wav, batch 256 per GPU: the headline, every N); config2 = configs[2] "
+                         "(synthetic pink noise + chirp, batch 1024 per GPU-step, chunk ids sharded contiguously over the ranks with birdnet_b200.dist.shard_range)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-two-callers", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.workload == "config2" and a.batch == BATCH:
+        a.batch = 1024
     config = {"workload": "soundscape.wav 3s window / 1.5s overlap (79 chunks) tiled to batch=%d per GPU, BirdNET v2.4 fp32 weights" % a.batch,
               "batch_per_gpu": a.batch, "global_batch": a.batch * world, "l2": "device inputs rotate over 2 distinct 147 MB buffers (> 126 MB L2)"}
 
@@ -417,9 +424,17 @@ def main():
     prec = {"default": bb.PRECISION_DEFAULT, "f32": bb.PRECISION_F32, "f16x3": bb.PRECISION_F16X3}[a.precision]
     clf = bb.B200Classifier(device=local, max_batch=a.batch, micro_batch=a.micro_batch, precision=prec, lanes=a.lanes)
     B = a.batch
-    host = soundscape_batch(B)
-    if world > 1:
-        host = np.roll(host, rank * 7, axis=0)     # each rank analyses its own shard of the stream
+    if a.workload == "config2":
+        # BASELINE configs[2]: one GPU-step = 1024 synthetic chunks per rank; the global chunk index space [0, world * B) of a
+        # step is cut into contiguous shards exactly like the 100 k-chunk job would be (seed = 1234 + chunk id)
+        from birdnet_b200 import dist as bdist0
+        lo, hi = bdist0.shard_range(world * B, rank, world)
+        host = synth_chunks(hi - lo, seed0=1234 + lo)
+        config["workload"] = "synthetic 48 kHz pink noise + chirp (seed 1234 + chunk id), %d chunks per GPU-step, contiguous shard [%d, %d) of %d, BirdNET v2.4 fp32 weights" % (B, lo, hi, world * B)
+    else:
+        host = soundscape_batch(B)
+        if world > 1:
+            host = np.roll(host, rank * 7, axis=0)     # each rank analyses its own shard of the stream
     # device-resident inputs: two distinct copies so consecutive steps never find their input in L2
     d_in = [torch.from_numpy(host).cuda(), torch.from_numpy(host[::-1].copy()).cuda()]
     d_logits = torch.empty((B, N_SPECIES), dtype=torch.float32, device="cuda")
@@ -599,6 +614,30 @@ def main():
         clf.predict(one)
         if i >= 5:
             lat_plain.append(1e3 * (time.perf_counter() - t0))
+    # BASELINE config 5 shape (realtime, one GPU): 8 streams whose 3 s windows become ready in the same 100 ms monitor tick are
+    # coalesced into ONE int16 call (birdnet_b200.realtime.RealtimeCoalescer does this); latency = window ready -> top-10 on the host
+    extra = {}
+    if world == 1 and not a.no_two_callers:
+        w8 = np.clip(np.round(host[:8] * 32768.0), -32768, 32767).astype(np.int16)
+        l8 = []
+        for i in range(110):
+            t0 = time.perf_counter()
+            clf1.analyze_batch(w8, 1.0, TOP_K)
+            if i >= 10:
+                l8.append(1e3 * (time.perf_counter() - t0))
+        extra["config5_realtime_8_streams_coalesced"] = {"p50_ms": float(np.percentile(l8, 50)), "p99_ms": float(np.percentile(l8, 99)),
+                                                         "windows_per_call": 8, "sustained_chunks_per_s": 8e3 / float(np.mean(l8)),
+                                                         "note": "8 int16 windows ready in one tick -> one bnb_analyze_batch (CUDA graph); the reference's realtime path needs 8 serialized Predict calls under inferenceMu"}
+        # BASELINE config 4 shape (bat backbone): 144000 samples captured at 256 kHz through the same backbone, embedding out
+        # (bat_onnx.go:252); synthetic pink noise + 20-80 kHz sweeps; e2e through bnb_predict_batch with embeddings
+        xb = synth_chunks(B, seed0=99000, fs=256000)
+        tb = []
+        for i in range(5):
+            t0 = time.perf_counter()
+            clf.predict_batch(xb, with_embeddings=True)
+            tb.append(time.perf_counter() - t0)
+        extra["config4_bat_backbone_embeddings"] = {"value": B / float(np.median(tb[1:])), "unit": UNIT,
+                                                     "note": "the config-3 generator at fs = 256000; synchronous bnb_predict_batch, pageable float32 host PCM in, logits + 1024-d embeddings out (27 KB/chunk D2H): copy-bound"}
     clf1.close()
     lat_ms = float(np.median(lat))
     clocks = sampler.stop() if rank == 0 else None
@@ -644,6 +683,7 @@ def main():
             "hbm_floor_frac": (value / world) * MIN_HBM_BYTES_PER_CHUNK / (float(peaks["hbm_gbs"]) * 1e9),
             "precision": clf.runtime_info()[2],
         }
+        line.update(extra)
         if not a.no_cpu_baseline and world == 1:
             _, _, cb = cpu_reference_run(3, 1)
             line["cpu_baseline"] = cb

@@ -776,6 +776,7 @@ void Engine::wait_host(int ticket) {
 int Engine::detect_host(const void* pcm, int fmt, int B, float sensitivity, float threshold, int k, int max_det, int32_t* det_chunk,
                         int32_t* det_idx, float* det_conf, int32_t* counts) {
   BNB_CUDA(cudaSetDevice(device_));
+  ensure_host_staging();                          // sets topk_cap_ (first host call of this handle)
   if (k <= 0 || k > topk_cap_) throw std::invalid_argument("k must be in 1..64");
   const size_t cap = (size_t)max_batch_ * topk_cap_;
   if (!d_det_) {                                   // [3][cap] (chunk, idx, conf bits) + counts[max_batch] + length

@@ -150,3 +150,23 @@ def test_f16x3_plans_cover_every_block(lib_path):
     for M, N, K in ((6 * 256, 1024, 1728), (256, 6522, 1024), (1, 6522, 1024)):
         bn, stages, b_res, n_tiles, smem = bb.pw2_tiling(M, N, K, False)
         assert stages >= 2 and smem <= 227 * 1024 and n_tiles * bn >= N
+
+
+def test_go_backend_binds_only_declared_symbols(lib_path):
+    """The Go side (go/internal/inference/b200, not compilable here: no Go toolchain) must reference only functions and constants
+    that include/birdnet_b200.h declares and the library exports; the stub must offer the same method set as the cgo file."""
+    import re
+    root = os.path.join(REPO, "go", "internal", "inference", "b200")
+    hdr = open(os.path.join(REPO, "include", "birdnet_b200.h")).read()
+    cgo = open(os.path.join(root, "backend_b200.go")).read()
+    stub = open(os.path.join(root, "stub_nob200.go")).read()
+    used = set(re.findall(r"\bC\.(bnb_\w+|BNB_\w+)", cgo))
+    assert len(used) >= 12
+    lib = bb.load_library()
+    for name in sorted(used):
+        assert re.search(r"\b%s\b" % name, hdr), name
+        if name.startswith("bnb_") and not name.endswith("_t") and name not in ("bnb_classifier", "bnb_options"):
+            assert hasattr(lib, name), name
+    assert "//go:build b200" in cgo and "//go:build !b200" in stub
+    meth = lambda src: set(re.findall(r"^func \(c \*Classifier\) (\w+)\(", src, re.M)) | set(re.findall(r"^func (\w+)\(", src, re.M))
+    assert meth(cgo) - {"sizeMismatch", "lastErr"} <= meth(stub) | {"analyze"}, sorted(meth(cgo) - meth(stub))
