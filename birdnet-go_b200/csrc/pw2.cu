@@ -46,6 +46,7 @@ struct Pw2Args {
   int o_pitch, out_mode;                  // out_mode: 0 fp32, 1 plain planes, 2 PatchTiles image
   uint32_t a_tile_bytes;
   int n_pad, k_pad, n_tiles, bn, stages, b_res, conv, out_vec;
+  int epi_teams;                          // 2: the 16 epilogue warps work as two teams of 8 on alternate m-tiles (narrow layers), 1: all on every tile
   int a_ldgsts;                           // A stage blocks fetched by the loader warp's 32 lanes with cp.async (16 B each) instead of one bulk copy
   int n_acc;                              // independent accumulators per tile (column ranges of bn): MMA i goes to accumulator i % n_acc
   PatchTiles rp, op;                      // residual / output patch layouts
@@ -81,7 +82,7 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) { mbar_init(tma_bar(s), a.a_ldgsts ? 33 : 1); mbar_init(full_bar(s), kConvThreads); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps * 32); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiWarps * 32 / a.epi_teams); }
     mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -279,13 +280,19 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
     // memory (no shared-memory transpose: the staging buffers cost 32 KB that now hold resident weights, and their traffic
     // competed with the MMA operand reads).  Sixteen warps because one warp per 32x32 sub-tile was latency-bound
     // (profiles/r02 timeline: 4.5 k cycles per m-tile).
+    // Narrow layers (bn <= 64: a warp would own one chunk per m-tile) run the warps as TWO TEAMS on alternate m-tiles = alternate
+    // TMEM buffers: the epilogue of a tile is a chain of dependent global accesses (lookup table -> residual pieces -> stores:
+    // 2-4 k cycles each while the copy engine keeps the memory system busy), and one team handled 8.3 k cycles per tile
+    // against 5-6 k of main loop (r02 timeline of block 1); two tiles in flight hide it.
     const int quarter = warp & 3, sub = warp >> 2;
+    const int team = a.epi_teams == 2 ? (sub >> 1) : 0, csub = a.epi_teams == 2 ? (sub & 1) : sub, cstep = a.epi_teams == 2 ? 32 : 64;
     const int n0 = nt_fix * a.bn;
     const int bn = min(a.bn, a.n_pad - n0);
     const bool plane_mode = a.out_mode != 0;
     uint32_t tcount = 0;
     for (int mt = mt_first; mt < m_tiles; mt += mt_step, ++tcount) {
       const int buf = tcount & 1;
+      if (a.epi_teams == 2 && buf != team) continue;
       const int mrow = mt * kBM + quarter * 32 + lane;
       const bool row_ok = mrow < a.M;
       // where this row lives in the residual / output patch images (one table lookup per row and m-tile)
@@ -295,16 +302,11 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
         if (a.r_img != nullptr) { a.rp.split_chunk((uint32_t)mrow, &pb, &pix); res_ent = __ldg(a.rp.res_tbl + pix); }
         if (a.out_mode == 2) { a.op.split_chunk((uint32_t)mrow, &pb, &pix); dst_ent = __ldg(a.op.dst_tbl + pix); }
       }
-      mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
-      tc_fence_after();
-      if (threadIdx.x == 0) PW2_TRACE(5, tcount);
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kAccCols;
-      for (int c0 = sub * 16; c0 < bn; c0 += 64) {
-        const int n = n0 + c0;
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
-        // residual pieces (the block input: pixel m is interior to exactly one patch tile of its image) requested before the wait
-        uint4 rvh[2], rvl[2];
+      // residual pieces (the block input: pixel m is interior to exactly one patch tile of its image): independent of the
+      // accumulator, so the first chunk's are requested BEFORE the wait for it — on the 36-column front layers a warp has one
+      // chunk per m-tile and their L2 latency (1-2 k cycles) was the epilogue's critical path (r02 timeline: 8.5 k cycles per tile)
+      uint4 rvh[2], rvl[2];
+      auto load_res = [&](int n) {
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
           rvh[p] = make_uint4(0, 0, 0, 0); rvl[p] = rvh[p];
@@ -317,6 +319,17 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
             rvl[p] = __ldcg(reinterpret_cast<const uint4*>(src + a.rp.st_plane[rs]));
           }
         }
+      };
+      if (csub * 16 < bn) load_res(n0 + csub * 16);
+      mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) PW2_TRACE(5, tcount);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kAccCols;
+      for (int c0 = csub * 16; c0 < bn; c0 += cstep) {
+        const int n = n0 + c0;
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c0, r);
+        if (c0 != csub * 16) load_res(n);
         tmem_ld_wait();
         for (int ac = 1; ac < a.n_acc; ++ac) {             // add the other accumulators of the tile (fixed order)
           uint32_t r2[16];
@@ -456,6 +469,8 @@ void launch_pw2(const PwTcLayer& L, const Pw2Launch& p, cudaStream_t s, LaunchCo
   a.rp = p.r_patch; a.op = p.o_patch;
   a.n_pad = L.n_pad; a.k_pad = L.k_pad; a.bn = bn; a.n_tiles = (L.n_pad + bn - 1) / bn; a.stages = stages; a.b_res = b_res;
   a.conv = p.gate != nullptr ? 1 : 0;
+  a.epi_teams = bn <= 64 ? 2 : 1;
+  { static const int et = getenv("BNB_PW2_TEAMS") ? atoi(getenv("BNB_PW2_TEAMS")) : 0; if (et == 1 || et == 2) a.epi_teams = et; }
   // experiment knob: A stage blocks by 2048 per-thread cp.async instead of one bulk copy.  Measured (r02 run k16): the blocks
   // still land ~2.5 k cycles apart and the step is 1 % slower, so one SM ingests ~13 B/clk whichever engine asks: default off.
   { static const int ld = getenv("BNB_PW2_LDGSTS") ? atoi(getenv("BNB_PW2_LDGSTS")) : 0; a.a_ldgsts = ld; }
