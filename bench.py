@@ -415,6 +415,10 @@ def main():
         import torch.distributed as dist
         # NCCL prints its version banner to fd 1 when the communicator comes up (NCCL_DEBUG=VERSION on the boxes): keep
         # stdout to the one JSON line by pointing fd 1 at stderr while the communicator is created
+        # the only collective is an 80 B-per-chunk all-gather: one channel is plenty, and every extra NCCL CTA takes an SM away
+        # from the 148-CTA persistent kernels it overlaps with (r02: 2.7 % per step at N = 2 and N = 4 alike)
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
         sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))

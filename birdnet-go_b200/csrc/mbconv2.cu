@@ -76,7 +76,7 @@ struct Mb2Args {
 #define MB2_TRACE(ev, i) do { if (a.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (i) < 64) \
     a.trace[((blockIdx.x == 0 ? 0 : 1) * 10 + (ev)) * 64 + (i)] = clock64(); } while (0)
 
-template <int PW>
+template <int PW, int POLY>
 __device__ __forceinline__ void load_row(float (&dst)[PW], uint32_t taddr, bool row_in, bool left_oob, bool right_oob, float be, int dbg = 0) {
   if (!row_in) {                                  // warp-uniform: the whole patch row lies outside the image
 #pragma unroll
@@ -97,13 +97,13 @@ __device__ __forceinline__ void load_row(float (&dst)[PW], uint32_t taddr, bool 
   // whatever ran in the buffer before).
   if (left_oob) dst[0] = 0.f;
   if (right_oob) dst[PW - 1] = 0.f;
-  silu_n<PW>(dst);
+  silu_n<PW, POLY>(dst);
 }
 
 // TW outputs of one output row from three SiLU'd patch rows.  `prow` points at this thread's 2-byte slot of output 0 in the hi
 // plane of the RowTiles image (row r0 = multiple of TW; the swizzle term of output o is ((o + (r0 & 7)) & 7): r0_lo = r0 & 7
 // is 0 for TW = 8 and 0 or 4 for TW = 4); chunk16 = this channel's 16-byte chunk index << 4; the lo plane is + 16384.
-template <int S, int TW, int PW>
+template <int S, int TW, int PW, int POLY>
 __device__ __forceinline__ void out_row(const float (&r0)[PW], const float (&r1)[PW], const float (&r2)[PW], const float (&wd)[9],
                                         float bd, uint8_t* prow, uint32_t chunk16, uint32_t r0_lo, bool active, float& lsum) {
 #pragma unroll
@@ -118,7 +118,7 @@ __device__ __forceinline__ void out_row(const float (&r0)[PW], const float (&r1)
       v = fmaf(r2[c0], wd[6], v); v = fmaf(r2[c0 + 1], wd[7], v); v = fmaf(r2[c0 + 2], wd[8], v);
       acc[i] = v;
     }
-    silu4(acc[0], acc[1], acc[2], acc[3]);
+    silu4<POLY>(acc[0], acc[1], acc[2], acc[3]);
     if (active) {
       lsum += acc[0]; lsum += acc[1]; lsum += acc[2]; lsum += acc[3];        // fixed order: deterministic SE sums
       uint32_t h01, l01, h23, l23;
@@ -134,7 +134,7 @@ __device__ __forceinline__ void out_row(const float (&r0)[PW], const float (&r1)
   }
 }
 
-template <int S, int TW>
+template <int S, int TW, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 mbconv2_kernel(const Mb2Args a) {
   constexpr int PW = (TW - 1) * S + 3;
@@ -342,7 +342,7 @@ mbconv2_kernel(const Mb2Args a) {
         float rA[PW], rB[PW], rC[PW];
         auto ld = [&](float (&dst)[PW], int r) {
           const int hi = hi0 + r;
-          load_row<PW>(dst, tbuf + (uint32_t)(r * PW), hi >= 0 && hi < a.H, left_oob, right_oob, be, a.dbg);
+          load_row<PW, POLY>(dst, tbuf + (uint32_t)(r * PW), hi >= 0 && hi < a.H, left_oob, right_oob, be, a.dbg);
           if (r == a.PH - 1) { tc_fence_before(); mbar_arrive(t_empty(mybuf)); if (lane == 0 && quarter == 0 && half == 0) MB2_TRACE(5, seq); }     // accumulator fully read: hand the buffer back
         };
         // RowTiles image of the result: row m = (b*Ho + ho)*Wo + wo, 64-channel stage c >> 6, chunk (c >> 3) & 7
@@ -351,7 +351,7 @@ mbconv2_kernel(const Mb2Args a) {
         const uint32_t chunk16 = (uint32_t)((c >> 3) & 7) << 4;
         auto out = [&](const float (&r0)[PW], const float (&r1)[PW], const float (&r2)[PW], int oh) {
           const uint32_t m = m_tile0 + (uint32_t)oh * a.Wo;
-          out_row<S, TW, PW>(r0, r1, r2, wd, bd, out_c + (size_t)(m >> 7) * a.d_tile_bytes + (m & 127u) * 128u, chunk16, m & 7u, active && !(a.dbg & 4), lsum);
+          out_row<S, TW, PW, POLY>(r0, r1, r2, wd, bd, out_c + (size_t)(m >> 7) * a.d_tile_bytes + (m & 127u) * 128u, chunk16, m & 7u, active && !(a.dbg & 4), lsum);
         };
         if (S == 1) {
           ld(rA, 0); ld(rB, 1);
@@ -522,8 +522,10 @@ PatchTiles mb2_patch_layout(const Mb2Plan& P, int H, int W) {
 }
 
 void mb2_set_attributes() {
-  BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
-  BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
+  BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
+  BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<2, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
+  BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
+  BNB_CUDA(cudaFuncSetAttribute(mbconv2_kernel<2, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMb2SmemLimit));
 }
 
 void launch_mbconv2(const Mb2Plan& P, const Mb2Launch& L, cudaStream_t s, LaunchCounter& lc) {
@@ -554,9 +556,14 @@ void launch_mbconv2(const Mb2Plan& P, const Mb2Launch& L, cudaStream_t s, Launch
   const long long my_idx = launch_idx.fetch_add(1);
   long long* trace = nullptr;
   if (trace_path && my_idx == trace_idx) { BNB_CUDA(cudaMalloc(&trace, 2 * 10 * 64 * sizeof(long long))); BNB_CUDA(cudaMemsetAsync(trace, 0, 2 * 10 * 64 * sizeof(long long), s)); a.trace = trace; }
-  if (P.S == 1 && P.TW == 8) launch_k(mbconv2_kernel<1, 8>, dim3(grid), dim3(kThreads), P.smem_bytes, s, a);
-  else if (P.S == 2 && P.TW == 4) launch_k(mbconv2_kernel<2, 4>, dim3(grid), dim3(kThreads), P.smem_bytes, s, a);
-  else throw std::runtime_error("mbconv2: unsupported tile shape");
+  // BNB_MB2_POLY=1: one of every four SiLU exponentials on the FMA pipe instead of MUFU (tc_common.cuh: ex2_poly).  Experiment
+  // knob, default off: ncu shows the XU pipe 78 % busy, yet moving exponentials over made the kernel SLOWER (r02 run k20:
+  // pw_expand 1.453 ms -> 1.514 with one of four, 1.608 with two of four) — the epilogue is issue-bound, not MUFU-bound.
+  static const int poly = getenv("BNB_MB2_POLY") ? atoi(getenv("BNB_MB2_POLY")) : 0;
+  const bool s1 = P.S == 1 && P.TW == 8, s2 = P.S == 2 && P.TW == 4;
+  if (!s1 && !s2) throw std::runtime_error("mbconv2: unsupported tile shape");
+  if (poly <= 0) { if (s1) launch_k(mbconv2_kernel<1, 8, 0>, dim3(grid), dim3(kThreads), P.smem_bytes, s, a); else launch_k(mbconv2_kernel<2, 4, 0>, dim3(grid), dim3(kThreads), P.smem_bytes, s, a); }
+  else { if (s1) launch_k(mbconv2_kernel<1, 8, 1>, dim3(grid), dim3(kThreads), P.smem_bytes, s, a); else launch_k(mbconv2_kernel<2, 4, 1>, dim3(grid), dim3(kThreads), P.smem_bytes, s, a); }
   if (trace) {
     std::vector<long long> h(2 * 10 * 64);
     BNB_CUDA(cudaStreamSynchronize(s));

@@ -229,14 +229,31 @@ __device__ __forceinline__ float silu_e(float t) {       // 1 + exp(-x) from t =
 __device__ __forceinline__ float rcp_f(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 constexpr float kNegLog2e = -1.4426950408889634f;
 __device__ __forceinline__ float ex2_f(float t) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t)); return e; }
+// 2^t for t in [-30, 30] WITHOUT the MUFU pipe: round-to-nearest split t = n + f with the 1.5 * 2^23 constant (two FADDs), degree-6
+// interpolating polynomial for 2^f on [-0.5, 0.5] (6 FFMAs, max relative error 1.0e-7 in fp32 Horner form: better than
+// ex2.approx's 2 ulp), n added to the exponent field (shift + integer add).  The FA4 trick; measured NOT to pay here (mbconv2.cu,
+// BNB_MB2_POLY): the epilogue is issue-bound, so 11 extra instructions cost more than the MUFU slot they free.
+__device__ __forceinline__ float ex2_poly(float t) {
+  const float magic = 12582912.0f;                       // 1.5 * 2^23
+  const float r = t + magic;
+  const float f = t - (r - magic);
+  float p = 1.5461444697e-04f;
+  p = fmaf(p, f, 1.3400428177e-03f); p = fmaf(p, f, 9.6180566785e-03f); p = fmaf(p, f, 5.5503272267e-02f);
+  p = fmaf(p, f, 2.4022650922e-01f); p = fmaf(p, f, 6.9314720670e-01f); p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
 // Four SiLUs with ONE reciprocal (of the product of the four denominators) and packed fp32 multiplies / adds (sm_100 FMUL2 /
-// FADD2 work on register pairs): 22 instructions instead of 30.  Bit-identical to the scalar form: every product is formed
-// in the same association, and the packed instructions round each half like their scalar counterparts.
+// FADD2 work on register pairs): 22 instructions instead of 30.  POLY of the four exponentials (which ones is fixed by the
+// position in the group, never by data: results stay independent of batch composition) use ex2_poly instead of MUFU.EX2.
+template <int POLY = 0>
 __device__ __forceinline__ void silu4(float& x0, float& x1, float& x2, float& x3) {
   const float2 k = make_float2(kNegLog2e, kNegLog2e), one = make_float2(1.0f, 1.0f);
   const float2 t01 = __fmul2_rn(make_float2(x0, x1), k), t23 = __fmul2_rn(make_float2(x2, x3), k);
-  const float2 e01 = make_float2(ex2_f(fminf(t01.x, 30.f)), ex2_f(fminf(t01.y, 30.f)));
-  const float2 e23 = make_float2(ex2_f(fminf(t23.x, 30.f)), ex2_f(fminf(t23.y, 30.f)));
+  float2 e01, e23;
+  e01.x = ex2_f(fminf(t01.x, 30.f));
+  e01.y = POLY >= 2 ? ex2_poly(fmaxf(fminf(t01.y, 30.f), -30.f)) : ex2_f(fminf(t01.y, 30.f));
+  e23.x = ex2_f(fminf(t23.x, 30.f));
+  e23.y = POLY >= 1 ? ex2_poly(fmaxf(fminf(t23.y, 30.f), -30.f)) : ex2_f(fminf(t23.y, 30.f));
   const float2 ab2 = __fadd2_rn(e01, one), cd2 = __fadd2_rn(e23, one);          // (a, b), (c, d) = 1 + exp(-x)
   const float ab = ab2.x * ab2.y, cd = cd2.x * cd2.y;
   const float r = rcp_f(ab * cd);
@@ -252,10 +269,10 @@ __device__ __forceinline__ void silu2b(float& x0, float& x1) {
   x0 *= r * b; x1 *= r * a;
 }
 __device__ __forceinline__ void silu1b(float& x0) { x0 *= rcp_f(silu_e(x0 * kNegLog2e)); }
-template <int N>
+template <int N, int POLY = 0>
 __device__ __forceinline__ void silu_n(float* v) {
 #pragma unroll
-  for (int i = 0; i + 4 <= N; i += 4) silu4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  for (int i = 0; i + 4 <= N; i += 4) silu4<POLY>(v[i], v[i + 1], v[i + 2], v[i + 3]);
   if constexpr (N % 4 == 3) { silu2b(v[N - 3], v[N - 2]); silu1b(v[N - 1]); }
   if constexpr (N % 4 == 2) silu2b(v[N - 2], v[N - 1]);
   if constexpr (N % 4 == 1) silu1b(v[N - 1]);
