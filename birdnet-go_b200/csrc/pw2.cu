@@ -307,16 +307,23 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
       // chunk per m-tile and their L2 latency (1-2 k cycles) was the epilogue's critical path (r02 timeline: 8.5 k cycles per tile)
       uint4 rvh[2], rvl[2];
       auto load_res = [&](int n) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          rvh[p] = make_uint4(0, 0, 0, 0); rvl[p] = rvh[p];
-          const int pcol = n + 8 * p;
-          if (plane_mode && a.r_img != nullptr && row_ok && pcol < a.o_pitch) {
-            int rs, rchunk;
-            a.rp.stage_of(pcol >> 3, &rs, &rchunk);
-            const uint8_t* src = a.r_img + a.rp.entry_piece(pb, res_ent, rs, rchunk);
-            rvh[p] = __ldcg(reinterpret_cast<const uint4*>(src));              // coherent loads: written by an earlier kernel (PDL)
-            rvl[p] = __ldcg(reinterpret_cast<const uint4*>(src + a.rp.st_plane[rs]));
+        rvh[0] = make_uint4(0, 0, 0, 0); rvl[0] = rvh[0]; rvh[1] = rvh[0]; rvl[1] = rvh[0];
+        if (plane_mode && a.r_img != nullptr && row_ok && n < a.o_pitch) {
+          int rs, rchunk;
+          a.rp.stage_of(n >> 3, &rs, &rchunk);                               // piece 0: an even chunk of its stage (n % 16 == 0)
+          const size_t a0 = a.rp.entry_piece(pb, res_ent, rs, rchunk);
+          const uint32_t lo_off = a.rp.st_plane[rs];
+          if (n + 8 < a.o_pitch) {
+            // both pieces: chunks c and c + 1 of the same swizzled row differ only in address bit 4 -> ONE aligned 32-byte sector
+            // per plane (coherent 256-bit loads: the image was written by an earlier kernel, PDL)
+            const uint8_t* base = a.r_img + (a0 & ~(size_t)31);
+            const bool swapped = (a0 & 16) != 0;
+            uint4 h0, h1, l0, l1;
+            ldg256_cg(base, h0, h1); ldg256_cg(base + lo_off, l0, l1);
+            rvh[0] = swapped ? h1 : h0; rvh[1] = swapped ? h0 : h1; rvl[0] = swapped ? l1 : l0; rvl[1] = swapped ? l0 : l1;
+          } else {
+            rvh[0] = __ldcg(reinterpret_cast<const uint4*>(a.r_img + a0));
+            rvl[0] = __ldcg(reinterpret_cast<const uint4*>(a.r_img + a0 + lo_off));
           }
         }
       };
@@ -349,33 +356,46 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
           else if (a.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           v[4 * q] = o.x; v[4 * q + 1] = o.y; v[4 * q + 2] = o.z; v[4 * q + 3] = o.w;
         }
-        if (row_ok && plane_mode) {
+        if (row_ok && plane_mode && n < a.o_pitch) {
+          const bool two = n + 8 < a.o_pitch;              // past the last piece of the pitch nothing is stored (pad columns INSIDE a piece get exact zeros: zero weights, zero bias)
+          uint4 ho[2], lo[2];
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
-            const int pcol = n + 8 * p;
-            if (pcol >= a.o_pitch) continue;               // past the last piece of the pitch (pad columns INSIDE a piece get exact zeros: zero weights, zero bias)
             float* w = v + 8 * p;
             if (a.r_img != nullptr) {
               const float2 q0 = join2(rvh[p].x, rvl[p].x), q1 = join2(rvh[p].y, rvl[p].y), q2 = join2(rvh[p].z, rvl[p].z), q3 = join2(rvh[p].w, rvl[p].w);
               w[0] += q0.x; w[1] += q0.y; w[2] += q1.x; w[3] += q1.y; w[4] += q2.x; w[5] += q2.y; w[6] += q3.x; w[7] += q3.y;
             }
-            uint4 ho, lo;
-            split2(w[0], w[1], ho.x, lo.x); split2(w[2], w[3], ho.y, lo.y); split2(w[4], w[5], ho.z, lo.z); split2(w[6], w[7], ho.w, lo.w);
-            if (a.out_mode == 1) {
-              *reinterpret_cast<uint4*>(a.oh + (size_t)mrow * a.o_pitch + pcol) = ho;
-              *reinterpret_cast<uint4*>(a.ol + (size_t)mrow * a.o_pitch + pcol) = lo;
-            } else {
-              // the next block's PatchTiles image: the pixel goes into every tile whose halo patch contains it (<= 4, from the table)
-              int os, ochunk;
-              a.op.stage_of(pcol >> 3, &os, &ochunk);
-              const uint32_t lo_off = a.op.st_plane[os];
-              const uint32_t e4[4] = {dst_ent.x, dst_ent.y, dst_ent.z, dst_ent.w};
+            split2(w[0], w[1], ho[p].x, lo[p].x); split2(w[2], w[3], ho[p].y, lo[p].y); split2(w[4], w[5], ho[p].z, lo[p].z); split2(w[6], w[7], ho[p].w, lo[p].w);
+          }
+          if (a.out_mode == 1) {
+            *reinterpret_cast<uint4*>(a.oh + (size_t)mrow * a.o_pitch + n) = ho[0];
+            *reinterpret_cast<uint4*>(a.ol + (size_t)mrow * a.o_pitch + n) = lo[0];
+            if (two) {
+              *reinterpret_cast<uint4*>(a.oh + (size_t)mrow * a.o_pitch + n + 8) = ho[1];
+              *reinterpret_cast<uint4*>(a.ol + (size_t)mrow * a.o_pitch + n + 8) = lo[1];
+            }
+          } else {
+            // the next block's PatchTiles image: the pixel goes into every tile whose halo patch contains it (<= 4, from the table).
+            // The two pieces are chunks c, c + 1 (c even) of one swizzled row = the two halves of one aligned 32-byte sector, in
+            // either order: ONE 256-bit store per plane and destination instead of two half-sector stores (the front layers'
+            // epilogue was bound by store sectors: r02 timeline of block 1, 8.3 k cycles per m-tile)
+            int os, ochunk;
+            a.op.stage_of(n >> 3, &os, &ochunk);
+            const uint32_t lo_off = a.op.st_plane[os];
+            const uint32_t e4[4] = {dst_ent.x, dst_ent.y, dst_ent.z, dst_ent.w};
 #pragma unroll
-              for (int d = 0; d < 4; ++d) {
-                if (e4[d] != 0xffffffffu) {
-                  uint8_t* dst = a.o_img + a.op.entry_piece(pb, e4[d], os, ochunk);
-                  *reinterpret_cast<uint4*>(dst) = ho;
-                  *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+            for (int d = 0; d < 4; ++d) {
+              if (e4[d] != 0xffffffffu) {
+                const size_t a0 = a.op.entry_piece(pb, e4[d], os, ochunk);
+                if (two) {
+                  uint8_t* dst = a.o_img + (a0 & ~(size_t)31);
+                  const bool swapped = (a0 & 16) != 0;
+                  stg256(dst, swapped ? ho[1] : ho[0], swapped ? ho[0] : ho[1]);
+                  stg256(dst + lo_off, swapped ? lo[1] : lo[0], swapped ? lo[0] : lo[1]);
+                } else {
+                  *reinterpret_cast<uint4*>(a.o_img + a0) = ho[0];
+                  *reinterpret_cast<uint4*>(a.o_img + a0 + lo_off) = lo[0];
                 }
               }
             }

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== kernel + parity tests"; timeout 1500 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider 2>&1 | tail -5
+b() { python bench.py --steps 10 --warmup 3 --micro-batch $1 --lanes $2 --no-cpu-baseline --no-two-callers 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['e2e']['value']), round(d['e2e']['value_synchronous_call']), d['latency_batch1_ms'], d['latency_batch1_ms_no_graph'], {k:round(v,3) for k,v in d['kernel_ms_per_step'].items()})"; }
+export -f b
+echo "== bench"; timeout 300 bash -c "b 128 2"
+tr() { BNB_PW2_TRACE=gpurun_out/trace_$2.txt BNB_PW2_TRACE_IDX=$1 timeout 200 python tools/launch_times.py --batch 64 --micro-batch 64 --lanes 1 > /dev/null 2>&1; echo "-- $2"; head -9 gpurun_out/trace_$2.txt; }
+tr 37 pw2_b1_v8
