@@ -121,16 +121,27 @@ stem_mix_kernel(const StemMixDev p, const float* __restrict__ in, float* __restr
     for (int c = 0; c < kStemCo / 2; ++c) tc::split2(mix[c].x, mix[c].y, hw[c], lw[c]);
     const uint4 ent = __ldg(op.dst_tbl + (size_t)h * op.W + tid);
     const uint32_t e4[4] = {ent.x, ent.y, ent.z, ent.w};
+    // 24 channels = chunks 0, 1, 2 of the pixel's 64-byte row; chunk 3 holds the pad channels 24..31 (zero expand weights), written
+    // as zeros, so that each plane is two aligned 256-bit stores (chunks c, c + 1 of a swizzled row are the halves of one 32-byte
+    // sector, in either order) instead of three half-sector ones
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
       if (e4[d] == 0xffffffffu) continue;
 #pragma unroll
-      for (int q = 0; q < kStemCo / 8; ++q) {
+      for (int qp = 0; qp < (kStemCo / 8 + 1) / 2; ++qp) {
+        const int q0 = 2 * qp, q1 = q0 + 1;
         int st, chunk;
-        op.stage_of(q, &st, &chunk);
-        uint8_t* dst = out_img + op.entry_piece(b, e4[d], st, chunk);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-        *reinterpret_cast<uint4*>(dst + op.st_plane[st]) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+        op.stage_of(q0, &st, &chunk);
+        const size_t a0 = op.entry_piece(b, e4[d], st, chunk);
+        uint8_t* dst = out_img + (a0 & ~(size_t)31);
+        const bool swapped = (a0 & 16) != 0;
+        const uint4 hA = make_uint4(hw[4 * q0], hw[4 * q0 + 1], hw[4 * q0 + 2], hw[4 * q0 + 3]);
+        const uint4 lA = make_uint4(lw[4 * q0], lw[4 * q0 + 1], lw[4 * q0 + 2], lw[4 * q0 + 3]);
+        const uint4 hB = q1 < kStemCo / 8 ? make_uint4(hw[(4 * q1) % (kStemCo / 2)], hw[(4 * q1 + 1) % (kStemCo / 2)], hw[(4 * q1 + 2) % (kStemCo / 2)], hw[(4 * q1 + 3) % (kStemCo / 2)]) : zero4;
+        const uint4 lB = q1 < kStemCo / 8 ? make_uint4(lw[(4 * q1) % (kStemCo / 2)], lw[(4 * q1 + 1) % (kStemCo / 2)], lw[(4 * q1 + 2) % (kStemCo / 2)], lw[(4 * q1 + 3) % (kStemCo / 2)]) : zero4;
+        tc::stg256(dst, swapped ? hB : hA, swapped ? hA : hB);
+        tc::stg256(dst + op.st_plane[st], swapped ? lB : lA, swapped ? lA : lB);
       }
     }
     return;
@@ -553,6 +564,7 @@ void launch_stem_mix(const StemMixDev& p, const float* in, float* stem_out_or_nu
                      cudaStream_t s, LaunchCounter& lc, uint8_t* out_img, const PatchTiles* out_patch) {
   dim3 grid(p.out_h, B);
   if (out_img && (!out_patch || !out_patch->dst_tbl || out_patch->C != kStemCo || out_patch->H != p.out_h || out_patch->W != p.out_w / 2)) throw std::runtime_error("stem_mix: patch layout does not match the pooled stem output");
+  if (out_img && (out_patch->n_stages != 1 || out_patch->st_rb[0] < 64)) throw std::runtime_error("stem_mix: the 24-channel patch image must be one stage with at least four 16-byte chunks per row");
   launch_k(stem_mix_kernel, grid, dim3(kStemThreads), 0, s, p, in, stem_out_or_null, out, out_img, out_patch ? *out_patch : PatchTiles());
   lc.n++;
 }

@@ -403,6 +403,12 @@ pw2_kernel(const __grid_constant__ Pw2Args a) {
         } else if (row_ok) {
           // fp32 output: this thread's 16 consecutive columns of row mrow
           float* dst = a.out32 + (size_t)mrow * a.N + n;
+          if (a.out_vec == 4 && (a.N & 7) == 0 && c0 + 16 <= bn && n + 16 <= a.N) {        // whole 64-byte run: two 256-bit stores
+            stg256(dst, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                   make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+            stg256(dst + 8, make_uint4(__float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11])),
+                   make_uint4(__float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15])));
+          } else
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int ncol = n + 4 * q;
