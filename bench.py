@@ -392,7 +392,8 @@ def main():
     if a.workload == "config2" and a.batch == BATCH:
         a.batch = 1024
     config = {"workload": "soundscape.wav 3s window / 1.5s overlap (79 chunks) tiled to batch=%d per GPU, BirdNET v2.4 fp32 weights" % a.batch,
-              "batch_per_gpu": a.batch, "global_batch": a.batch * world, "l2": "device inputs rotate over 2 distinct 147 MB buffers (> 126 MB L2)"}
+              "batch_per_gpu": a.batch, "global_batch": a.batch * world, "micro_batch": a.micro_batch, "lanes": a.lanes,
+              "l2": "device inputs rotate over 2 distinct 147 MB buffers (> 126 MB L2)"}
 
     if a.impl == "reference":
         if rank != 0:
