@@ -34,6 +34,35 @@ def test_sass_is_sm100a(lib_path):
     assert "sm_100a" in out
 
 
+def test_sass_uses_the_blackwell_paths(lib_path):
+    """The shipped library's SASS (not just the arch string): the F16X3 kernels issue tcgen05 MMAs (UTCHMMA), read
+    TMEM (LDTM), fetch operands with bulk copies (UBLKCP), wait for the previous grid (ACQBULK = griddepcontrol.wait), use the
+    256-bit stores, and the MMA / copy issue is NOT wrapped in waterfall loops (BRA.U.ANY) any more; the frontend and stem use the
+    packed fp32 pipe.  profiles/r02_sass_tc.txt is the committed listing of the same counts (tools/sass_counts.py)."""
+    sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    per, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1); per[cur] = []
+        elif cur is not None:
+            m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+            if m:
+                per[cur].append(m.group(1))
+    def kernel(sub):
+        ks = [k for k in per if sub in k]
+        assert ks, sub
+        return [op for k in ks for op in per[k]]
+    mb2, pw2 = kernel("mbconv2_kernel"), kernel("pw2_kernel")
+    for ops in (mb2, pw2):
+        assert sum(o.startswith("UTCHMMA") for o in ops) >= 12 and any(o.startswith("LDTM") for o in ops)
+        assert any(o.startswith("UBLKCP") for o in ops) and any(o.startswith("ACQBULK") for o in ops)
+        assert sum(o.startswith("BRA.U.ANY") for o in ops) <= 1
+    assert any(".256" in o and o.startswith("STG") for o in pw2)
+    assert sum(o.startswith("FFMA2") for o in kernel("stem_mix_kernel")) > 1000
+    assert any(o.startswith("FADD2") for o in kernel("frontend_kernel"))
+
+
 def test_plan_extraction_matches_the_graph(lib_path):
     d = json.loads(bb.describe_model(open(bb.DEFAULT_MODEL, "rb").read()))
     assert d["n_samples"] == 144000 and d["n_species"] == 6522 and d["embedding_dim"] == 1024
