@@ -725,7 +725,9 @@ int Engine::submit_host(const void* pcm, int fmt, int B, float sensitivity, int 
     for (int i = 0; i < B; ++mi) {
       int n = micro_;
       static const int ramp = getenv("BNB_RAMP") ? atoi(getenv("BNB_RAMP")) : 1;     // 0 = none, 1 = /4 /4 /2, 2 = /2 (tuning knob)
-      if (micro_ >= 16 && B > micro_) {
+      // no ramp when another submission is still in flight: this call's copies already overlap THAT call's kernels, and the small
+      // head micro-batches would only cost kernel efficiency (r02: e2e 0.92 -> see profiles/README.md)
+      if (micro_ >= 16 && B > micro_ && !slots_[si ^ 1].busy) {
         if (ramp == 1) n = mi < 2 ? micro_ / 4 : (mi == 2 ? micro_ / 2 : micro_);
         else if (ramp == 2) n = mi == 0 ? micro_ / 2 : micro_;
       }
