@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from birdnet_b200.dist import gather_topk, shard_range
+from birdnet_b200.dist import gather_topk, gather_topk_packed, pack_topk, shard_range, unpack_topk
 
 
 def _fake_topk(chunk_ids, k=10):
@@ -29,6 +29,52 @@ def _worker(rank, world, port, n_chunks, out):
         out.put((gi.numpy(), gc.numpy()))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _worker_packed(rank, world, port, n_per_rank, out):
+    """bench.py's N > 1 step: equal shards, ONE packed [n, 2k] int32 all-gather (confidences bit-cast), double-buffered."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    got = []
+    packed = [torch.empty((n_per_rank, 20), dtype=torch.int32) for _ in range(2)]
+    gathered = [torch.empty((world * n_per_rank, 20), dtype=torch.int32) for _ in range(2)]
+    for step in range(3):
+        ids = range(step * 1000 + rank * n_per_rank, step * 1000 + (rank + 1) * n_per_rank)
+        idx, conf = _fake_topk(ids)
+        j = step & 1
+        gather_topk_packed(pack_topk(idx, conf, packed[j]), gathered[j])
+        gi, gc = unpack_topk(gathered[j])
+        got.append((gi.clone().numpy(), gc.clone().numpy()))
+    if rank == 0:
+        out.put(got)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_packed_gather_is_what_two_gathers_would_give():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n = 37
+    procs = [ctx.Process(target=_worker_packed, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for step, (gi, gc) in enumerate(got):
+        wi, wc = _fake_topk(range(step * 1000, step * 1000 + 2 * n))
+        assert np.array_equal(gi, wi.numpy()) and np.array_equal(gc, wc.numpy())       # rank order = chunk order, bits intact
+
+
+def test_pack_unpack_round_trip_keeps_the_bits():
+    idx, conf = _fake_topk(range(50))
+    conf[3, 2] = float("nan"); conf[4, 0] = -0.0
+    p = pack_topk(idx, conf)
+    assert p.dtype == torch.int32 and p.shape == (50, 20)
+    i2, c2 = unpack_topk(p)
+    assert torch.equal(i2, idx) and torch.equal(c2.view(torch.int32), conf.view(torch.int32))
 
 
 def _free_port():
