@@ -16,6 +16,7 @@
 // Header-only; link with -lbirdnet_b200.
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -190,6 +191,125 @@ class BirdNET {
   std::vector<std::string> labels_;
   double sensitivity_;
   std::mutex mu_;
+};
+
+// ---- inference counters + the orchestrator's predict surface ------------------------------------------------
+// inferencestats.Counters / CounterMap (internal/classifier/inferencestats/counters.go:29-251): invoke count, total and max
+// microseconds (the interval max is reset by Snapshot, the lifetime max is not), errors, and a ring of the last 1024 durations
+// for a nearest-rank percentile (idx = ceil(p n) - 1, clamped).
+constexpr int latencyWindowSize = 1024;
+constexpr double healthLatencyPercentile = 0.95;
+struct CounterSnapshot { long long InvokeCount = 0, InvokeTotalUs = 0, InvokeMaxUs = 0, InvokeErrors = 0; };
+struct CounterPeek { long long InvokeCount = 0, InvokeTotalUs = 0, InvokeMaxUsLifetime = 0, RecentP95Us = 0, InvokeErrors = 0, BatchWindows = 0; };
+class Counters {
+ public:
+  void RecordInvoke(long long durationUs, long long windows = 1) {
+    std::lock_guard<std::mutex> lk(mu_);
+    ++count_; total_ += durationUs; max_ = std::max(max_, durationUs); maxLife_ = std::max(maxLife_, durationUs); windows_ += windows;
+    ring_[pos_] = durationUs; pos_ = (pos_ + 1) % latencyWindowSize; if (len_ < latencyWindowSize) ++len_;
+  }
+  void RecordError() { std::lock_guard<std::mutex> lk(mu_); ++errors_; }
+  long long RecentPercentileUs(double p) const {
+    std::vector<long long> v;
+    { std::lock_guard<std::mutex> lk(mu_); if (len_ == 0) return 0; v.assign(ring_, ring_ + len_); }
+    std::sort(v.begin(), v.end());
+    const int n = (int)v.size();
+    int idx = (int)std::ceil(p * n) - 1;
+    idx = std::min(std::max(idx, 0), n - 1);
+    return v[(size_t)idx];
+  }
+  CounterSnapshot Snapshot() { std::lock_guard<std::mutex> lk(mu_); CounterSnapshot s{count_, total_, max_, errors_}; max_ = 0; return s; }
+  CounterPeek Peek() const {
+    CounterPeek p;
+    { std::lock_guard<std::mutex> lk(mu_); p.InvokeCount = count_; p.InvokeTotalUs = total_; p.InvokeMaxUsLifetime = maxLife_; p.InvokeErrors = errors_; p.BatchWindows = windows_; }
+    p.RecentP95Us = RecentPercentileUs(healthLatencyPercentile);
+    return p;
+  }
+ private:
+  mutable std::mutex mu_;
+  long long count_ = 0, total_ = 0, max_ = 0, maxLife_ = 0, errors_ = 0, windows_ = 0;
+  long long ring_[latencyWindowSize] = {0};
+  int pos_ = 0, len_ = 0;
+};
+inline std::string SanitizeModelID(const std::string& id) {            // counters.go:123-130
+  std::string o = id;
+  for (char& c : o) if (!((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_')) c = '_';
+  return o;
+}
+inline std::string MetricKey(const std::string& id) { return "inference." + SanitizeModelID(id) + ".avg_ms"; }
+class CounterMap {
+ public:
+  void RecordInvoke(const std::string& id, long long us, long long windows = 1) { get(id).RecordInvoke(us, windows); }
+  void RecordError(const std::string& id) { get(id).RecordError(); }
+  std::map<std::string, CounterSnapshot> SnapshotAll() { std::map<std::string, CounterSnapshot> r; std::lock_guard<std::mutex> lk(mu_); for (auto& kv : m_) r[kv.first] = kv.second->Snapshot(); return r; }
+  std::map<std::string, CounterPeek> PeekAll() { std::map<std::string, CounterPeek> r; std::lock_guard<std::mutex> lk(mu_); for (auto& kv : m_) r[kv.first] = kv.second->Peek(); return r; }
+  void Delete(const std::string& id) { std::lock_guard<std::mutex> lk(mu_); m_.erase(id); }
+ private:
+  Counters& get(const std::string& id) { std::lock_guard<std::mutex> lk(mu_); auto& p = m_[id]; if (!p) p.reset(new Counters()); return *p; }
+  std::mutex mu_;
+  std::map<std::string, std::unique_ptr<Counters>> m_;
+};
+
+// Orchestrator.PredictModel (internal/classifier/orchestrator.go:507-572): a lock on the models map to fetch the entry, then the
+// global inferenceMu (one model runs at a time), then the entry's own mutex (instance lifecycle), counters on the way out.
+// PredictModelBatch is the additive batched form: one pass through the same locks for a whole batch of windows.
+class ModelInstance {
+ public:
+  virtual ~ModelInstance() = default;
+  virtual std::vector<Result> Predict(const std::vector<std::vector<float>>& sample) = 0;
+  virtual std::vector<std::vector<Result>> PredictBatch(const std::vector<std::vector<float>>& windows) {
+    std::vector<std::vector<Result>> out;
+    for (const auto& w : windows) out.push_back(Predict({w}));
+    return out;
+  }
+  virtual void Close() {}
+};
+class Orchestrator {
+ public:
+  void Register(const std::string& id, std::shared_ptr<ModelInstance> inst) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto e = std::make_shared<Entry>(); e->instance = std::move(inst); models_[id] = e;
+    if (primary_.empty()) primary_ = id;
+  }
+  void CloseModel(const std::string& id) {
+    std::shared_ptr<Entry> e = find(id);
+    if (!e) return;
+    std::shared_ptr<ModelInstance> inst;
+    { std::lock_guard<std::mutex> lk(e->mu); inst.swap(e->instance); }
+    if (inst) inst->Close();
+  }
+  void DeleteModel(const std::string& id) { CloseModel(id); { std::lock_guard<std::mutex> lk(mu_); models_.erase(id); } counters.Delete(id); }
+  std::vector<Result> Predict(const std::vector<std::vector<float>>& sample) { std::string id; { std::lock_guard<std::mutex> lk(mu_); id = primary_; } return PredictModel(id, sample); }
+  std::vector<Result> PredictModel(const std::string& id, const std::vector<std::vector<float>>& sample) {
+    std::vector<Result> out;
+    run(id, 1, [&](ModelInstance& m) { out = m.Predict(sample); });
+    return out;
+  }
+  std::vector<std::vector<Result>> PredictModelBatch(const std::string& id, const std::vector<std::vector<float>>& windows) {
+    std::vector<std::vector<Result>> out;
+    run(id, (long long)windows.size(), [&](ModelInstance& m) { out = m.PredictBatch(windows); });
+    return out;
+  }
+  CounterMap counters;
+
+ private:
+  struct Entry { std::mutex mu; std::shared_ptr<ModelInstance> instance; };
+  std::shared_ptr<Entry> find(const std::string& id) { std::lock_guard<std::mutex> lk(mu_); auto it = models_.find(id); return it == models_.end() ? nullptr : it->second; }
+  template <class F>
+  void run(const std::string& id, long long windows, F&& call) {
+    std::shared_ptr<Entry> e = find(id);                               // map lock released before the inference / model locks
+    if (!e) throw std::invalid_argument("unknown model: " + id);
+    std::lock_guard<std::mutex> inf(inferenceMu_);
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->instance) throw std::runtime_error("model " + id + " has been closed");
+    const auto t0 = std::chrono::steady_clock::now();
+    try { call(*e->instance); }
+    catch (...) { counters.RecordError(id); throw; }
+    counters.RecordInvoke(id, std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count(), windows);
+  }
+  std::mutex mu_, inferenceMu_;
+  std::map<std::string, std::shared_ptr<Entry>> models_;
+  std::string primary_;
 };
 
 // Tumbling-window overrun accounting per (source, model): process.go:44-215.  `now` is a monotonic clock in seconds supplied by

@@ -76,6 +76,55 @@ static void test_postprocessing() {
   CHECK(f.size() == 5 && f[0] == 0.f && f[1] == 1.f / 32768.f && f[2] == -1.f / 32768.f && f[3] == 32767.f / 32768.f && f[4] == -1.f);
 }
 
+// inferencestats counters + Orchestrator.PredictModel / PredictModelBatch (counters_test.go cases, orchestrator.go:507-572)
+struct FakeModel : ModelInstance {
+  bool fail = false, closed = false; int calls = 0, batchCalls = 0;
+  std::vector<Result> Predict(const std::vector<std::vector<float>>& sample) override {
+    ++calls; if (fail) throw std::runtime_error("backend failed");
+    Result r; r.Species = "species"; r.Confidence = (float)sample[0].size(); return {r};
+  }
+  std::vector<std::vector<Result>> PredictBatch(const std::vector<std::vector<float>>& w) override { ++batchCalls; return ModelInstance::PredictBatch(w); }
+  void Close() override { closed = true; }
+};
+static void test_counters_and_orchestrator() {
+  Counters c;
+  c.RecordInvoke(100); c.RecordInvoke(300); c.RecordInvoke(200); c.RecordError();
+  CounterSnapshot s = c.Snapshot();
+  CHECK(s.InvokeCount == 3 && s.InvokeTotalUs == 600 && s.InvokeMaxUs == 300 && s.InvokeErrors == 1);
+  CHECK(c.Snapshot().InvokeMaxUs == 0 && c.Peek().InvokeMaxUsLifetime == 300);           // interval max reset, lifetime max kept
+  struct { std::vector<long long> v; double p; long long want; } cases[] = {{{}, 0.95, 0}, {{42}, 0.95, 42}, {{10, 20, 30, 40, 50, 60, 70}, 0.95, 70},
+                                                                            {{1, 2, 3, 4}, 1.0, 4}, {{10, 20, 30, 40, 50}, 0.5, 30}, {{5, 6, 7}, 0.0, 5}};
+  for (auto& t : cases) { Counters k; for (long long x : t.v) k.RecordInvoke(x); CHECK(k.RecentPercentileUs(t.p) == t.want); }
+  Counters ring;
+  for (int i = 0; i < 1024; ++i) ring.RecordInvoke(9000);
+  for (int i = 0; i < 1024; ++i) ring.RecordInvoke(10);
+  CHECK(ring.RecentPercentileUs(0.95) == 10);                                              // old samples evicted from the 1024 ring
+  CHECK(SanitizeModelID("BirdNET_V2.4-fp32") == "BirdNET_V2_4_fp32" && MetricKey("a.b") == "inference.a_b.avg_ms");
+
+  Orchestrator o;
+  auto good = std::make_shared<FakeModel>(); auto bad = std::make_shared<FakeModel>(); bad->fail = true;
+  o.Register("birdnet", good); o.Register("bad", bad);
+  CHECK(o.Predict({std::vector<float>(5, 0.f)})[0].Confidence == 5.f);                     // Predict = PredictModel(primary)
+  bool threw = false;
+  try { o.PredictModel("nope", {{0.f}}); } catch (const std::invalid_argument& e) { threw = std::string(e.what()) == "unknown model: nope"; }
+  CHECK(threw);
+  threw = false;
+  try { o.PredictModel("bad", {{0.f}}); } catch (const std::runtime_error&) { threw = true; }
+  CHECK(threw);
+  auto out = o.PredictModelBatch("birdnet", std::vector<std::vector<float>>(7, std::vector<float>(3, 0.f)));
+  CHECK(out.size() == 7 && good->batchCalls == 1);
+  auto peek = o.counters.PeekAll();
+  CHECK(peek["birdnet"].InvokeCount == 2 && peek["birdnet"].BatchWindows == 8);            // one invoke for the whole batch
+  CHECK(peek["bad"].InvokeErrors == 1 && peek["bad"].InvokeCount == 0);
+  o.CloseModel("birdnet");
+  CHECK(good->closed);
+  threw = false;
+  try { o.PredictModel("birdnet", {{0.f}}); } catch (const std::runtime_error& e) { threw = std::string(e.what()) == "model birdnet has been closed"; }
+  CHECK(threw);
+  o.DeleteModel("birdnet");
+  CHECK(o.counters.PeekAll().count("birdnet") == 0);
+}
+
 static void test_overrun_tracker() {
   OverrunTrackers tr;
   OverrunReport rep;
@@ -147,6 +196,7 @@ int main(int argc, char** argv) {
     test_analysis_buffer();
     test_postprocessing();
     test_overrun_tracker();
+    test_counters_and_orchestrator();
     std::printf(g_fail ? "FAILED %d\n" : "OK\n", g_fail);
     return g_fail ? 1 : 0;
   } catch (const std::exception& e) { std::printf("EXCEPTION %s\n", e.what()); return 2; }
